@@ -1,0 +1,154 @@
+/*
+ * lego_klt.h -- C ABI of the B200-native pyramid Gauss-Newton KLT tracker.
+ *
+ * This is the drop-in boundary for ONE hot path of LEGO-SLAM (reference paths are relative to the
+ * upstream tree):
+ *
+ *   legoslam::LKOpticalFlow1Layer   include/legoslam/algorithm.h:123-128, src/algorithm.cpp:11-31
+ *   legoslam::LKOpticalFlow4Layer   include/legoslam/algorithm.h:131-136, src/algorithm.cpp:128-206
+ *   LKOpticalFlowTracker::calcLKOpticalFlow            src/algorithm.cpp:37-125   (the per-feature solver)
+ *   GetPixelValue / IsPtInImg       include/legoslam/algorithm.h:40-66           (sampler / in-image test)
+ *
+ * called from Frontend::TrackLastFrameLKOpticalFlow4LayerSelf (src/frontend_g2o.cpp:473) and
+ * Frontend::FindFeaturesInRightLKOpticalFlow4LayerSelf (src/frontend_g2o.cpp:515).
+ *
+ * Everything here is plain C: pointers, sizes, PODs.  No torch / OpenCV / Eigen types.  The C++
+ * shim that keeps the reference's own signatures lives in include/legoslam_gpu/algorithm_shim.h.
+ *
+ * There is NO CPU fallback behind these entry points: every compute call runs hand-written sm_100a
+ * CUDA kernels and returns a negative error code if no CUDA device / kernel image is available.
+ */
+#ifndef LEGO_KLT_H
+#define LEGO_KLT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEGO_KLT_ABI_VERSION 1
+#define LEGO_KLT_MAX_LEVELS 8
+
+/* ---- error codes (reference returns void and has no status; see SURVEY.md 8b "Errors") ---- */
+enum {
+    LEGO_KLT_OK = 0,
+    LEGO_KLT_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, levels out of range ...   */
+    LEGO_KLT_ERR_CUDA = -2,         /* a CUDA runtime call failed; see lego_klt_last_error()       */
+    LEGO_KLT_ERR_NO_DEVICE = -3,    /* no CUDA device: the product path never falls back to CPU    */
+    LEGO_KLT_ERR_UNSUPPORTED = -4,  /* e.g. pyramid level would be empty, patch too large          */
+    LEGO_KLT_ERR_STATE = -5         /* batch object used out of order (run before upload ...)      */
+};
+
+/* ---- solver kernel selection ---- */
+enum {
+    LEGO_KLT_KERNEL_AUTO = 0,   /* fastest parity-green kernel (currently WARP)                    */
+    LEGO_KLT_KERNEL_EXACT = 1,  /* one thread per feature, reference operation order, flat global
+                                   addressing: bit-identical to the CPU oracle; the on-GPU checker  */
+    LEGO_KLT_KERNEL_WARP = 2,   /* one warp per feature, windows staged in shared memory, fp64
+                                   warp-shuffle reductions, all levels fused in-kernel             */
+    LEGO_KLT_KERNEL_LANE = 3    /* one thread per feature, persistent iteration state machine,
+                                   shared sample grid                              */
+};
+
+/*
+ * Tracker parameters.  Defaults (lego_klt_default_params) are the reference's compile-time
+ * literals: src/algorithm.cpp:40-42 (half_patch_size 3, half_grad_step 1, iterations 10),
+ * :113 (1e-2), :135-137 (4 levels, scale 0.5); call sites pass inverse=false, has_initial=true
+ * (src/frontend_g2o.cpp:473,515).
+ */
+typedef struct lego_klt_params {
+    int32_t levels;       /* pyramid levels L (1 == LKOpticalFlow1Layer, 4 == LKOpticalFlow4Layer) */
+    int32_t patch_lo;     /* patch offsets x,y run patch_lo..patch_hi inclusive; reference: -3     */
+    int32_t patch_hi;     /* reference: +3  (7x7).  8x8 = (-4,3);  11x11 = (-5,5)                  */
+    int32_t max_iters;    /* Gauss-Newton iterations per level; reference: 10                      */
+    int32_t inverse;      /* 0 = forward-additive; 1 = the reference's inverse mode INCLUDING its
+                             stale-Jacobian behaviour (src/algorithm.cpp:57,74-80,83)              */
+    int32_t has_initial;  /* use kp2 as the initial guess on the coarsest level                    */
+    int32_t kernel;       /* LEGO_KLT_KERNEL_*                                                     */
+    int32_t reserved;
+    double eps;           /* convergence: stop when |update| < eps; reference: 1e-2                */
+} lego_klt_params;
+
+/* Per-call counters (SURVEY.md 5 "Metrics", 8d: iteration counts drive the roofline accounting). */
+typedef struct lego_klt_stats {
+    uint64_t n_features;
+    uint64_t n_success;                          /* final flags set                                */
+    uint64_t n_nan;                              /* solves that returned NaN/Inf (algorithm.cpp:94) */
+    uint64_t n_out_of_image;                     /* final level: result outside img2 (:123)        */
+    uint64_t gn_iters[LEGO_KLT_MAX_LEVELS];      /* patch passes executed per level, level 0 = fine */
+    uint64_t n_slow_path;                        /* feature-levels solved on the exact border path */
+    float ms_h2d, ms_pyramid, ms_solver, ms_d2h; /* device times (CUDA events) of the last call    */
+} lego_klt_stats;
+
+typedef struct lego_klt_ctx lego_klt_ctx;       /* one per (calling thread, device)               */
+typedef struct lego_klt_batch lego_klt_batch;   /* device-resident batch of B image pairs         */
+
+int lego_klt_abi_version(void);
+const char *lego_klt_last_error(void);           /* thread-local message of the last failure       */
+void lego_klt_default_params(lego_klt_params *p);
+int lego_klt_device_count(void);                 /* >=0, or LEGO_KLT_ERR_NO_DEVICE                 */
+
+/* Context: owns a stream, scratch device buffers and pinned staging buffers on `device`. */
+int lego_klt_create(int device, lego_klt_ctx **out);
+void lego_klt_destroy(lego_klt_ctx *ctx);
+/* Launch on a caller-owned stream (cudaStream_t passed as void*); NULL restores the context's own. */
+int lego_klt_set_stream(lego_klt_ctx *ctx, void *cuda_stream);
+
+/*
+ * Replaces LKOpticalFlow4Layer / LKOpticalFlow1Layer (levels = 4 / 1).  Synchronous: returns after
+ * results are in the caller's buffers.
+ *   img1,img2 : 8-bit single channel, `rows` x `cols`, `step` bytes per row  (cv::Mat data/cols/rows/step)
+ *   kp1_xy    : n x {x,y} float  (cv::KeyPoint::pt of kp1)
+ *   kp2_xy    : n x {x,y} float, in: initial guesses (read when has_initial), out: tracked points
+ *   success   : n bytes out, 0/1   (std::vector<bool> success)
+ */
+int lego_klt_track(lego_klt_ctx *ctx, const lego_klt_params *params,
+                   const uint8_t *img1, const uint8_t *img2, int cols, int rows, size_t step,
+                   const float *kp1_xy, float *kp2_xy, uint8_t *success, int n,
+                   lego_klt_stats *stats_or_null);
+
+/*
+ * The pyramid part of LKOpticalFlow4Layer alone (src/algorithm.cpp:140-154): builds levels
+ * 1..levels-1 of `img` on the GPU and copies them, tightly packed (step == cols) and concatenated
+ * level 1 first, to `out`.  level_cols/level_rows (length `levels`) receive all level sizes.
+ */
+int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step,
+                           int levels, uint8_t *out, size_t out_capacity,
+                           int *level_cols, int *level_rows);
+
+/*
+ * Batched path (north star (3)): B independent image pairs of one shape, n features per pair.
+ * Host buffers should come from lego_klt_alloc_pinned for asynchronous copies.
+ *   imgs1, imgs2 : B images, image b at  base + b * rows * step
+ *   kp1_xy, kp2_xy : B*n x {x,y};  success : B*n bytes
+ */
+int lego_klt_batch_create(lego_klt_ctx *ctx, int batch, int cols, int rows, size_t step,
+                          int n_per_pair, int levels, lego_klt_batch **out);
+void lego_klt_batch_destroy(lego_klt_batch *b);
+/* H2D of images and keypoints (asynchronous on the context stream). */
+int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t *imgs2,
+                          const float *kp1_xy, const float *kp2_xy);
+/* Pyramids + solver on whatever is resident; inputs are preserved, so it can be re-run. */
+int lego_klt_batch_run(lego_klt_batch *b, const lego_klt_params *params);
+/* D2H of results; synchronises the stream. */
+int lego_klt_batch_download(lego_klt_batch *b, float *kp2_xy, uint8_t *success,
+                            lego_klt_stats *stats_or_null);
+/* upload + run + download in one call (the end-to-end path bench.py times as `e2e`). */
+int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params,
+                           const uint8_t *imgs1, const uint8_t *imgs2,
+                           const float *kp1_xy, float *kp2_xy, uint8_t *success,
+                           lego_klt_stats *stats_or_null);
+/* Device pointers of the resident buffers (for callers that already hold data in HBM). */
+int lego_klt_batch_device_ptrs(lego_klt_batch *b, void **imgs1, void **imgs2,
+                               void **kp1_xy, void **kp2_xy_init, void **kp2_xy_out, void **success);
+int lego_klt_sync(lego_klt_ctx *ctx);
+
+void *lego_klt_alloc_pinned(size_t bytes);
+void lego_klt_free_pinned(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEGO_KLT_H */
