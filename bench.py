@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- KLT feature-tracks/s of the B200-native pyramid Gauss-Newton KLT path.
+
+Metric (BASELINE.json): KLT feature-tracks/sec, 4-level pyramid, at 1/2/4/8 B200, with the CPU
+ParallelLoopBody-style path timed beside it, and pyramid GB/s.
+
+Workload (config C3, the batched multi-GPU one the metric is quoted on): per GPU, B=256 independent
+synthetic KITTI-shaped stereo pairs 1241x376 x 2000 features, 4 levels, the reference's 7x7 patch
+(src/algorithm.cpp:40: half_patch_size=3 -- SURVEY.md F1; "8x8" in the metric text is not what the
+reference computes), forward mode, initial guess kp2 = kp1.  A step = pyramids of all 512 images +
+the fused 4-level solver over 512,000 features.  Weak scaling: every rank owns its own 256 pairs, no
+data-path collective, final gather of (x,y,flag) outside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ROWS, COLS, LEVELS = 376, 1241, 4
+PATCH_LO, PATCH_HI = -3, 3
+FLOP_PER_PIXEL_ITER = 123          # SURVEY.md 8d, reference formulation, forward mode
+PYR_BYTES_PER_IMAGE = 619_601      # level 0 read once + levels 1..3 written once
+METRIC = "KLT feature-tracks/sec (4-level pyramid, 1241x376, 2000 features/pair, batched pairs)"
+
+
+def _make_pair(args):
+    seed, n = args
+    from lego_slam_b200 import synth
+    L, R, kp1, kp2, _ = synth.stereo_case(ROWS, COLS, n, seed=seed)
+    return L, R, kp1, kp2
+
+
+def make_workload(n_pairs: int, n_feat: int, distinct: int, seed0: int):
+    """`distinct` generated pairs (seeds seed0..), tiled cyclically to n_pairs; odd repeats are
+    vertically flipped so that repeated slots are not byte-identical."""
+    distinct = max(1, min(distinct, n_pairs))
+    jobs = [(seed0 + i, n_feat) for i in range(distinct)]
+    workers = min(len(jobs), max(1, (os.cpu_count() or 2) // 2), 32)
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            base = pool.map(_make_pair, jobs)
+    else:
+        base = [_make_pair(j) for j in jobs]
+    return base
+
+
+def fill_batch(base, n_pairs, n_feat, alloc):
+    imgs1 = alloc((n_pairs, ROWS, COLS), np.uint8)
+    imgs2 = alloc((n_pairs, ROWS, COLS), np.uint8)
+    kp1 = alloc((n_pairs, n_feat, 2), np.float32)
+    kp2 = alloc((n_pairs, n_feat, 2), np.float32)
+    for b in range(n_pairs):
+        L, R, a, g = base[b % len(base)]
+        if (b // len(base)) % 2 == 1:  # vertical flip: still a valid stereo pair
+            imgs1[b], imgs2[b] = L[::-1], R[::-1]
+            f = a.copy()
+            f[:, 1] = (ROWS - 1) - f[:, 1]
+            kp1[b] = f
+            kp2[b] = f
+        else:
+            imgs1[b], imgs2[b], kp1[b], kp2[b] = L, R, a, g
+    return imgs1, imgs2, kp1, kp2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_throughput(base, n_feat, budget_s: float, threads: int):
+    """The reference's CPU path (oracle port: pyramids + 4 levels, src/algorithm.cpp:128-206) on the host
+    cores: pairs run concurrently on `threads` worker threads (ctypes releases the GIL), one
+    single-threaded LKOpticalFlow4Layer-equivalent per pair."""
+    from oracle import binding as ob
+    p = ob.make_params(levels=LEVELS, patch_lo=PATCH_LO, patch_hi=PATCH_HI)
+    t0 = time.perf_counter()
+    ob.track(base[0][0], base[0][1], base[0][2], base[0][3], p, threads=1)
+    t1 = time.perf_counter() - t0
+    n_pairs = int(max(threads, min(4096, budget_s * threads / max(t1, 1e-4))))
+    n_pairs = (n_pairs + threads - 1) // threads * threads
+
+    def one(i):
+        L, R, a, g = base[i % len(base)]
+        ob.track(L, R, a, g, p, threads=1)
+
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(one, range(n_pairs)))
+        dt = time.perf_counter() - t0
+    return n_pairs * n_feat / dt, n_pairs, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Its translation unit
+    cannot be built offline (needs OpenCV/Eigen/Sophus/glog), so this is the oracle PORT, compiled
+    with the reference's flags, on all host threads; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    base = make_workload(args.pairs, args.features, min(args.distinct, 16), 1000)
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals, sample = [], None
+    for s in range(args.warmup + args.steps):
+        v, n_pairs, dt = cpu_oracle_throughput(base, args.features, per_step_budget, threads)
+        if s >= args.warmup:
+            vals.append((v, dt))
+        sample = f"{n_pairs} pairs x {args.features} features per step ({dt:.1f} s), full pyramids + 4 levels"
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 sampling + f64 normal equations",
+        "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "tracks/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tracks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"C3: {args.pairs} independent stereo pairs {COLS}x{ROWS} u8 per GPU x {args.features} "
+                        f"features, {LEVELS}-level pyramid, 7x7 patch (reference half_patch_size=3), forward, kp2=kp1",
+            "pairs_per_gpu": args.pairs, "features_per_pair": args.features, "levels": LEVELS,
+            "patch": [PATCH_LO, PATCH_HI], "distinct_pairs": min(args.distinct, args.pairs),
+            "l2_policy": "inputs larger than L2 (level-0 images of one step: %.0f MB > 126 MB)"
+                         % (2 * args.pairs * ROWS * COLS / 1e6),
+            "sharding": "block partition of pairs, one process per GPU, no data-path collective"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lego_slam_b200 as klt
+    from lego_slam_b200 import build, sharding
+    build.build()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the KLT path has no CPU fallback (use --impl reference "
+                         "for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    B, n = args.pairs, args.features
+    base = make_workload(B, n, args.distinct, 1000 + rank * B)
+    trk = klt.Tracker(local)
+    stream = torch.cuda.Stream(device=local)
+    trk.set_stream(stream.cuda_stream)
+    imgs1, imgs2, kp1, kp2 = fill_batch(base, B, n, klt.pinned_empty)
+    kp2_io = klt.pinned_empty((B, n, 2), np.float32)
+    succ = klt.pinned_empty((B, n), np.uint8)
+    batch = trk.batch(B, ROWS, COLS, n, levels=LEVELS)
+    params = klt.make_params(levels=LEVELS, patch_lo=PATCH_LO, patch_hi=PATCH_HI, kernel=args.kernel)
+    n_tracks = B * n
+
+    # ---------------- device-resident: inputs already in HBM, results stay in HBM ----------------
+    batch.upload(imgs1, imgs2, kp1, kp2)
+    for _ in range(args.warmup):
+        batch.run(params)
+    trk.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        batch.run(params)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-kernel launch durations (CUDA events on the launching stream, recorded inside the library
+    # around each kernel), averaged over the same number of steps
+    ms_pyr, ms_sol, iters = [], [], None
+    for _ in range(args.steps):
+        batch.run(params)
+        _, _, st = batch.download(kp2_io, succ)
+        ms_pyr.append(st.ms_pyramid)
+        ms_sol.append(st.ms_solver)
+        iters = [int(v) for v in st.gn_iters][:LEVELS]
+        slow = int(st.n_slow_path)
+        n_success = int(st.n_success)
+    ms_pyr, ms_sol = float(np.mean(ms_pyr)), float(np.mean(ms_sol))
+
+    # ---------------- end to end: host buffers -> lego_klt_track_batched -> host buffers ----------------
+    for _ in range(min(args.warmup, 3)):
+        np.copyto(kp2_io, kp2)
+        batch.track(imgs1, imgs2, kp1, kp2_io, succ, params)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        np.copyto(kp2_io, kp2)
+        batch.track(imgs1, imgs2, kp1, kp2_io, succ, params)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # max over ranks of the timed regions
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    # final gather (outside the timed regions): the only exchange of the sharded path
+    if world > 1:
+        kp_full, su_full = sharding.gather_results(torch.from_numpy(kp2_io).cuda(), torch.from_numpy(succ).cuda(),
+                                                   B * world)
+        assert kp_full.shape[0] == B * world and su_full.shape[0] == B * world
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    props = torch.cuda.get_device_properties(local)
+    sm_count = props.multi_processor_count
+    sm_max_mhz = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    fp32_peak_tflops = sm_count * 128 * sm_max_mhz * 1e6 / 1e12   # un-fused fp32 lane-ops/s
+    P = (PATCH_HI - PATCH_LO + 1) ** 2
+    algo_flop = sum(iters) * P * FLOP_PER_PIXEL_ITER
+    achieved_tflops = algo_flop / (ms_sol * 1e-3) / 1e12
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    pyr_bytes = 2 * B * PYR_BYTES_PER_IMAGE
+    pyr_gbs = pyr_bytes / (ms_pyr * 1e-3) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, n_pairs, dt = cpu_oracle_throughput(base, n, args.cpu_budget, threads)
+        cpu = {"value": v, "unit": "tracks/s", "cores": threads, "kind": "port",
+               "sample": f"{n_pairs} pairs x {n} features of the same workload ({dt:.1f} s wall), full pyramids + "
+                         f"{LEVELS} levels, oracle built -std=c++11 -O3 (reference flags), one pair per thread"}
+
+    value = world * n_tracks * args.steps / (ms_total * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 sampling + f64 normal equations", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": world * n_tracks * args.steps / (e2e_ms * 1e-3), "unit": "tracks/s",
+                "h2d_bytes_per_step": int(imgs1.nbytes + imgs2.nbytes + kp1.nbytes + kp2.nbytes),
+                "d2h_bytes_per_step": int(kp2_io.nbytes + succ.nbytes + 12 * 8),
+                "ms_per_step": e2e_ms / args.steps, "api": "lego_klt_track_batched (pinned host buffers)"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"kernel": "klt_warp_kernel (fused 4-level GN solver)", "bound": "fp32-issue (non-tensor)",
+                     "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                     "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
+                     "peak_source": f"computed: {sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz un-fused fp32 "
+                                    "(not in MEASURED_PEAKS.json, which has only HBM and bf16 tensor peaks)",
+                     "algorithmic_flop_per_launch": algo_flop, "gn_iters_per_level": iters,
+                     "ms_per_launch": ms_sol, "share_of_step": ms_sol / (ms_sol + ms_pyr)},
+        "roofline_pyramid": {"kernel": "pyramid_fused_kernel", "bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": pyr_gbs / hbm_peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                             "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": ms_pyr},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "solver": {"n_success": n_success, "n_slow_path_passes": slow, "kernel": int(args.kernel)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=256, help="stereo pairs per GPU")
+    ap.add_argument("--features", type=int, default=2000)
+    ap.add_argument("--distinct", type=int, default=64, help="distinct generated pairs (tiled to --pairs)")
+    ap.add_argument("--kernel", type=int, default=0, help="LEGO_KLT_KERNEL_* (0 = auto)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's entry points on top of the C ABI (include/lego_klt.h).
+
+Names, argument meaning and flag semantics follow /root/reference include/legoslam/algorithm.h:123-136:
+    LKOpticalFlow1Layer(img1, img2, kp1, kp2, success, inverse=false, has_initial=true)
+    LKOpticalFlow4Layer(img1, img2, kp1, kp2, success, inverse=false, has_initial=true)
+Python returns (kp2, success) instead of filling reference arguments; images are uint8 numpy arrays
+(cv::Mat data/cols/rows/step), keypoints are float32 (n, 2) arrays of cv::KeyPoint::pt.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import KERNEL_AUTO, KERNEL_EXACT, KERNEL_LANE, KERNEL_WARP, Params, Stats  # noqa: F401
+
+
+def make_params(levels=4, patch_lo=-3, patch_hi=3, max_iters=10, inverse=False, has_initial=True,
+                kernel=KERNEL_AUTO, eps=1e-2) -> Params:
+    """Defaults are the reference's literals (src/algorithm.cpp:40-42,113,135)."""
+    return Params(levels, patch_lo, patch_hi, max_iters, int(inverse), int(has_initial), kernel, 0, eps)
+
+
+def _img_args(img: np.ndarray):
+    if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
+        raise ValueError("image must be a 2-D uint8 array with unit column stride")
+    return img.shape[0], img.shape[1], img.strides[0]
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory (lego_klt_alloc_pinned), freed with the array."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.lego_klt_alloc_pinned(max(nbytes, 1))
+    if not ptr:
+        raise MemoryError(f"lego_klt_alloc_pinned({nbytes}) failed")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.lego_klt_free_pinned, ptr)
+    return arr
+
+
+class Tracker:
+    """One lego_klt_ctx: a device, a stream, cached single-pair buffers."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.lego_klt_create(device, C.byref(h)), "lego_klt_create")
+        self._h = h
+        self.device = device
+        self._fin = weakref.finalize(self, self._lib.lego_klt_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def set_stream(self, cuda_stream_handle: int | None):
+        _lib.check(self._lib.lego_klt_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)),
+                   "lego_klt_set_stream")
+
+    def sync(self):
+        _lib.check(self._lib.lego_klt_sync(self._h), "lego_klt_sync")
+
+    def track(self, img1, img2, kp1, kp2, params: Params | None = None):
+        """lego_klt_track: returns (kp2_out float32 (n,2), success uint8 (n,), Stats)."""
+        params = params or make_params()
+        rows, cols, step = _img_args(img1)
+        if _img_args(img2) != (rows, cols, step):
+            raise ValueError("img1 and img2 must have the same shape and step")
+        kp1 = np.ascontiguousarray(kp1, np.float32).reshape(-1, 2)
+        out = np.ascontiguousarray(kp2, np.float32).reshape(-1, 2).copy()
+        n = kp1.shape[0]
+        if out.shape[0] != n:
+            raise ValueError("kp1 and kp2 must have the same length")
+        succ = np.zeros(max(n, 1), np.uint8)
+        st = Stats()
+        _lib.check(self._lib.lego_klt_track(self._h, C.byref(params), img1.ctypes.data, img2.ctypes.data,
+                                            cols, rows, step, kp1.ctypes.data, out.ctypes.data,
+                                            succ.ctypes.data, n, C.byref(st)), "lego_klt_track")
+        return out, succ[:n], st
+
+    def LKOpticalFlow4Layer(self, img1, img2, kp1, kp2, inverse=False, has_initial=True, kernel=KERNEL_AUTO):
+        out, succ, _ = self.track(img1, img2, kp1, kp2, make_params(4, inverse=inverse,
+                                                                    has_initial=has_initial, kernel=kernel))
+        return out, succ.astype(bool)
+
+    def LKOpticalFlow1Layer(self, img1, img2, kp1, kp2, inverse=False, has_initial=True, kernel=KERNEL_AUTO):
+        out, succ, _ = self.track(img1, img2, kp1, kp2, make_params(1, inverse=inverse,
+                                                                    has_initial=has_initial, kernel=kernel))
+        return out, succ.astype(bool)
+
+    def build_pyramid(self, img: np.ndarray, levels: int = 4):
+        """The pyramid part of LKOpticalFlow4Layer (src/algorithm.cpp:140-154) on the GPU."""
+        rows, cols, step = _img_args(img)
+        cap = rows * cols
+        out = np.zeros(cap, np.uint8)
+        lc = (C.c_int * levels)()
+        lr = (C.c_int * levels)()
+        _lib.check(self._lib.lego_klt_build_pyramid(self._h, img.ctypes.data, cols, rows, step, levels,
+                                                    out.ctypes.data, cap, lc, lr), "lego_klt_build_pyramid")
+        res, off = [img], 0
+        for l in range(1, levels):
+            nb = lc[l] * lr[l]
+            res.append(out[off:off + nb].reshape(lr[l], lc[l]).copy())
+            off += nb
+        return res
+
+    def batch(self, batch: int, rows: int, cols: int, n_per_pair: int, levels: int = 4, step: int | None = None):
+        return Batch(self, batch, rows, cols, n_per_pair, levels, step)
+
+
+class Batch:
+    """Device-resident batch of B independent image pairs (lego_klt_batch)."""
+
+    def __init__(self, tracker: Tracker, batch: int, rows: int, cols: int, n_per_pair: int, levels: int = 4,
+                 step: int | None = None):
+        self._lib = tracker._lib
+        self.tracker = tracker
+        self.B, self.rows, self.cols, self.n, self.levels = batch, rows, cols, n_per_pair, levels
+        self.step = step or cols
+        h = C.c_void_p()
+        _lib.check(self._lib.lego_klt_batch_create(tracker._h, batch, cols, rows, self.step, n_per_pair, levels,
+                                                   C.byref(h)), "lego_klt_batch_create")
+        self._h = h
+        self._fin = weakref.finalize(self, self._lib.lego_klt_batch_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def _check_inputs(self, imgs1, imgs2, kp1, kp2):
+        for a in (imgs1, imgs2):
+            if a.dtype != np.uint8 or not a.flags.c_contiguous or a.size != self.B * self.rows * self.step:
+                raise ValueError("images must be C-contiguous uint8 of B*rows*step bytes")
+        for a in (kp1, kp2):
+            if a.dtype != np.float32 or not a.flags.c_contiguous or a.size != self.B * self.n * 2:
+                raise ValueError("keypoints must be C-contiguous float32 of B*n*2 values")
+
+    def upload(self, imgs1, imgs2, kp1, kp2):
+        self._check_inputs(imgs1, imgs2, kp1, kp2)
+        _lib.check(self._lib.lego_klt_batch_upload(self._h, imgs1.ctypes.data, imgs2.ctypes.data,
+                                                   kp1.ctypes.data, kp2.ctypes.data), "lego_klt_batch_upload")
+
+    def run(self, params: Params | None = None):
+        params = params or make_params(self.levels)
+        _lib.check(self._lib.lego_klt_batch_run(self._h, C.byref(params)), "lego_klt_batch_run")
+
+    def download(self, kp2_out=None, success=None):
+        if kp2_out is None:
+            kp2_out = np.empty((self.B, self.n, 2), np.float32)
+        if success is None:
+            success = np.empty((self.B, self.n), np.uint8)
+        st = Stats()
+        _lib.check(self._lib.lego_klt_batch_download(self._h, kp2_out.ctypes.data, success.ctypes.data,
+                                                     C.byref(st)), "lego_klt_batch_download")
+        return kp2_out, success, st
+
+    def track(self, imgs1, imgs2, kp1, kp2_inout, success, params: Params | None = None):
+        """lego_klt_track_batched: H2D + pyramids + solver + D2H; kp2_inout is overwritten."""
+        self._check_inputs(imgs1, imgs2, kp1, kp2_inout)
+        params = params or make_params(self.levels)
+        st = Stats()
+        _lib.check(self._lib.lego_klt_track_batched(self._h, C.byref(params), imgs1.ctypes.data,
+                                                    imgs2.ctypes.data, kp1.ctypes.data, kp2_inout.ctypes.data,
+                                                    success.ctypes.data, C.byref(st)), "lego_klt_track_batched")
+        return st
+
+
+_default = {}
+
+
+def _default_tracker(device: int = 0) -> Tracker:
+    if device not in _default:
+        _default[device] = Tracker(device)
+    return _default[device]
+
+
+def LKOpticalFlow4Layer(img1, img2, kp1, kp2, inverse=False, has_initial=True, device=0):
+    """GPU replacement of legoslam::LKOpticalFlow4Layer; returns (kp2, success[bool])."""
+    return _default_tracker(device).LKOpticalFlow4Layer(img1, img2, kp1, kp2, inverse, has_initial)
+
+
+def LKOpticalFlow1Layer(img1, img2, kp1, kp2, inverse=False, has_initial=True, device=0):
+    """GPU replacement of legoslam::LKOpticalFlow1Layer; returns (kp2, success[bool])."""
+    return _default_tracker(device).LKOpticalFlow1Layer(img1, img2, kp1, kp2, inverse, has_initial)

@@ -1,0 +1,55 @@
+"""Builds lego_slam_b200/liblego_klt.so (hand-written sm_100a CUDA + the C ABI) in-tree with nvcc.
+
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container; the resulting .so
+travels to the GPU box with the repo snapshot (it is git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liblego_klt.so")
+SOURCES = ["lego_klt_capi.cu", "pyramid_sm100.cu", "klt_solver_exact.cu", "klt_solver_warp.cu",
+           "klt_solver_lane.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # parity: the reference CPU build has no fused multiply-add; fused ops are
+    # written explicitly as fma() only where the product is exact
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc() -> str:
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(HERE, "..", "include", "lego_klt.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode:
+        raise RuntimeError("nvcc failed building liblego_klt.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,151 @@
+// klt_common.cuh -- shared host/device declarations of the sm_100a KLT path.
+//
+// Reference text restated by the device functions here (paths relative to the upstream tree):
+//   include/legoslam/algorithm.h:40-57  GetPixelValue      -> sample_flat()
+//   include/legoslam/algorithm.h:60-66  IsPtInImg          -> point_in_image()
+//   src/algorithm.cpp:93                H.ldlt().solve(b)  -> ldlt2_solve()  (Eigen 3.3 LDLT.h, 2x2)
+//
+// Arithmetic contract: fp32 sampling with individually rounded mul/add (this TU is
+// compiled with -fmad=false; fused ops are written explicitly as fma() only where the product is
+// exact), fp64 for dx,dy,J,H,b,cost,update.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lego_klt.h"
+
+namespace legoklt {
+
+constexpr int kMaxLevels = LEGO_KLT_MAX_LEVELS;
+constexpr int kMaxPatch = 13;       // (patch_hi - patch_lo + 1) <= 13
+constexpr int kWinW = 32;           // TMA window box, bytes per row (multiple of 16)
+constexpr int kWinH = 24;           // TMA window box, rows
+
+// One pyramid level of a batch of images, device resident.
+//   pixel (img k, row r, col c) of set s lives at base[s] + k*slot + r*pitch + c
+// `step` is the LOGICAL row step the reference would see (level 0: the caller's cv::Mat::step,
+// levels >= 1: cols, because cv::resize outputs are continuous) -- the border path reproduces the
+// reference's flat addressing data[int(y)*step + int(x) (+1, +step, +step+1)] with it.
+struct LevelView {
+    uint8_t *base[2];
+    unsigned long long slot;  // bytes between consecutive images (multiple of 256)
+    int cols, rows;
+    int pitch;                // device bytes per row (multiple of 16, >= step for level 0)
+    int step;                 // logical step (see above)
+};
+
+struct PyramidView {
+    LevelView lv[kMaxLevels];
+    int levels;
+    int n_images;             // images per set (= batch size B)
+};
+
+// Device-side counters (one block of uint64 per batch).
+enum StatSlot {
+    kStatIters0 = 0,                       // + level
+    kStatNan = kMaxLevels,
+    kStatOutOfImage,
+    kStatSuccess,
+    kStatSlowPath,
+    kStatCount
+};
+
+struct SolverArgs {
+    const float2 *kp1;        // [B*n]
+    const float2 *kp2_init;   // [B*n]
+    float2 *kp2_out;          // [B*n]
+    uint8_t *success;         // [B*n]
+    unsigned long long *stats;  // [kStatCount]
+    int n_per_pair;
+    int n_total;
+    int patch_lo, patch_hi;
+    int max_iters;
+    int inverse;
+    int has_initial;
+    double eps;
+};
+
+#ifdef __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// Flat-addressed byte fetch with the reference's semantics on our pitched layout.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fetch_flat(const uint8_t *img, const LevelView &lv, long long f) {
+    int row = (int)(f / lv.step);
+    int col = (int)(f - (long long)row * lv.step);
+    if (row >= lv.rows) return 0.f;        // reference: out-of-buffer read; oracle: zero padding
+    return (float)__ldg(img + (size_t)row * lv.pitch + col);
+}
+
+// GetPixelValue -- algorithm.h:40-57.  Products and sums individually rounded, source order.
+__device__ __forceinline__ float sample_flat(const uint8_t *img, const LevelView &lv, float x, float y) {
+    if (x < 0.f) x = 0.f;
+    if (y < 0.f) y = 0.f;
+    if (x >= (float)lv.cols) x = (float)(lv.cols - 1);
+    if (y >= (float)lv.rows) y = (float)(lv.rows - 1);
+    int ix = (int)x, iy = (int)y;
+    float xx = x - floorf(x);
+    float yy = y - floorf(y);
+    float p0, p1, p2, p3;
+    if (ix + 1 < lv.cols && iy + 1 < lv.rows) {   // all four taps inside the image: plain 2-D fetch
+        const uint8_t *p = img + (size_t)iy * lv.pitch + ix;
+        p0 = (float)__ldg(p);
+        p1 = (float)__ldg(p + 1);
+        p2 = (float)__ldg(p + lv.pitch);
+        p3 = (float)__ldg(p + lv.pitch + 1);
+    } else {                                      // sliver / last row: the reference's flat addressing
+        long long f = (long long)iy * lv.step + ix;
+        p0 = fetch_flat(img, lv, f);
+        p1 = fetch_flat(img, lv, f + 1);
+        p2 = fetch_flat(img, lv, f + lv.step);
+        p3 = fetch_flat(img, lv, f + lv.step + 1);
+    }
+    float omx = 1.f - xx, omy = 1.f - yy;
+    float r = __fmul_rn(__fmul_rn(omx, omy), p0);
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(xx, omy), p1));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(omx, yy), p2));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(xx, yy), p3));
+    return r;
+}
+
+// IsPtInImg -- algorithm.h:60-66.
+__device__ __forceinline__ bool point_in_image(float px, float py, const LevelView &lv) {
+    double x = px, y = py;
+    return !(x < 0 || y < 0 || x >= lv.cols || y >= lv.rows);
+}
+
+// Eigen 3.3 LDLT<Matrix2d,Lower> compute()+solve() for 2x2 (third party, restated):
+// pivot on the larger |diagonal| (first on ties); all-zero diagonal stops the factorisation;
+// solve uses the pseudo-inverse of D with tol = 1/DBL_MAX.  No fused multiply-adds (the CPU
+// reference build has none).
+__device__ __forceinline__ void ldlt2_solve(double h00, double h10, double h11, double b0, double b1,
+                                            double &x0, double &x1) {
+    bool swapped = fabs(h11) > fabs(h00);
+    double a = swapped ? h11 : h00;
+    double d = swapped ? h00 : h11;
+    double l, d1;
+    if (a == 0.0) {
+        l = h10;
+        d1 = d;
+    } else {
+        l = __ddiv_rn(h10, a);
+        d1 = __dsub_rn(d, __dmul_rn(l, __dmul_rn(a, l)));
+    }
+    double y0 = swapped ? b1 : b0;
+    double y1 = swapped ? b0 : b1;
+    y1 = __dsub_rn(y1, __dmul_rn(l, y0));
+    const double tol = 1.0 / 1.7976931348623157e308;
+    y0 = (fabs(a) > tol) ? __ddiv_rn(y0, a) : 0.0;
+    y1 = (fabs(d1) > tol) ? __ddiv_rn(y1, d1) : 0.0;
+    y0 = __dsub_rn(y0, __dmul_rn(l, y1));
+    x0 = swapped ? y1 : y0;
+    x1 = swapped ? y0 : y1;
+}
+
+__device__ __forceinline__ bool not_finite(double v) { return isnan(v) || isinf(v); }
+
+#endif  // __CUDACC__
+
+}  // namespace legoklt

@@ -1,0 +1,47 @@
+// klt_kernels.h -- host-side launch interface of the sm_100a kernels (internal to the library).
+#pragma once
+
+#include "klt_common.cuh"
+
+namespace legoklt {
+
+// ---- pyramid (pyramid_sm100.cu) ---------------------------------------------------------------
+// Fixed-point resize tables of one level transition (l-1 -> l), restating OpenCV's
+// cv::resize INTER_LINEAR for CV_8UC1 (third party; reference call sites src/algorithm.cpp:147-150).
+struct ResizeTables {
+    int *xofs;      // [cols_l]  left tap in level l-1
+    short2 *xcoef;  // [cols_l]  {a0, a1}, 2^11 scale
+    int *yofs;      // [rows_l]  top tap
+    short2 *ycoef;  // [rows_l]
+    int x_exact2;   // xofs[c] == 2c and a0 == a1 == 1024 for every c
+};
+
+struct PyramidPlan {
+    int levels = 0;
+    int cols[kMaxLevels] = {0}, rows[kMaxLevels] = {0}, pitch[kMaxLevels] = {0};
+    ResizeTables tab[kMaxLevels] = {};  // tab[l] valid for l >= 1 (device pointers)
+    int top_rows_per_cta = 1;
+    int smem_off[kMaxLevels] = {0};     // byte offset of level l's staging rows in dynamic smem
+    int max_rows[kMaxLevels] = {0};     // max staged rows of level l over all CTAs
+    size_t smem_bytes = 0;
+    void *table_blob = nullptr;         // single device allocation behind all tables
+};
+
+// Level sizes of the reference's pyramid: cv::Size(cols*0.5, rows*0.5) repeatedly (truncation).
+// Returns false if a level would be empty.
+bool pyramid_level_sizes(int cols, int rows, int levels, int *lcols, int *lrows);
+cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan);
+void pyramid_plan_destroy(PyramidPlan *plan);
+// Builds levels 1..L-1 of both image sets (2 * n_images images) from level 0, one fused launch.
+cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, cudaStream_t stream);
+
+// ---- solver kernels ---------------------------------------------------------------------------
+cudaError_t launch_klt_exact(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
+
+struct WarpKernelMaps;  // TMA descriptors, defined in klt_solver_warp.cu
+cudaError_t warp_maps_create(const PyramidView &pyr, WarpKernelMaps **out);
+void warp_maps_destroy(WarpKernelMaps *maps);
+cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, const SolverArgs &args,
+                            int sm_count, cudaStream_t stream);
+
+}  // namespace legoklt

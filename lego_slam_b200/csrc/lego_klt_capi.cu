@@ -1,0 +1,504 @@
+// lego_klt_capi.cu -- the C ABI of include/lego_klt.h: contexts, device-resident batches, uploads,
+// kernel launches, downloads.  No CPU fallback exists behind any compute entry point.
+//
+// Reference boundary replaced: legoslam::LKOpticalFlow4Layer / LKOpticalFlow1Layer
+// (include/legoslam/algorithm.h:123-136), called at src/frontend_g2o.cpp:473 and :515.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "klt_kernels.h"
+
+using namespace legoklt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(LEGO_KLT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
+
+}  // namespace
+
+struct lego_klt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    lego_klt_batch *single = nullptr;  // cached B=1 batch behind lego_klt_track / build_pyramid
+    uint8_t *pinned = nullptr;         // staging for the single-pair path
+    size_t pinned_bytes = 0;
+};
+
+struct lego_klt_batch {
+    lego_klt_ctx *ctx = nullptr;
+    int B = 0, cols = 0, rows = 0, n_cap = 0, n_active = 0, levels = 0;
+    size_t step = 0;
+    PyramidPlan plan;
+    PyramidView view;
+    WarpKernelMaps *maps = nullptr;
+    uint8_t *d_images = nullptr;  // all levels, both sets
+    float2 *d_kp1 = nullptr, *d_kp2_init = nullptr, *d_kp2_out = nullptr;
+    uint8_t *d_success = nullptr;
+    unsigned long long *d_stats = nullptr;
+    unsigned long long *h_stats = nullptr;  // pinned
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool uploaded = false, ran = false, pyramids_valid = false;
+    lego_klt_params last_params;
+};
+
+namespace {
+
+int validate_params(const lego_klt_params *p, int levels_of_batch) {
+    if (!p) return fail(LEGO_KLT_ERR_BAD_ARG, "params is null");
+    if (p->levels != levels_of_batch)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "params->levels (%d) != batch levels (%d)", p->levels, levels_of_batch);
+    if (p->patch_lo > p->patch_hi || p->patch_hi - p->patch_lo + 1 > kMaxPatch)
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "patch %d..%d unsupported (max %d wide)", p->patch_lo, p->patch_hi,
+                    kMaxPatch);
+    if (p->max_iters < 0) return fail(LEGO_KLT_ERR_BAD_ARG, "max_iters < 0");
+    if (p->kernel < LEGO_KLT_KERNEL_AUTO || p->kernel > LEGO_KLT_KERNEL_LANE)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "unknown kernel id %d", p->kernel);
+    return LEGO_KLT_OK;
+}
+
+int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n, int levels,
+                lego_klt_batch **out) {
+    if (!ctx || !out) return fail(LEGO_KLT_ERR_BAD_ARG, "null ctx/out");
+    if (B <= 0 || cols <= 0 || rows <= 0 || step < (size_t)cols || n < 0 || levels < 1 || levels > kMaxLevels)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "bad batch shape B=%d cols=%d rows=%d step=%zu n=%d levels=%d", B, cols,
+                    rows, step, n, levels);
+    if (B > 32000) return fail(LEGO_KLT_ERR_UNSUPPORTED, "batch too large (%d > 32000)", B);
+    int lc[kMaxLevels], lr[kMaxLevels];
+    if (!pyramid_level_sizes(cols, rows, levels, lc, lr))
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "pyramid level would be empty for %dx%d, %d levels", cols, rows,
+                    levels);
+    CU_TRY(cudaSetDevice(ctx->device));
+    lego_klt_batch *b = new (std::nothrow) lego_klt_batch();
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "out of host memory");
+    b->ctx = ctx;
+    b->B = B;
+    b->cols = cols;
+    b->rows = rows;
+    b->step = step;
+    b->n_cap = n;
+    b->n_active = n;
+    b->levels = levels;
+
+    // ---- device image blob: per level, per set: B images of rows*pitch bytes ----
+    int pitch[kMaxLevels];
+    size_t total = 0, off[kMaxLevels][2];
+    memset(&b->view, 0, sizeof(b->view));
+    b->view.levels = levels;
+    b->view.n_images = B;
+    for (int l = 0; l < levels; ++l) {
+        LevelView &lv = b->view.lv[l];
+        lv.cols = lc[l];
+        lv.rows = lr[l];
+        lv.step = (l == 0) ? (int)step : lc[l];
+        pitch[l] = (int)align_up((size_t)lv.step, 16);
+        lv.pitch = pitch[l];
+        lv.slot = (unsigned long long)lr[l] * pitch[l];
+        for (int s = 0; s < 2; ++s) {
+            off[l][s] = total;
+            total += align_up((size_t)B * lv.slot, 256);
+        }
+    }
+    total += 256;
+    auto cleanup = [&](int code) {
+        lego_klt_batch_destroy(b);
+        return code;
+    };
+    cudaError_t e = cudaMalloc(&b->d_images, total);
+    if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMalloc(%zu) images: %s", total, cudaGetErrorString(e)));
+    e = cudaMemsetAsync(b->d_images, 0, total, ctx->stream);
+    if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMemset images: %s", cudaGetErrorString(e)));
+    for (int l = 0; l < levels; ++l)
+        for (int s = 0; s < 2; ++s) b->view.lv[l].base[s] = b->d_images + off[l][s];
+
+    const size_t nt = (size_t)B * (size_t)(n > 0 ? n : 1);
+    if ((e = cudaMalloc(&b->d_kp1, nt * sizeof(float2))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_kp2_init, nt * sizeof(float2))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_kp2_out, nt * sizeof(float2))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_success, nt)) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMallocHost(&b->h_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess)
+        return cleanup(fail(LEGO_KLT_ERR_CUDA, "allocating keypoint buffers: %s", cudaGetErrorString(e)));
+    for (int i = 0; i < EV_COUNT; ++i)
+        if ((e = cudaEventCreate(&b->ev[i])) != cudaSuccess)
+            return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)));
+    if ((e = pyramid_plan_create(cols, rows, levels, pitch, &b->plan)) != cudaSuccess)
+        return cleanup(fail(LEGO_KLT_ERR_CUDA, "pyramid plan: %s", cudaGetErrorString(e)));
+    if ((e = warp_maps_create(b->view, &b->maps)) != cudaSuccess)
+        return cleanup(fail(LEGO_KLT_ERR_CUDA, "TMA descriptor creation failed: %s", cudaGetErrorString(e)));
+    *out = b;
+    return LEGO_KLT_OK;
+}
+
+// H2D of level 0 of one image set: rows of `step` bytes into the pitched device layout.
+cudaError_t upload_set(lego_klt_batch *b, int set, const uint8_t *src, size_t src_step) {
+    const LevelView &l0 = b->view.lv[0];
+    return cudaMemcpy2DAsync(l0.base[set], (size_t)l0.pitch, src, src_step, src_step,
+                             (size_t)b->B * (size_t)b->rows, cudaMemcpyHostToDevice, b->ctx->stream);
+}
+
+int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
+    int rc = validate_params(params, b->levels);
+    if (rc) return rc;
+    if (!b->uploaded) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_run before upload");
+    lego_klt_ctx *ctx = b->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
+    CU_TRY(launch_pyramid(b->plan, b->view, st));
+    b->pyramids_valid = true;
+    CU_TRY(cudaEventRecord(b->ev[EV_PYR], st));
+    SolverArgs a;
+    a.kp1 = b->d_kp1;
+    a.kp2_init = b->d_kp2_init;
+    a.kp2_out = b->d_kp2_out;
+    a.success = b->d_success;
+    a.stats = b->d_stats;
+    a.n_per_pair = b->n_active > 0 ? b->n_active : 1;
+    a.n_total = b->B * b->n_active;
+    a.patch_lo = params->patch_lo;
+    a.patch_hi = params->patch_hi;
+    a.max_iters = params->max_iters;
+    a.inverse = params->inverse;
+    a.has_initial = params->has_initial;
+    a.eps = params->eps;
+    int kernel = params->kernel;
+    if (kernel == LEGO_KLT_KERNEL_AUTO || kernel == LEGO_KLT_KERNEL_LANE) kernel = LEGO_KLT_KERNEL_WARP;
+    if (kernel == LEGO_KLT_KERNEL_EXACT)
+        CU_TRY(launch_klt_exact(b->view, a, st));
+    else
+        CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
+    CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
+    b->ran = true;
+    b->last_params = *params;
+    return LEGO_KLT_OK;
+}
+
+void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
+    memset(s, 0, sizeof(*s));
+    s->n_features = (uint64_t)b->B * (uint64_t)b->n_active;
+    s->n_success = b->h_stats[kStatSuccess];
+    s->n_nan = b->h_stats[kStatNan];
+    s->n_out_of_image = b->h_stats[kStatOutOfImage];
+    s->n_slow_path = b->h_stats[kStatSlowPath];
+    for (int l = 0; l < kMaxLevels; ++l) s->gn_iters[l] = b->h_stats[kStatIters0 + l];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->ev[EV_START], b->ev[EV_H2D]) == cudaSuccess) s->ms_h2d = ms;
+    if (cudaEventElapsedTime(&ms, b->ev[EV_H2D], b->ev[EV_PYR]) == cudaSuccess) s->ms_pyramid = ms;
+    if (cudaEventElapsedTime(&ms, b->ev[EV_PYR], b->ev[EV_SOLVE]) == cudaSuccess) s->ms_solver = ms;
+    if (cudaEventElapsedTime(&ms, b->ev[EV_SOLVE], b->ev[EV_D2H]) == cudaSuccess) s->ms_d2h = ms;
+    cudaGetLastError();  // events not recorded yet (run without upload) are not an error of this call
+}
+
+int ensure_pinned(lego_klt_ctx *ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return LEGO_KLT_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    CU_TRY(cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return LEGO_KLT_OK;
+}
+
+// (Re)creates the cached single-pair batch when the shape changes or more features are needed.
+int ensure_single(lego_klt_ctx *ctx, int cols, int rows, size_t step, int n, int levels) {
+    lego_klt_batch *s = ctx->single;
+    if (s && s->cols == cols && s->rows == rows && s->step == step && s->levels == levels && s->n_cap >= n)
+        return LEGO_KLT_OK;
+    if (s) lego_klt_batch_destroy(s);
+    ctx->single = nullptr;
+    int cap = n < 256 ? 256 : (int)align_up((size_t)n, 256);
+    return batch_alloc(ctx, 1, cols, rows, step, cap, levels, &ctx->single);
+}
+
+}  // namespace
+
+extern "C" {
+
+int lego_klt_abi_version(void) { return LEGO_KLT_ABI_VERSION; }
+
+const char *lego_klt_last_error(void) { return g_last_error.c_str(); }
+
+void lego_klt_default_params(lego_klt_params *p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->levels = 4;        // src/algorithm.cpp:135
+    p->patch_lo = -3;     // :40,63-64
+    p->patch_hi = 3;
+    p->max_iters = 10;    // :42
+    p->inverse = 0;       // src/frontend_g2o.cpp:473,515
+    p->has_initial = 1;
+    p->kernel = LEGO_KLT_KERNEL_AUTO;
+    p->eps = 1e-2;        // :113
+}
+
+int lego_klt_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(LEGO_KLT_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int lego_klt_create(int device, lego_klt_ctx **out) {
+    if (!out) return fail(LEGO_KLT_ERR_BAD_ARG, "out is null");
+    *out = nullptr;
+    int n = lego_klt_device_count();
+    if (n < 0) return n;
+    if (device < 0 || device >= n) return fail(LEGO_KLT_ERR_BAD_ARG, "device %d out of range [0,%d)", device, n);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LEGO_KLT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device,
+                    prop.major, prop.minor);
+    lego_klt_ctx *ctx = new (std::nothrow) lego_klt_ctx();
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(LEGO_KLT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return LEGO_KLT_OK;
+}
+
+void lego_klt_destroy(lego_klt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->single) lego_klt_batch_destroy(ctx->single);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int lego_klt_set_stream(lego_klt_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_sync(lego_klt_ctx *ctx) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return LEGO_KLT_OK;
+}
+
+void *lego_klt_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void lego_klt_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int lego_klt_batch_create(lego_klt_ctx *ctx, int batch, int cols, int rows, size_t step, int n_per_pair,
+                          int levels, lego_klt_batch **out) {
+    if (out) *out = nullptr;
+    return batch_alloc(ctx, batch, cols, rows, step, n_per_pair, levels, out);
+}
+
+void lego_klt_batch_destroy(lego_klt_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->maps) warp_maps_destroy(b->maps);
+    pyramid_plan_destroy(&b->plan);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    cudaFree(b->d_images);
+    cudaFree(b->d_kp1);
+    cudaFree(b->d_kp2_init);
+    cudaFree(b->d_kp2_out);
+    cudaFree(b->d_success);
+    cudaFree(b->d_stats);
+    if (b->h_stats) cudaFreeHost(b->h_stats);
+    cudaGetLastError();
+    delete b;
+}
+
+int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t *imgs2, const float *kp1_xy,
+                          const float *kp2_xy) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (!imgs1 || !imgs2) return fail(LEGO_KLT_ERR_BAD_ARG, "image pointer is null");
+    const size_t nt = (size_t)b->B * (size_t)b->n_active;
+    if (nt && (!kp1_xy || !kp2_xy)) return fail(LEGO_KLT_ERR_BAD_ARG, "keypoint pointer is null");
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    CU_TRY(cudaEventRecord(b->ev[EV_START], st));
+    CU_TRY(upload_set(b, 0, imgs1, b->step));
+    CU_TRY(upload_set(b, 1, imgs2, b->step));
+    if (nt) {
+        CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
+    }
+    b->uploaded = true;
+    b->pyramids_valid = false;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_batch_run(lego_klt_batch *b, const lego_klt_params *params) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    return batch_run(b, params);
+}
+
+int lego_klt_batch_download(lego_klt_batch *b, float *kp2_xy, uint8_t *success, lego_klt_stats *stats) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (!b->ran) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_download before run");
+    const size_t nt = (size_t)b->B * (size_t)b->n_active;
+    if (nt && (!kp2_xy || !success)) return fail(LEGO_KLT_ERR_BAD_ARG, "output pointer is null");
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    if (nt) {
+        CU_TRY(cudaMemcpyAsync(kp2_xy, b->d_kp2_out, nt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(success, b->d_success, nt, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(b->h_stats, b->d_stats, kStatCount * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(b->ev[EV_D2H], st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (stats) fill_stats(b, stats);
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, const uint8_t *imgs1,
+                           const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success,
+                           lego_klt_stats *stats) {
+    int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
+    if (rc) return rc;
+    rc = lego_klt_batch_run(b, params);
+    if (rc) return rc;
+    return lego_klt_batch_download(b, kp2_xy, success, stats);
+}
+
+int lego_klt_batch_device_ptrs(lego_klt_batch *b, void **imgs1, void **imgs2, void **kp1_xy, void **kp2_xy_init,
+                               void **kp2_xy_out, void **success) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (imgs1) *imgs1 = b->view.lv[0].base[0];
+    if (imgs2) *imgs2 = b->view.lv[0].base[1];
+    if (kp1_xy) *kp1_xy = b->d_kp1;
+    if (kp2_xy_init) *kp2_xy_init = b->d_kp2_init;
+    if (kp2_xy_out) *kp2_xy_out = b->d_kp2_out;
+    if (success) *success = b->d_success;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_track(lego_klt_ctx *ctx, const lego_klt_params *params, const uint8_t *img1, const uint8_t *img2,
+                   int cols, int rows, size_t step, const float *kp1_xy, float *kp2_xy, uint8_t *success, int n,
+                   lego_klt_stats *stats) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    if (!params) return fail(LEGO_KLT_ERR_BAD_ARG, "params is null");
+    if (!img1 || !img2 || cols <= 0 || rows <= 0 || step < (size_t)cols)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "bad image arguments");
+    if (n < 0 || (n > 0 && (!kp1_xy || !kp2_xy || !success))) return fail(LEGO_KLT_ERR_BAD_ARG, "bad keypoint arguments");
+    if (params->levels < 1 || params->levels > kMaxLevels) return fail(LEGO_KLT_ERR_BAD_ARG, "levels out of range");
+    int rc = ensure_single(ctx, cols, rows, step, n, params->levels);
+    if (rc) return rc;
+    lego_klt_batch *b = ctx->single;
+    b->n_active = n;
+    // Stage through pinned memory: a cv::Mat guarantees only (rows-1)*step + cols readable bytes.
+    const size_t img_bytes = (size_t)rows * step, kp_bytes = (size_t)n * sizeof(float2);
+    rc = ensure_pinned(ctx, 2 * img_bytes + 3 * kp_bytes + (size_t)n + 64);
+    if (rc) return rc;
+    uint8_t *h1 = ctx->pinned, *h2 = h1 + img_bytes;
+    float *hk1 = reinterpret_cast<float *>(h2 + img_bytes);
+    float *hk2 = hk1 + 2 * (size_t)n;
+    float *hout = hk2 + 2 * (size_t)n;
+    uint8_t *hs = reinterpret_cast<uint8_t *>(hout + 2 * (size_t)n);
+    const size_t valid = (size_t)(rows - 1) * step + (size_t)cols;
+    memcpy(h1, img1, valid);
+    memset(h1 + valid, 0, img_bytes - valid);
+    memcpy(h2, img2, valid);
+    memset(h2 + valid, 0, img_bytes - valid);
+    if (n) {
+        memcpy(hk1, kp1_xy, kp_bytes);
+        memcpy(hk2, kp2_xy, kp_bytes);
+    }
+    rc = lego_klt_batch_upload(b, h1, h2, hk1, hk2);
+    if (rc) return rc;
+    rc = batch_run(b, params);
+    if (rc) return rc;
+    rc = lego_klt_batch_download(b, hout, hs, stats);
+    if (rc) return rc;
+    if (n) {
+        memcpy(kp2_xy, hout, kp_bytes);
+        memcpy(success, hs, (size_t)n);
+    }
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step, int levels,
+                           uint8_t *out, size_t out_capacity, int *level_cols, int *level_rows) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    if (!img || cols <= 0 || rows <= 0 || step < (size_t)cols || levels < 1 || levels > kMaxLevels)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "bad image arguments");
+    int rc = ensure_single(ctx, cols, rows, step, 0, levels);
+    if (rc) return rc;
+    lego_klt_batch *b = ctx->single;
+    const size_t img_bytes = (size_t)rows * step;
+    rc = ensure_pinned(ctx, 2 * img_bytes);
+    if (rc) return rc;
+    const size_t valid = (size_t)(rows - 1) * step + (size_t)cols;
+    memcpy(ctx->pinned, img, valid);
+    memset(ctx->pinned + valid, 0, img_bytes - valid);
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU_TRY(upload_set(b, 0, ctx->pinned, step));
+    CU_TRY(upload_set(b, 1, ctx->pinned, step));
+    CU_TRY(launch_pyramid(b->plan, b->view, st));
+    size_t off = 0;
+    for (int l = 0; l < levels; ++l) {
+        const LevelView &lv = b->view.lv[l];
+        if (level_cols) level_cols[l] = lv.cols;
+        if (level_rows) level_rows[l] = lv.rows;
+        if (l == 0) continue;
+        const size_t nbytes = (size_t)lv.cols * lv.rows;
+        if (!out || off + nbytes > out_capacity) return fail(LEGO_KLT_ERR_BAD_ARG, "output buffer too small");
+        CU_TRY(cudaMemcpy2DAsync(out + off, (size_t)lv.cols, lv.base[0], (size_t)lv.pitch, (size_t)lv.cols,
+                                 (size_t)lv.rows, cudaMemcpyDeviceToHost, st));
+        off += nbytes;
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    b->uploaded = false;
+    return LEGO_KLT_OK;
+}
+
+}  // extern "C"

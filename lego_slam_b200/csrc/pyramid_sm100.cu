@@ -1,0 +1,260 @@
+// pyramid_sm100.cu -- K1: fused image-pyramid build for a batch of 8-bit images (sm_100a).
+//
+// Replaces the pyramid part of LKOpticalFlow4Layer, src/algorithm.cpp:140-154:
+//     level i = cv::resize(level i-1, cv::Size(cols*0.5, rows*0.5))      // INTER_LINEAR, CV_8UC1
+// OpenCV is third party (not under /root/reference); its 8-bit linear resize is integer fixed point
+// and is restated here (pinned bit-exact against Python cv2 by the oracle tests):
+//     f = (float)((d+0.5)*scale-0.5); s = floor(f); f -= s;   (x only: clamp s to [0,sn-1] with f=0)
+//     a0 = rint((1-f)*2048), a1 = rint(f*2048)
+//     h(x)  = S[sx]*a0 + S[sx+1]*a1                                        (int32, per source row)
+//     dst   = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2
+//
+// B200 design: HBM-bound (level 0 is read once, levels 1..L-1 written once; 619,601 B per 1241x376
+// image at L=4).  One CTA owns a band of top-level rows of one image: it stages the level-0 rows it
+// needs in shared memory with coalesced 16-byte loads, derives every coarser level from shared
+// memory, and writes each level's rows back with 16-byte stores -- no level is re-read from HBM.
+// The coefficient tables are built once per shape on the host and live in global memory (L1/L2 hits).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "klt_kernels.h"
+
+namespace legoklt {
+
+bool pyramid_level_sizes(int cols, int rows, int levels, int *lcols, int *lrows) {
+    lcols[0] = cols;
+    lrows[0] = rows;
+    for (int l = 1; l < levels; ++l) {
+        lcols[l] = (int)(lcols[l - 1] * 0.5);  // cv::Size(int * double) truncates
+        lrows[l] = (int)(lrows[l - 1] * 0.5);
+        if (lcols[l] <= 0 || lrows[l] <= 0) return false;
+    }
+    return true;
+}
+
+namespace {
+
+struct HostAxis {
+    std::vector<int> ofs;
+    std::vector<short2> coef;
+};
+
+HostAxis build_axis(int sn, int dn, bool horizontal) {
+    HostAxis t;
+    t.ofs.resize(dn);
+    t.coef.resize(dn);
+    const double inv_scale = (double)dn / sn;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dn; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(f);
+        f -= (float)s;
+        if (horizontal) {
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+        }
+        t.ofs[d] = s;
+        t.coef[d].x = (short)std::lrintf((1.f - f) * 2048.f);
+        t.coef[d].y = (short)std::lrintf(f * 2048.f);
+    }
+    return t;
+}
+
+inline int clip_row(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
+
+struct PyrKernelParams {
+    ResizeTables tab[kMaxLevels];
+    int smem_off[kMaxLevels];
+    int top_rows;
+};
+
+__device__ __forceinline__ int d_clip(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
+
+__global__ void __launch_bounds__(256)
+pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ PyrKernelParams kp) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int L = pyr.levels;
+    const int set = blockIdx.y / pyr.n_images;
+    const int img = blockIdx.y - set * pyr.n_images;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+
+    // Row bands [lo, hi) needed at every level for this CTA's top-level rows.
+    int lo[kMaxLevels], hi[kMaxLevels];
+    lo[L - 1] = blockIdx.x * kp.top_rows;
+    hi[L - 1] = min(lo[L - 1] + kp.top_rows, pyr.lv[L - 1].rows);
+#pragma unroll
+    for (int k = kMaxLevels - 1; k >= 1; --k) {
+        if (k <= L - 1) {
+            const int *yofs = kp.tab[k].yofs;
+            const int rows_src = pyr.lv[k - 1].rows;
+            lo[k - 1] = d_clip(__ldg(yofs + lo[k]), rows_src);
+            hi[k - 1] = d_clip(__ldg(yofs + hi[k] - 1) + 1, rows_src) + 1;
+        }
+    }
+
+    // Stage the level-0 band: contiguous bytes, 16-byte aligned (pitch % 16 == 0).
+    {
+        const LevelView &l0 = pyr.lv[0];
+        const uint4 *src = reinterpret_cast<const uint4 *>(l0.base[set] + (size_t)img * l0.slot +
+                                                           (size_t)lo[0] * l0.pitch);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem + kp.smem_off[0]);
+        const int nvec = (hi[0] - lo[0]) * (l0.pitch >> 4);
+        for (int i = tid; i < nvec; i += nthreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k = 1; k < L; ++k) {
+        const LevelView &ld = pyr.lv[k];
+        const LevelView &ls = pyr.lv[k - 1];
+        const uint8_t *S = smem + kp.smem_off[k - 1];
+        uint8_t *D = smem + kp.smem_off[k];
+        const ResizeTables &tb = kp.tab[k];
+        const int nr = hi[k] - lo[k];
+        const int ng = ld.pitch >> 2;  // 4-pixel groups per row (covers the padded pitch)
+        const int src_last = ls.cols - 1;
+        for (int i = tid; i < nr * ng; i += nthreads) {
+            const int r = i / ng, g = i - r * ng;
+            const int R = lo[k] + r;
+            const int yo = __ldg(tb.yofs + R);
+            const short2 b = __ldg(tb.ycoef + R);
+            const uint8_t *s0 = S + (d_clip(yo, ls.rows) - lo[k - 1]) * ls.pitch;
+            const uint8_t *s1 = S + (d_clip(yo + 1, ls.rows) - lo[k - 1]) * ls.pitch;
+            uint32_t packed = 0;
+            const int c0 = 4 * g;
+            if (c0 < ld.cols) {
+                const int4 xo = __ldg(reinterpret_cast<const int4 *>(tb.xofs) + g);
+                const uint4 xc = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
+                const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
+                const uint32_t cs[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c0 + j < ld.cols) {
+                        const int sx = xs[j];
+                        const int sx1 = min(sx + 1, src_last);
+                        const int a0 = (int)(short)(cs[j] & 0xffffu), a1 = (int)(short)(cs[j] >> 16);
+                        const int h0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1;
+                        const int h1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
+                        int v = ((((int)b.x * (h0 >> 4)) >> 16) + (((int)b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+                        v = min(max(v, 0), 255);
+                        packed |= (uint32_t)v << (8 * j);
+                    }
+                }
+            }
+            *reinterpret_cast<uint32_t *>(D + r * ld.pitch + c0) = packed;
+        }
+        __syncthreads();
+        // Write this level's band back: contiguous, 16-byte vectors.
+        {
+            uint4 *dst = reinterpret_cast<uint4 *>(ld.base[set] + (size_t)img * ld.slot +
+                                                   (size_t)lo[k] * ld.pitch);
+            const uint4 *src = reinterpret_cast<const uint4 *>(D);
+            const int nvec = nr * (ld.pitch >> 4);
+            for (int i = tid; i < nvec; i += nthreads) dst[i] = src[i];
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan) {
+    *plan = PyramidPlan();
+    plan->levels = levels;
+    if (!pyramid_level_sizes(cols, rows, levels, plan->cols, plan->rows)) return cudaErrorInvalidValue;
+    for (int l = 0; l < levels; ++l) plan->pitch[l] = pitch[l];
+    if (levels == 1) return cudaSuccess;
+
+    // ---- tables (one blob; every table padded to a multiple of 4 entries, 16-byte aligned) ----
+    std::vector<HostAxis> hx(levels), hy(levels);
+    size_t blob = 0;
+    auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
+    for (int l = 1; l < levels; ++l) {
+        hx[l] = build_axis(plan->cols[l - 1], plan->cols[l], true);
+        hy[l] = build_axis(plan->rows[l - 1], plan->rows[l], false);
+        blob += pad4(plan->cols[l]) * 8 + pad4(plan->rows[l]) * 8;
+    }
+    std::vector<uint8_t> host(blob, 0);
+    cudaError_t err = cudaMalloc(&plan->table_blob, blob);
+    if (err != cudaSuccess) return err;
+    size_t off = 0;
+    for (int l = 1; l < levels; ++l) {
+        uint8_t *dbase = static_cast<uint8_t *>(plan->table_blob);
+        ResizeTables &t = plan->tab[l];
+        const int nc = plan->cols[l], nr = plan->rows[l];
+        t.xofs = reinterpret_cast<int *>(dbase + off);
+        memcpy(&host[off], hx[l].ofs.data(), 4 * (size_t)nc);
+        off += pad4(nc) * 4;
+        t.xcoef = reinterpret_cast<short2 *>(dbase + off);
+        memcpy(&host[off], hx[l].coef.data(), 4 * (size_t)nc);
+        off += pad4(nc) * 4;
+        t.yofs = reinterpret_cast<int *>(dbase + off);
+        memcpy(&host[off], hy[l].ofs.data(), 4 * (size_t)nr);
+        off += pad4(nr) * 4;
+        t.ycoef = reinterpret_cast<short2 *>(dbase + off);
+        memcpy(&host[off], hy[l].coef.data(), 4 * (size_t)nr);
+        off += pad4(nr) * 4;
+        t.x_exact2 = 1;
+        for (int c = 0; c < nc; ++c)
+            if (hx[l].ofs[c] != 2 * c || hx[l].coef[c].x != 1024 || hx[l].coef[c].y != 1024) t.x_exact2 = 0;
+    }
+    err = cudaMemcpy(plan->table_blob, host.data(), blob, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return err;
+
+    // ---- band sizes: pick the largest top-row band whose staging fits comfortably in smem ----
+    const int top = levels - 1;
+    for (int tr = 4; tr >= 1; tr >>= 1) {
+        int maxr[kMaxLevels] = {0};
+        for (int t0 = 0; t0 < plan->rows[top]; t0 += tr) {
+            int lo = t0, hi = std::min(t0 + tr, plan->rows[top]);
+            maxr[top] = std::max(maxr[top], hi - lo);
+            for (int k = top; k >= 1; --k) {
+                int nlo = clip_row(hy[k].ofs[lo], plan->rows[k - 1]);
+                int nhi = clip_row(hy[k].ofs[hi - 1] + 1, plan->rows[k - 1]) + 1;
+                lo = nlo;
+                hi = nhi;
+                maxr[k - 1] = std::max(maxr[k - 1], hi - lo);
+            }
+        }
+        size_t bytes = 0;
+        for (int l = 0; l < levels; ++l) {
+            plan->smem_off[l] = (int)bytes;
+            plan->max_rows[l] = maxr[l];
+            bytes += (size_t)maxr[l] * plan->pitch[l];
+        }
+        plan->smem_bytes = bytes;
+        plan->top_rows_per_cta = tr;
+        if (bytes <= 56 * 1024 || tr == 1) break;
+    }
+    if (plan->smem_bytes > 220 * 1024) return cudaErrorInvalidValue;
+    return cudaSuccess;
+}
+
+void pyramid_plan_destroy(PyramidPlan *plan) {
+    if (plan->table_blob) cudaFree(plan->table_blob);
+    *plan = PyramidPlan();
+}
+
+cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, cudaStream_t stream) {
+    if (plan.levels <= 1 || pyr.n_images <= 0) return cudaSuccess;
+    PyrKernelParams kp;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        kp.tab[l] = plan.tab[l];
+        kp.smem_off[l] = plan.smem_off[l];
+    }
+    kp.top_rows = plan.top_rows_per_cta;
+    static thread_local size_t configured = 0;
+    if (plan.smem_bytes > 48 * 1024 && plan.smem_bytes > configured) {
+        cudaError_t err = cudaFuncSetAttribute(pyramid_fused_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)plan.smem_bytes);
+        if (err != cudaSuccess) return err;
+        configured = plan.smem_bytes;
+    }
+    const int top = plan.levels - 1;
+    dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, 2 * pyr.n_images);
+    pyramid_fused_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
+    return cudaGetLastError();
+}
+
+}  // namespace legoklt

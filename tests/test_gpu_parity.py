@@ -1,0 +1,202 @@
+"""GPU parity tests proper: every call goes through the C ABI (liblego_klt.so) and is compared with
+the CPU oracle on the same seeded inputs.  Tolerances (BASELINE.json north_star): success flags
+bit-identical (borderline features reported), positions within 1e-3 px; the EXACT kernel and the
+pyramid are held to bit-exactness."""
+import numpy as np
+import pytest
+
+import lego_slam_b200 as klt
+from lego_slam_b200 import synth
+from parity_util import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+FAST_KERNELS = [klt.KERNEL_WARP]
+
+
+def _iters(st, levels):
+    return [int(v) for v in st.gn_iters][:levels]
+
+
+# ------------------------------------------------------------------ pyramid (K1): bit exact
+@pytest.mark.parametrize("rows,cols,levels", [(376, 1241, 4), (188, 620, 4), (1080, 1920, 5), (217, 333, 3),
+                                              (95, 157, 4), (64, 64, 5), (9, 11, 2), (376, 1241, 1)])
+def test_pyramid_bit_exact(tracker, oracle, rows, cols, levels):
+    img = np.random.default_rng(rows * 31 + cols).integers(0, 256, size=(rows, cols), dtype=np.uint8)
+    got = tracker.build_pyramid(img, levels)
+    ref = oracle.build_pyramid(img, levels)
+    for l in range(1, levels):
+        assert got[l].shape == ref[l].shape
+        assert np.array_equal(got[l], ref[l]), f"level {l}: {(got[l] != ref[l]).sum()} pixels differ"
+
+
+def test_pyramid_with_row_step(tracker, oracle):
+    big = np.random.default_rng(3).integers(0, 256, size=(120, 400), dtype=np.uint8)
+    view = big[:, :333]
+    got, ref = tracker.build_pyramid(view, 3), oracle.build_pyramid(view, 3)
+    for l in range(1, 3):
+        assert np.array_equal(got[l], ref[l])
+
+
+# ------------------------------------------------------------------ golden vectors through the C ABI
+def test_exact_kernel_reproduces_golden_vectors_bitwise(tracker, golden):
+    meta, vec = golden
+    for name, kw in meta["solver"].items():
+        kw = dict(kw)
+        iters, nsucc = kw.pop("gn_iters"), kw.pop("n_success")
+        p = klt.make_params(kernel=klt.KERNEL_EXACT, **kw)
+        out, succ, st = tracker.track(vec["left"], vec["right"], vec["kp1"], vec["kp2"], p)
+        assert np.array_equal(out.view(np.uint32), vec[f"{name}_kp2"].view(np.uint32)), name
+        assert np.array_equal(succ, vec[f"{name}_succ"]), name
+        assert _iters(st, p.levels) == iters and int(st.n_success) == nsucc, name
+
+
+@pytest.mark.parametrize("kernel", FAST_KERNELS)
+def test_fast_kernel_matches_golden_vectors(tracker, golden, kernel):
+    meta, vec = golden
+    rows, cols = vec["left"].shape
+    for name, kw in meta["solver"].items():
+        kw = dict(kw)
+        iters, _ = kw.pop("gn_iters"), kw.pop("n_success")
+        p = klt.make_params(kernel=kernel, **kw)
+        out, succ, st = tracker.track(vec["left"], vec["right"], vec["kp1"], vec["kp2"], p)
+        assert_parity(out, succ, vec[f"{name}_kp2"], vec[f"{name}_succ"], cols, rows, name)
+        assert _iters(st, p.levels) == iters, name  # same convergence decisions
+
+
+# ------------------------------------------------------------------ BASELINE configs, GPU vs oracle
+def _check_case(tracker, oracle, L, R, kp1, kp2, params_kw, kernels, what):
+    rows, cols = L.shape
+    ref, rs, rst = oracle.track(L, R, kp1, kp2, oracle.make_params(**params_kw), threads=8)
+    reports = {}
+    for kernel in kernels:
+        p = klt.make_params(kernel=kernel, **params_kw)
+        out, succ, st = tracker.track(L, R, kp1, kp2, p)
+        if kernel == klt.KERNEL_EXACT:
+            assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), what
+            assert np.array_equal(succ, rs), what
+        rep = assert_parity(out, succ, ref, rs, cols, rows, f"{what} kernel={kernel}")
+        rep["gn_iters_gpu"], rep["gn_iters_cpu"] = _iters(st, p.levels), _iters(rst, p.levels)
+        assert rep["gn_iters_gpu"] == rep["gn_iters_cpu"], (what, rep)
+        reports[kernel] = rep
+    return reports
+
+
+@pytest.mark.parametrize("guess", ["same", "noisy"])
+def test_config1_single_pair_150_features(tracker, oracle, guess):
+    L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, 150, seed=1, guess=guess)
+    _check_case(tracker, oracle, L, R, kp1, kp2, dict(levels=4), [klt.KERNEL_EXACT] + FAST_KERNELS, "C1")
+
+
+def test_config2_sequence_temporal_and_stereo_2000(tracker, oracle):
+    for frame in (1, 2):
+        P, Cur, kp1, kp2, _ = synth.temporal_case(376, 1241, 2000, seed=2, frame=frame)
+        _check_case(tracker, oracle, P, Cur, kp1, kp2, dict(levels=4), [klt.KERNEL_EXACT] + FAST_KERNELS,
+                    f"C2 temporal f{frame}")
+    L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, 2000, seed=2)
+    _check_case(tracker, oracle, L, R, kp1, kp2, dict(levels=4), [klt.KERNEL_EXACT] + FAST_KERNELS, "C2 stereo")
+
+
+def test_config4_1080p_5_levels_inverse(tracker, oracle):
+    L, R, kp1, kp2, _ = synth.stereo_case(1080, 1920, 5000, seed=3)
+    _check_case(tracker, oracle, L, R, kp1, kp2, dict(levels=5, inverse=True),
+                [klt.KERNEL_EXACT] + FAST_KERNELS, "C4")
+
+
+@pytest.mark.parametrize("n,lo,hi", [(100, -3, 3), (20000, -3, 3), (3000, -5, 5), (3000, -4, 3)])
+def test_config5_stress_feature_counts_and_patches(tracker, oracle, n, lo, hi):
+    L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, n, seed=4, min_dist=3 if n > 5000 else 5)
+    _check_case(tracker, oracle, L, R, kp1, kp2, dict(levels=4, patch_lo=lo, patch_hi=hi), FAST_KERNELS,
+                f"C5 n={n} patch={lo}..{hi}")
+
+
+# ------------------------------------------------------------------ batched path (north star (3))
+def _make_batch(B, rows, cols, n, seed0):
+    imgs1 = klt.pinned_empty((B, rows, cols), np.uint8)
+    imgs2 = klt.pinned_empty((B, rows, cols), np.uint8)
+    kp1 = klt.pinned_empty((B, n, 2), np.float32)
+    kp2 = klt.pinned_empty((B, n, 2), np.float32)
+    for b in range(B):
+        L, R, a, g, _ = synth.stereo_case(rows, cols, n, seed=seed0 + b)
+        imgs1[b], imgs2[b], kp1[b], kp2[b] = L, R, a, g
+    return imgs1, imgs2, kp1, kp2
+
+
+@pytest.mark.parametrize("kernel", FAST_KERNELS)
+def test_config3_batched_pairs_match_oracle_per_pair(tracker, oracle, kernel):
+    B, rows, cols, n = 6, 376, 1241, 2000
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 1000)
+    guess = kp2.copy()
+    succ = klt.pinned_empty((B, n), np.uint8)
+    batch = tracker.batch(B, rows, cols, n, levels=4)
+    st = batch.track(imgs1, imgs2, kp1, kp2, succ, klt.make_params(kernel=kernel))
+    assert int(st.n_features) == B * n
+    total_iters = np.zeros(4, np.int64)
+    for b in range(B):
+        ref, rs, rst = oracle.track(imgs1[b], imgs2[b], kp1[b], guess[b], threads=8)
+        assert_parity(kp2[b], succ[b], ref, rs, cols, rows, f"C3 pair {b}")
+        total_iters += np.array(_iters(rst, 4))
+    assert _iters(st, 4) == total_iters.tolist()
+    assert int(st.n_success) == int(succ.sum())
+    batch.close()
+
+
+def test_batch_is_idempotent_and_equals_single_calls(tracker):
+    """size-independent property: re-running a resident batch gives the same bytes, and each pair of
+    the batch equals the single-pair entry point on that pair."""
+    B, rows, cols, n = 4, 188, 620, 500
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 2000)
+    batch = tracker.batch(B, rows, cols, n, levels=4)
+    batch.upload(imgs1, imgs2, kp1, kp2)
+    batch.run()
+    a, sa, _ = batch.download()
+    batch.run()
+    b, sb, _ = batch.download()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(sa, sb)
+    for i in range(B):
+        o, s, _ = tracker.track(imgs1[i], imgs2[i], kp1[i], kp2[i])
+        assert np.array_equal(o.view(np.uint32), a[i].view(np.uint32)) and np.array_equal(s, sa[i])
+    batch.close()
+
+
+# ------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT] + FAST_KERNELS)
+def test_edge_cases(tracker, oracle, kernel):
+    rows, cols = 94, 310
+    L, R, kp1, kp2, _ = synth.stereo_case(rows, cols, 64, seed=9, min_dist=6)
+    # empty list
+    out, succ, st = tracker.track(L, R, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32),
+                                  klt.make_params(levels=3, kernel=kernel))
+    assert out.shape == (0, 2) and succ.shape == (0,) and int(st.n_features) == 0
+    # one feature
+    o1, s1, _ = tracker.track(L, R, kp1[:1], kp2[:1], klt.make_params(levels=3, kernel=kernel))
+    r1, rs1, _ = oracle.track(L, R, kp1[:1], kp2[:1], oracle.make_params(levels=3))
+    assert_parity(o1, s1, r1, rs1, cols, rows, "n=1")
+    # border / outside / sliver / binade-crossing features, guesses off-image
+    ugly = np.array([[0, 0], [1.5, 1.5], [cols - 1, rows - 1], [cols - 0.5, 10], [20, rows - 0.25],
+                     [-5, 20], [cols + 3, rows + 3], [127.9999, 63.9999], [255.5, 31.75], [3.9999, 7.9999],
+                     [cols - 4.2, rows - 4.1], [2.9, 2.9]], np.float32)
+    guess = ugly + np.array([[0.7, -0.4]], np.float32)
+    guess[5] = [-30, 20]
+    for kw in (dict(levels=3), dict(levels=1), dict(levels=3, inverse=True), dict(levels=3, has_initial=False),
+               dict(levels=2, patch_lo=-5, patch_hi=5)):
+        o, s, _ = tracker.track(L, R, ugly, guess, klt.make_params(kernel=kernel, **kw))
+        r, rs, _ = oracle.track(L, R, ugly, guess, oracle.make_params(**kw))
+        assert_parity(o, s, r, rs, cols, rows, f"ugly {kw}")
+    # flat image: H == 0 -> zero update, success (Eigen LDLT pseudo-inverse)
+    flat = np.full((64, 64), 77, np.uint8)
+    kp = np.array([[32, 32], [10, 50]], np.float32)
+    o, s, st = tracker.track(flat, flat, kp, kp + np.float32(0.25), klt.make_params(levels=2, kernel=kernel))
+    assert s.all() and int(st.n_nan) == 0 and np.array_equal(o, kp + np.float32(0.25))
+
+
+def test_bad_arguments_are_rejected(tracker):
+    from lego_slam_b200 import _lib
+    img = np.zeros((32, 32), np.uint8)
+    kp = np.zeros((1, 2), np.float32)
+    with pytest.raises(_lib.KltError):
+        tracker.track(img, img, kp, kp, klt.make_params(levels=9))
+    with pytest.raises(_lib.KltError):
+        tracker.track(img, img, kp, kp, klt.make_params(levels=7))  # level would be empty
+    with pytest.raises(_lib.KltError):
+        tracker.track(img, img, kp, kp, klt.make_params(levels=1, patch_lo=-8, patch_hi=8))
