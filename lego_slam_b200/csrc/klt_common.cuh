@@ -20,7 +20,7 @@ namespace legoklt {
 
 constexpr int kMaxLevels = LEGO_KLT_MAX_LEVELS;
 constexpr int kMaxPatch = 13;       // (patch_hi - patch_lo + 1) <= 13
-constexpr int kWinW = 32;           // TMA window box, bytes per row (multiple of 16)
+constexpr int kWinW = 48;           // TMA window box, bytes per row (multiple of 16)
 constexpr int kWinH = 24;           // TMA window box, rows
 
 // One pyramid level of a batch of images, device resident.
@@ -49,6 +49,7 @@ enum StatSlot {
     kStatOutOfImage,
     kStatSuccess,
     kStatSlowPath,
+    kStatTmaTimeout,
     kStatCount
 };
 
@@ -65,6 +66,7 @@ struct SolverArgs {
     int inverse;
     int has_initial;
     double eps;
+    int debug_flags;          // LEGO_KLT_DEBUG env: 1 = never use the TMA fast path, 2 = count TMA timeouts instead of trapping
 };
 
 #ifdef __CUDACC__

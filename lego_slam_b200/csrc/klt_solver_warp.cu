@@ -7,7 +7,7 @@
 //   * one warp owns one feature for all levels; dx,dy,cost,lastCost and the decisions live in
 //     registers, replicated on every lane (the butterfly reduction leaves identical bits everywhere,
 //     so every lane takes the same branch without a broadcast);
-//   * the img2 neighbourhood of the current estimate is staged in shared memory as a 32x24-byte tile
+//   * the img2 neighbourhood of the current estimate is staged in shared memory as a 48x24-byte tile
 //     by TMA (cp.async.bulk.tensor.3d, one elected lane, mbarrier completion) and re-staged only when
 //     the sample footprint drifts out of it;
 //   * per Gauss-Newton pass the warp first evaluates the (P+2)^2 grid of bilinear samples ONCE
@@ -77,11 +77,15 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t 
 }
 
 // Bounded wait: a TMA that never completes (bad descriptor) traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t parity, bool trap_on_timeout) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 22)) {
+            if (trap_on_timeout) __trap();
+            return false;
+        }
     }
+    return true;
 }
 
 __device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *map, int x, int y, int z,
@@ -226,7 +230,7 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         interior = (coord >= 0.f) && (coord < (float)(limit - 1));
                         ic = (int)coord;
                     }
-                    const bool usable = __all_sync(0xffffffffu, consistent && interior);
+                    const bool usable = __all_sync(0xffffffffu, consistent && interior) && !(args.debug_flags & 1);
                     if (usable) {
                         const int ix_min = __shfl_sync(0xffffffffu, ic, 0);
                         const int iy_min = __shfl_sync(0xffffffffu, ic, 16);
@@ -235,17 +239,20 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         if (is_row) covered = win_valid && ic >= wy0 && ic + 1 <= wy0 + kWinH - 1;
                         if (!__all_sync(0xffffffffu, covered)) {
                             // (re)stage the tile centred on the current footprint
-                            wx0 = ix_min - (kWinW - (G + 1)) / 2;
+                            // TMA tile mode needs a 16-byte aligned innermost start coordinate (measured on
+                            // B200: an unaligned uint8 x faults with 'illegal instruction'); floor to 16.
+                            wx0 = (ix_min - (kWinW - 15 - (G + 1)) / 2) & ~15;
                             wy0 = iy_min - (kWinH - (G + 1)) / 2;
                             __syncwarp();
                             if (lane == 0) {
                                 mbar_expect_tx(&ws.bar, kWinW * kWinH);
                                 tma_load_tile(ws.win, &maps.img2[level], wx0, wy0, img, &ws.bar);
                             }
-                            mbar_wait(&ws.bar, tma_phase);
+                            const bool arrived = mbar_wait(&ws.bar, tma_phase, !(args.debug_flags & 2));
+                            if (!arrived && lane == 0) atomicAdd(&s_stats[kStatTmaTimeout], 1ull);
                             tma_phase ^= 1u;
-                            win_valid = true;
-                            covered = true;
+                            win_valid = arrived;
+                            covered = arrived;
                             if (is_col) covered = ic >= wx0 && ic + 1 <= wx0 + kWinW - 1;
                             if (is_row) covered = ic >= wy0 && ic + 1 <= wy0 + kWinH - 1;
                         }

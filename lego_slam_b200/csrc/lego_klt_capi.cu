@@ -5,6 +5,7 @@
 // (include/legoslam/algorithm.h:123-136), called at src/frontend_g2o.cpp:473 and :515.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -189,6 +190,10 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     a.inverse = params->inverse;
     a.has_initial = params->has_initial;
     a.eps = params->eps;
+    {
+        const char *dbg = getenv("LEGO_KLT_DEBUG");
+        a.debug_flags = dbg ? atoi(dbg) : 0;
+    }
     int kernel = params->kernel;
     if (kernel == LEGO_KLT_KERNEL_AUTO || kernel == LEGO_KLT_KERNEL_LANE) kernel = LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_EXACT)
@@ -208,6 +213,7 @@ void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     s->n_nan = b->h_stats[kStatNan];
     s->n_out_of_image = b->h_stats[kStatOutOfImage];
     s->n_slow_path = b->h_stats[kStatSlowPath];
+    if (b->h_stats[kStatTmaTimeout]) s->n_nan += 1000000ull * b->h_stats[kStatTmaTimeout];  // debug aid
     for (int l = 0; l < kMaxLevels; ++l) s->gn_iters[l] = b->h_stats[kStatIters0 + l];
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev[EV_START], b->ev[EV_H2D]) == cudaSuccess) s->ms_h2d = ms;

@@ -79,17 +79,26 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
     const int img = blockIdx.y - set * pyr.n_images;
     const int tid = threadIdx.x, nthreads = blockDim.x;
 
-    // Row bands [lo, hi) needed at every level for this CTA's top-level rows.
+    // Row bands [lo, hi) at every level for this CTA's top-level rows.  A band must contain the rows
+    // the next-coarser band reads (needed range) AND reach the first row of the next CTA's band, so
+    // that the bands of one level tile it completely: with truncated level sizes (135 -> 67) or a
+    // vertical scale above 2 the coarser level does not read every finer row.
     int lo[kMaxLevels], hi[kMaxLevels];
-    lo[L - 1] = blockIdx.x * kp.top_rows;
-    hi[L - 1] = min(lo[L - 1] + kp.top_rows, pyr.lv[L - 1].rows);
+    {
+        const bool last_band = (blockIdx.x + 1 == gridDim.x);
+        int next_lo = (blockIdx.x + 1) * kp.top_rows;  // first row of the next band at level k
+        lo[L - 1] = blockIdx.x * kp.top_rows;
+        hi[L - 1] = min(lo[L - 1] + kp.top_rows, pyr.lv[L - 1].rows);
 #pragma unroll
-    for (int k = kMaxLevels - 1; k >= 1; --k) {
-        if (k <= L - 1) {
-            const int *yofs = kp.tab[k].yofs;
-            const int rows_src = pyr.lv[k - 1].rows;
-            lo[k - 1] = d_clip(__ldg(yofs + lo[k]), rows_src);
-            hi[k - 1] = d_clip(__ldg(yofs + hi[k] - 1) + 1, rows_src) + 1;
+        for (int k = kMaxLevels - 1; k >= 1; --k) {
+            if (k <= L - 1) {
+                const int *yofs = kp.tab[k].yofs;
+                const int rows_src = pyr.lv[k - 1].rows;
+                lo[k - 1] = d_clip(__ldg(yofs + lo[k]), rows_src);
+                const int needed_hi = d_clip(__ldg(yofs + hi[k] - 1) + 1, rows_src) + 1;
+                next_lo = last_band ? rows_src : d_clip(__ldg(yofs + next_lo), rows_src);
+                hi[k - 1] = max(needed_hi, next_lo);
+            }
         }
     }
 
@@ -206,13 +215,15 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
     for (int tr = 4; tr >= 1; tr >>= 1) {
         int maxr[kMaxLevels] = {0};
         for (int t0 = 0; t0 < plan->rows[top]; t0 += tr) {
-            int lo = t0, hi = std::min(t0 + tr, plan->rows[top]);
+            const bool last_band = t0 + tr >= plan->rows[top];
+            int lo = t0, hi = std::min(t0 + tr, plan->rows[top]), next_lo = t0 + tr;
             maxr[top] = std::max(maxr[top], hi - lo);
             for (int k = top; k >= 1; --k) {
                 int nlo = clip_row(hy[k].ofs[lo], plan->rows[k - 1]);
-                int nhi = clip_row(hy[k].ofs[hi - 1] + 1, plan->rows[k - 1]) + 1;
+                int needed_hi = clip_row(hy[k].ofs[hi - 1] + 1, plan->rows[k - 1]) + 1;
+                next_lo = last_band ? plan->rows[k - 1] : clip_row(hy[k].ofs[next_lo], plan->rows[k - 1]);
                 lo = nlo;
-                hi = nhi;
+                hi = std::max(needed_hi, next_lo);
                 maxr[k - 1] = std::max(maxr[k - 1], hi - lo);
             }
         }
