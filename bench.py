@@ -79,53 +79,55 @@ def fill_batch(base, n_pairs, n_feat, alloc):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints), polled every 5 ms in a thread."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, cuda_index: int):
+        self.samples, self.mask, self.h, self.max_mhz, self.err = [], 0, None, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": reasons}
 
 
 def cpu_oracle_throughput(base, n_feat, budget_s: float, threads: int):
@@ -247,16 +249,10 @@ def run_ours(args):
 
     # per-kernel launch durations (CUDA events on the launching stream, recorded inside the library
     # around each kernel), averaged over the same number of steps
-    ms_pyr, ms_sol, iters = [], [], None
-    for _ in range(args.steps):
-        batch.run(params)
-        _, _, st = batch.download(kp2_io, succ)
-        ms_pyr.append(st.ms_pyramid)
-        ms_sol.append(st.ms_solver)
-        iters = [int(v) for v in st.gn_iters][:LEVELS]
-        slow = int(st.n_slow_path)
-        n_success = int(st.n_success)
-    ms_pyr, ms_sol = float(np.mean(ms_pyr)), float(np.mean(ms_sol))
+    ms_pyr, ms_sol = batch.timings(min(args.steps, 64))   # the timed steps above, back to back
+    _, _, st = batch.download(kp2_io, succ)
+    iters = [int(v) for v in st.gn_iters][:LEVELS]
+    slow, deferred, n_success = int(st.n_slow_path), int(st.n_deferred), int(st.n_success)
 
     # ---------------- end to end: host buffers -> lego_klt_track_batched -> host buffers ----------------
     for _ in range(min(args.warmup, 3)):
@@ -324,8 +320,9 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(imgs1.nbytes + imgs2.nbytes + kp1.nbytes + kp2.nbytes),
                 "d2h_bytes_per_step": int(kp2_io.nbytes + succ.nbytes + 12 * 8),
                 "ms_per_step": e2e_ms / args.steps, "api": "lego_klt_track_batched (pinned host buffers)"},
-        "gpu_launches": 2 * args.steps,
-        "roofline": {"kernel": "klt_warp_kernel (fused 4-level GN solver)", "bound": "fp32-issue (non-tensor)",
+        "gpu_launches": (3 if args.kernel in (0, 3) else 2) * args.steps,
+        "roofline": {"kernel": "klt_lane_kernel + klt_warp_kernel on deferred features (fused 4-level GN solver)"
+                     if args.kernel in (0, 3) else "klt_warp_kernel (fused 4-level GN solver)", "bound": "fp32-issue (non-tensor)",
                      "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
                      "peak_source": f"computed: {sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz un-fused fp32 "
@@ -338,7 +335,8 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": ms_pyr},
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "solver": {"n_success": n_success, "n_slow_path_passes": slow, "kernel": int(args.kernel)},
+        "solver": {"n_success": n_success, "n_slow_path_passes": slow, "n_deferred_features": deferred,
+                   "kernel": {0: "auto (lane + warp for deferred)", 1: "exact", 2: "warp", 3: "lane"}[int(args.kernel)]},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

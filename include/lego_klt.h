@@ -43,7 +43,7 @@ enum {
 
 /* ---- solver kernel selection ---- */
 enum {
-    LEGO_KLT_KERNEL_AUTO = 0,   /* fastest parity-green kernel (currently WARP)                    */
+    LEGO_KLT_KERNEL_AUTO = 0,   /* LANE where it applies (7x7 forward), else WARP                  */
     LEGO_KLT_KERNEL_EXACT = 1,  /* one thread per feature, reference operation order, flat global
                                    addressing: bit-identical to the CPU oracle; the on-GPU checker  */
     LEGO_KLT_KERNEL_WARP = 2,   /* one warp per feature, windows staged in shared memory, fp64
@@ -78,7 +78,10 @@ typedef struct lego_klt_stats {
     uint64_t n_nan;                              /* solves that returned NaN/Inf (algorithm.cpp:94) */
     uint64_t n_out_of_image;                     /* final level: result outside img2 (:123)        */
     uint64_t gn_iters[LEGO_KLT_MAX_LEVELS];      /* patch passes executed per level, level 0 = fine */
-    uint64_t n_slow_path;                        /* feature-levels solved on the exact border path */
+    uint64_t n_slow_path;                        /* warp kernel: passes run on the exact per-pixel path */
+    uint64_t n_deferred;                         /* lane kernel: features handed to the warp kernel  */
+    uint64_t defer_reason[4];                    /* ... by reason: kx+c inexact, rounding margin,
+                                                    nominal index, coordinate range               */
     float ms_h2d, ms_pyramid, ms_solver, ms_d2h; /* device times (CUDA events) of the last call    */
 } lego_klt_stats;
 
@@ -135,6 +138,9 @@ int lego_klt_batch_run(lego_klt_batch *b, const lego_klt_params *params);
 /* D2H of results; synchronises the stream. */
 int lego_klt_batch_download(lego_klt_batch *b, float *kp2_xy, uint8_t *success,
                             lego_klt_stats *stats_or_null);
+/* Device time of the pyramid and solver kernels, averaged over the last `last_n` (<= 64) runs of this
+ * batch, from CUDA events recorded around each launch on the batch's stream.  Synchronises. */
+int lego_klt_batch_timings(lego_klt_batch *b, int last_n, float *ms_pyramid_avg, float *ms_solver_avg);
 /* upload + run + download in one call (the end-to-end path bench.py times as `e2e`). */
 int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params,
                            const uint8_t *imgs1, const uint8_t *imgs2,

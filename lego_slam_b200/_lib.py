@@ -16,7 +16,7 @@ EXPORTS = [
     "lego_klt_abi_version", "lego_klt_last_error", "lego_klt_default_params", "lego_klt_device_count",
     "lego_klt_create", "lego_klt_destroy", "lego_klt_set_stream", "lego_klt_track",
     "lego_klt_build_pyramid", "lego_klt_batch_create", "lego_klt_batch_destroy", "lego_klt_batch_upload",
-    "lego_klt_batch_run", "lego_klt_batch_download", "lego_klt_track_batched",
+    "lego_klt_batch_run", "lego_klt_batch_download", "lego_klt_batch_timings", "lego_klt_track_batched",
     "lego_klt_batch_device_ptrs", "lego_klt_sync", "lego_klt_alloc_pinned", "lego_klt_free_pinned",
 ]
 
@@ -32,7 +32,7 @@ class Stats(C.Structure):
     """lego_klt_stats"""
     _fields_ = [("n_features", C.c_uint64), ("n_success", C.c_uint64), ("n_nan", C.c_uint64),
                 ("n_out_of_image", C.c_uint64), ("gn_iters", C.c_uint64 * MAX_LEVELS),
-                ("n_slow_path", C.c_uint64), ("ms_h2d", C.c_float), ("ms_pyramid", C.c_float),
+                ("n_slow_path", C.c_uint64), ("n_deferred", C.c_uint64), ("defer_reason", C.c_uint64 * 4), ("ms_h2d", C.c_float), ("ms_pyramid", C.c_float),
                 ("ms_solver", C.c_float), ("ms_d2h", C.c_float)]
 
 
@@ -78,6 +78,7 @@ def load():
     lib.lego_klt_batch_upload.argtypes = [vp, vp, vp, vp, vp]
     lib.lego_klt_batch_run.argtypes = [vp, pp]
     lib.lego_klt_batch_download.argtypes = [vp, vp, vp, sp]
+    lib.lego_klt_batch_timings.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.lego_klt_track_batched.argtypes = [vp, pp, vp, vp, vp, vp, vp, sp]
     lib.lego_klt_batch_device_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 6
     lib.lego_klt_alloc_pinned.argtypes = [C.c_size_t]

@@ -157,6 +157,12 @@ class Batch:
                                                      C.byref(st)), "lego_klt_batch_download")
         return kp2_out, success, st
 
+    def timings(self, last_n: int):
+        """(ms_pyramid, ms_solver) averaged over the last `last_n` runs (CUDA events around each launch)."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self._lib.lego_klt_batch_timings(self._h, last_n, C.byref(a), C.byref(b)), "lego_klt_batch_timings")
+        return a.value, b.value
+
     def track(self, imgs1, imgs2, kp1, kp2_inout, success, params: Params | None = None):
         """lego_klt_track_batched: H2D + pyramids + solver + D2H; kp2_inout is overwritten."""
         self._check_inputs(imgs1, imgs2, kp1, kp2_inout)

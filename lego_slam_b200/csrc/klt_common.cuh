@@ -50,6 +50,11 @@ enum StatSlot {
     kStatSuccess,
     kStatSlowPath,
     kStatTmaTimeout,
+    kStatDeferred,
+    kStatDeferInexact,   // reason counters of kStatDeferred
+    kStatDeferMargin,
+    kStatDeferNominal,
+    kStatDeferRange,
     kStatCount
 };
 
@@ -67,6 +72,13 @@ struct SolverArgs {
     int has_initial;
     double eps;
     int debug_flags;          // LEGO_KLT_DEBUG env: 1 = never use the TMA fast path, 2 = count TMA timeouts instead of trapping
+    // Optional work list (used for the features the LANE kernel defers): feature ids and their count.
+    const int *list;
+    const int *list_count;
+    // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
+    int *work_counter;
+    int *defer_list;
+    int *defer_count;
 };
 
 #ifdef __CUDACC__

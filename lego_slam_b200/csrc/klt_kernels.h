@@ -44,4 +44,9 @@ void warp_maps_destroy(WarpKernelMaps *maps);
 cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, const SolverArgs &args,
                             int sm_count, cudaStream_t stream);
 
+// LANE kernel (klt_solver_lane.cu): thread per feature, 7x7 forward only; defers irregular features to
+// args.defer_list (to be finished by launch_klt_warp with args.list = defer_list).
+bool lane_kernel_supports(const SolverArgs &args);
+cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
+
 }  // namespace legoklt

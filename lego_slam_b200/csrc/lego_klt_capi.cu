@@ -39,6 +39,7 @@ int fail(int code, const char *fmt, ...) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
+constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings)
 
 }  // namespace
 
@@ -65,6 +66,10 @@ struct lego_klt_batch {
     unsigned long long *d_stats = nullptr;
     unsigned long long *h_stats = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
+    cudaEvent_t ring[kRing][3] = {};  // run r: [0] before pyramid, [1] after pyramid, [2] after solver
+    long long runs = 0;
+    int *d_work = nullptr;         // [0] work counter, [1] deferred count (LANE kernel)
+    int *d_defer_list = nullptr;   // [B * n_cap]
     bool uploaded = false, ran = false, pyramids_valid = false;
     lego_klt_params last_params;
 };
@@ -144,11 +149,17 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
         (e = cudaMalloc(&b->d_kp2_out, nt * sizeof(float2))) != cudaSuccess ||
         (e = cudaMalloc(&b->d_success, nt)) != cudaSuccess ||
         (e = cudaMalloc(&b->d_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_work, 4 * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_defer_list, nt * sizeof(int))) != cudaSuccess ||
         (e = cudaMallocHost(&b->h_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess)
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "allocating keypoint buffers: %s", cudaGetErrorString(e)));
     for (int i = 0; i < EV_COUNT; ++i)
         if ((e = cudaEventCreate(&b->ev[i])) != cudaSuccess)
             return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)));
+    for (int r = 0; r < kRing; ++r)
+        for (int i = 0; i < 3; ++i)
+            if ((e = cudaEventCreate(&b->ring[r][i])) != cudaSuccess)
+                return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)));
     if ((e = pyramid_plan_create(cols, rows, levels, pitch, &b->plan)) != cudaSuccess)
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "pyramid plan: %s", cudaGetErrorString(e)));
     if ((e = warp_maps_create(b->view, &b->maps)) != cudaSuccess)
@@ -172,10 +183,14 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(b->d_work, 0, 4 * sizeof(int), st));
+    cudaEvent_t *ring = b->ring[b->runs % kRing];
     CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
+    CU_TRY(cudaEventRecord(ring[0], st));
     CU_TRY(launch_pyramid(b->plan, b->view, st));
     b->pyramids_valid = true;
     CU_TRY(cudaEventRecord(b->ev[EV_PYR], st));
+    CU_TRY(cudaEventRecord(ring[1], st));
     SolverArgs a;
     a.kp1 = b->d_kp1;
     a.kp2_init = b->d_kp2_init;
@@ -194,13 +209,29 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
         const char *dbg = getenv("LEGO_KLT_DEBUG");
         a.debug_flags = dbg ? atoi(dbg) : 0;
     }
+    a.list = nullptr;
+    a.list_count = nullptr;
+    a.work_counter = b->d_work;
+    a.defer_count = b->d_work + 1;
+    a.defer_list = b->d_defer_list;
     int kernel = params->kernel;
-    if (kernel == LEGO_KLT_KERNEL_AUTO || kernel == LEGO_KLT_KERNEL_LANE) kernel = LEGO_KLT_KERNEL_WARP;
-    if (kernel == LEGO_KLT_KERNEL_EXACT)
+    if (kernel == LEGO_KLT_KERNEL_AUTO) kernel = lane_kernel_supports(a) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
+    if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the 7x7 forward configuration only");
+    if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(b->view, a, st));
-    else
+    } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
+    } else {
+        CU_TRY(launch_klt_lane(b->view, a, ctx->sm_count, st));
+        // features the LANE kernel deferred (border slivers, inexact kx+c, ...) are finished exactly
+        a.list = b->d_defer_list;
+        a.list_count = b->d_work + 1;
+        CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
+    }
     CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
+    CU_TRY(cudaEventRecord(ring[2], st));
+    ++b->runs;
     b->ran = true;
     b->last_params = *params;
     return LEGO_KLT_OK;
@@ -213,6 +244,8 @@ void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     s->n_nan = b->h_stats[kStatNan];
     s->n_out_of_image = b->h_stats[kStatOutOfImage];
     s->n_slow_path = b->h_stats[kStatSlowPath];
+    s->n_deferred = b->h_stats[kStatDeferred];
+    for (int i = 0; i < 4; ++i) s->defer_reason[i] = b->h_stats[kStatDeferInexact + i];
     if (b->h_stats[kStatTmaTimeout]) s->n_nan += 1000000ull * b->h_stats[kStatTmaTimeout];  // debug aid
     for (int l = 0; l < kMaxLevels; ++l) s->gn_iters[l] = b->h_stats[kStatIters0 + l];
     float ms = 0.f;
@@ -350,6 +383,11 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     pyramid_plan_destroy(&b->plan);
     for (int i = 0; i < EV_COUNT; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    for (int r = 0; r < kRing; ++r)
+        for (int i = 0; i < 3; ++i)
+            if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
+    cudaFree(b->d_work);
+    cudaFree(b->d_defer_list);
     cudaFree(b->d_images);
     cudaFree(b->d_kp1);
     cudaFree(b->d_kp2_init);
@@ -402,6 +440,25 @@ int lego_klt_batch_download(lego_klt_batch *b, float *kp2_xy, uint8_t *success, 
     CU_TRY(cudaEventRecord(b->ev[EV_D2H], st));
     CU_TRY(cudaStreamSynchronize(st));
     if (stats) fill_stats(b, stats);
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_batch_timings(lego_klt_batch *b, int last_n, float *ms_pyramid_avg, float *ms_solver_avg) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (last_n <= 0 || last_n > kRing || last_n > b->runs)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "last_n must be in [1, min(%d, runs so far)]", kRing);
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    CU_TRY(cudaStreamSynchronize(b->ctx->stream));
+    double sp = 0, ss = 0;
+    for (long long r = b->runs - last_n; r < b->runs; ++r) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, b->ring[r % kRing][0], b->ring[r % kRing][1]));
+        sp += ms;
+        CU_TRY(cudaEventElapsedTime(&ms, b->ring[r % kRing][1], b->ring[r % kRing][2]));
+        ss += ms;
+    }
+    if (ms_pyramid_avg) *ms_pyramid_avg = (float)(sp / last_n);
+    if (ms_solver_avg) *ms_solver_avg = (float)(ss / last_n);
     return LEGO_KLT_OK;
 }
 

@@ -23,7 +23,7 @@ class Stats(C.Structure):
     """Mirror of lego_klt_stats (include/lego_klt.h)."""
     _fields_ = [("n_features", C.c_uint64), ("n_success", C.c_uint64), ("n_nan", C.c_uint64),
                 ("n_out_of_image", C.c_uint64), ("gn_iters", C.c_uint64 * MAX_LEVELS),
-                ("n_slow_path", C.c_uint64), ("ms_h2d", C.c_float), ("ms_pyramid", C.c_float),
+                ("n_slow_path", C.c_uint64), ("n_deferred", C.c_uint64), ("defer_reason", C.c_uint64 * 4), ("ms_h2d", C.c_float), ("ms_pyramid", C.c_float),
                 ("ms_solver", C.c_float), ("ms_d2h", C.c_float)]
 
 

@@ -47,7 +47,7 @@ def test_struct_layouts_match_the_header():
     from lego_slam_b200 import _lib
     from oracle import binding
     assert C.sizeof(_lib.Params) == 40 == C.sizeof(binding.Params)
-    assert C.sizeof(_lib.Stats) == 4 * 8 + 8 * 8 + 8 + 4 * 4 == C.sizeof(binding.Stats)
+    assert C.sizeof(_lib.Stats) == 4 * 8 + 8 * 8 + 2 * 8 + 4 * 8 + 4 * 4 == C.sizeof(binding.Stats)
 
 
 def test_no_silent_cpu_fallback_without_a_gpu(lib):

@@ -11,7 +11,14 @@ from parity_util import assert_parity
 
 pytestmark = pytest.mark.gpu
 
-FAST_KERNELS = [klt.KERNEL_WARP]
+FAST_KERNELS = [klt.KERNEL_WARP, klt.KERNEL_LANE]
+
+
+def _supported(kernel, kw):
+    """The LANE kernel is specialised for the reference's call-site configuration (7x7, forward)."""
+    if kernel != klt.KERNEL_LANE:
+        return True
+    return (kw.get("patch_lo", -3), kw.get("patch_hi", 3)) == (-3, 3) and not kw.get("inverse", False)
 
 
 def _iters(st, levels):
@@ -58,6 +65,8 @@ def test_fast_kernel_matches_golden_vectors(tracker, golden, kernel):
     for name, kw in meta["solver"].items():
         kw = dict(kw)
         iters, _ = kw.pop("gn_iters"), kw.pop("n_success")
+        if not _supported(kernel, kw):
+            continue
         p = klt.make_params(kernel=kernel, **kw)
         out, succ, st = tracker.track(vec["left"], vec["right"], vec["kp1"], vec["kp2"], p)
         assert_parity(out, succ, vec[f"{name}_kp2"], vec[f"{name}_succ"], cols, rows, name)
@@ -70,6 +79,8 @@ def _check_case(tracker, oracle, L, R, kp1, kp2, params_kw, kernels, what):
     ref, rs, rst = oracle.track(L, R, kp1, kp2, oracle.make_params(**params_kw), threads=8)
     reports = {}
     for kernel in kernels:
+        if not _supported(kernel, params_kw):
+            continue
         p = klt.make_params(kernel=kernel, **params_kw)
         out, succ, st = tracker.track(L, R, kp1, kp2, p)
         if kernel == klt.KERNEL_EXACT:
@@ -180,6 +191,8 @@ def test_edge_cases(tracker, oracle, kernel):
     guess[5] = [-30, 20]
     for kw in (dict(levels=3), dict(levels=1), dict(levels=3, inverse=True), dict(levels=3, has_initial=False),
                dict(levels=2, patch_lo=-5, patch_hi=5)):
+        if not _supported(kernel, kw):
+            continue
         o, s, _ = tracker.track(L, R, ugly, guess, klt.make_params(kernel=kernel, **kw))
         r, rs, _ = oracle.track(L, R, ugly, guess, oracle.make_params(**kw))
         assert_parity(o, s, r, rs, cols, rows, f"ugly {kw}")
@@ -188,6 +201,33 @@ def test_edge_cases(tracker, oracle, kernel):
     kp = np.array([[32, 32], [10, 50]], np.float32)
     o, s, st = tracker.track(flat, flat, kp, kp + np.float32(0.25), klt.make_params(levels=2, kernel=kernel))
     assert s.all() and int(st.n_nan) == 0 and np.array_equal(o, kp + np.float32(0.25))
+
+
+def test_subpixel_keypoints_and_deferred_features(tracker, oracle):
+    """Tracked (sub-pixel) source points, as Frontend::TrackLastFrame feeds them: kx+c is sometimes
+    inexact in fp32 near powers of two, which the LANE kernel must hand to the exact warp kernel."""
+    rows, cols, n = 376, 1241, 4000
+    L, R, kp1, kp2, _ = synth.stereo_case(rows, cols, n, seed=21)
+    rng = np.random.default_rng(5)
+    kp1 = (kp1 + rng.uniform(-0.5, 0.5, kp1.shape)).astype(np.float32)
+    kp2 = (kp1 + rng.normal(0, 1.0, kp1.shape)).astype(np.float32)
+    ref, rs, rst = oracle.track(L, R, kp1, kp2, threads=8)
+    for kernel in FAST_KERNELS:
+        out, succ, st = tracker.track(L, R, kp1, kp2, klt.make_params(kernel=kernel))
+        assert_parity(out, succ, ref, rs, cols, rows, f"subpixel kernel={kernel}")
+        assert _iters(st, 4) == _iters(rst, 4)
+        if kernel == klt.KERNEL_LANE:
+            assert 0 < int(st.n_deferred) < n // 2, int(st.n_deferred)
+
+
+def test_lane_kernel_rejects_unsupported_configurations(tracker):
+    from lego_slam_b200 import _lib
+    img = np.zeros((64, 64), np.uint8)
+    kp = np.full((1, 2), 30, np.float32)
+    with pytest.raises(_lib.KltError):
+        tracker.track(img, img, kp, kp, klt.make_params(levels=2, inverse=True, kernel=klt.KERNEL_LANE))
+    with pytest.raises(_lib.KltError):
+        tracker.track(img, img, kp, kp, klt.make_params(levels=2, patch_lo=-4, patch_hi=3, kernel=klt.KERNEL_LANE))
 
 
 def test_bad_arguments_are_rejected(tracker):
