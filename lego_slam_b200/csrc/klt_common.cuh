@@ -22,9 +22,15 @@ constexpr int kMaxLevels = LEGO_KLT_MAX_LEVELS;
 constexpr int kMaxPatch = 13;       // (patch_hi - patch_lo + 1) <= 13
 constexpr int kWinW = 48;           // TMA window box, bytes per row (multiple of 16)
 constexpr int kWinH = 24;           // TMA window box, rows
+constexpr int kApronL = 32;         // bytes of left apron in front of every device image row
+constexpr int kApronR = 48;         // minimum bytes of right apron (column `cols` onwards)
 
 // One pyramid level of a batch of images, device resident.
 //   pixel (img k, row r, col c) of set s lives at base[s] + k*slot + r*pitch + c
+// Every row carries an apron (written by the apron kernel after the pyramid build), valid for
+// c in [-kApronL, pitch - kApronL):  c < 0 replicates column 0;  c == cols holds the byte the reference's
+// flat addressing reads one past the row end, data[r*step + cols] (algorithm.h:48,53: first pixel of the
+// next row, 0 past the last row);  c > cols replicates column cols-1.
 // `step` is the LOGICAL row step the reference would see (level 0: the caller's cv::Mat::step,
 // levels >= 1: cols, because cv::resize outputs are continuous) -- the border path reproduces the
 // reference's flat addressing data[int(y)*step + int(x) (+1, +step, +step+1)] with it.
@@ -32,7 +38,7 @@ struct LevelView {
     uint8_t *base[2];
     unsigned long long slot;  // bytes between consecutive images (multiple of 256)
     int cols, rows;
-    int pitch;                // device bytes per row (multiple of 16, >= step for level 0)
+    int pitch;                // device bytes per row incl. aprons (multiple of 16)
     int step;                 // logical step (see above)
 };
 
@@ -76,6 +82,7 @@ struct SolverArgs {
     const int *list;
     const int *list_count;
     // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
+    float *templates;         // [n_total][levels][52]: I1 patches + regularity flag (template kernel)
     int *work_counter;
     int *defer_list;
     int *defer_count;

@@ -34,6 +34,8 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
 void pyramid_plan_destroy(PyramidPlan *plan);
 // Builds levels 1..L-1 of both image sets (2 * n_images images) from level 0, one fused launch.
 cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, cudaStream_t stream);
+// Writes the row aprons (see LevelView) of every level of both image sets; run after launch_pyramid.
+cudaError_t launch_aprons(const PyramidView &pyr, cudaStream_t stream);
 
 // ---- solver kernels ---------------------------------------------------------------------------
 cudaError_t launch_klt_exact(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
@@ -47,6 +49,7 @@ cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, 
 // LANE kernel (klt_solver_lane.cu): thread per feature, 7x7 forward only; defers irregular features to
 // args.defer_list (to be finished by launch_klt_warp with args.list = defer_list).
 bool lane_kernel_supports(const SolverArgs &args);
+size_t lane_template_bytes(int n_total, int levels);
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
 
 }  // namespace legoklt

@@ -3,39 +3,42 @@
 // configuration: src/frontend_g2o.cpp:473,515 with src/algorithm.cpp:40 half_patch_size = 3).
 //
 // Replaces LKOpticalFlow1Layer + LKOpticalFlowTracker::calcLKOpticalFlow (src/algorithm.cpp:11-125)
-// and the coarse-to-fine loop of LKOpticalFlow4Layer (:158-205).
+// and the coarse-to-fine loop of LKOpticalFlow4Layer (:158-205).  Two kernels:
 //
-// Why not warp-per-feature (measured, profiles/r01_warp_kernel.md): that mapping spends ~850 warp
-// instructions per Gauss-Newton pass -- shuffles for six fp64 reductions, a serial 2x2 solve on every
-// lane, per-sample index arithmetic -- for 49 pixels of useful work.  Here every lane runs a whole
-// pass for its own feature (no shuffles, no idle lanes in the solve), ~70 warp instructions per
-// feature-pass.  Divergence in iteration counts (1..10 per level) is removed by a state machine: each
-// trip of the main loop is exactly one pass for every live thread; a thread that converges moves to
-// its next level / next feature while its neighbours keep iterating.
+//   klt_template_kernel  one thread per (feature, level): the 7x7 template patch I1 of
+//                        src/algorithm.cpp:65 (GetPixelValue(img1, kx+x, ky+y)), constant over the
+//                        Gauss-Newton passes of a level, written once as 49 floats + a regularity flag.
+//   klt_lane_kernel      one thread per feature: all passes of all levels.
 //
-// Data movement: global memory is never read divergently per thread.  When a thread starts a level
-// (or its footprint drifts out of its window) the WARP stages for it, cooperatively and coalesced:
-//   * the 7x7 template patch I1 -- sampled with the reference's exact border semantics from a staged
-//     img1 tile, stored as 49 floats in the thread's shared-memory column;
-//   * a 32x14-byte img2 window (16-byte aligned origin, replicate-clamped at the image border) in a
-//     word-interleaved layout  win2[word][T+1]  -> bank = (word + thread) % 32: conflict-free for the
-//     cooperative writer (fixed thread, consecutive words) and for the pass (fixed word, all threads).
+// Why not warp-per-feature (measured, profiles/r01_*): that mapping spends ~850 warp instructions per
+// Gauss-Newton pass -- shuffles for six fp64 reductions, a serial 2x2 solve on every lane, per-sample
+// index arithmetic -- for 49 pixels of useful work.  Here every lane runs a whole pass for its own
+// feature (no shuffles, no idle lanes in the solve).  Divergence in iteration counts (1..10 per level)
+// is removed by a state machine: each trip of the main loop is exactly one pass for every runnable
+// thread; a thread that converges moves to its next level / next feature while its neighbours keep
+// iterating.  Level set-up (template fetch + img2 window staging) is per thread but BATCHED: threads
+// wait until enough of the warp needs set-up, so the divergent set-up code is issued rarely.
+//
+// Shared memory, per thread, word-interleaved  [word][T+1]  (bank = (word + thread) % 32, so a warp
+// reading "its" word w is conflict-free):  img2 window 32x14 bytes (16-byte aligned origin, border
+// semantics baked in by the stager), template 49 floats, 18 row weights.
 //
 // Bit-fidelity contract (same as the warp kernel): every fp32 value entering the sums is bit-identical
 // to the reference's; only the ORDER of the fp64 additions differs (row-major here, x-outer there; all
 // products are exact in fp64).  The (P+2)^2 sample grid is shared between "centre of pixel x+1" and
 // "+1 tap of pixel x" only when that is provably what the reference computes:
-//   (a) kx+c, ky+c are exact in fp32 for c in [-3,3] (checked per level);
+//   (a) kx+c, ky+c are exact in fp32 for c in [-3,3] (checked per level, in the template kernel);
 //   (b) the double coordinate is not within 16 ulp64 of an fp32 rounding midpoint (checked per pass,
 //       per grid column/row), so the <=2 ulp64 differences between the reference's three ways of
 //       forming a coordinate cannot change the rounded float -- or it is EXACTLY on a midpoint and all
-//       double sums are provably exact (TwoSum), which is the common first-pass case (kx + float dx);
+//       double sums are provably exact (TwoSum), which is the common first-pass case (kx + float dx).
 // The border semantics of algorithm.h:42-55 ARE part of the fast path: clamped coordinates get the
 // factors (1,0) over replicated border pixels; a sample in the last-pixel sliver x in (cols-1, cols)
-// reads the reference's flat-address neighbour (first pixel of the next row), which the stager puts in
-// window column `cols`; y in (rows-1, rows) reads zeros below the image (the oracle's definition of the
-// reference's out-of-buffer read).  A feature that violates (a) or (b) is appended to a deferred list
-// and finished by the exact warp kernel; its partial work is dropped.
+// reads the reference's flat-address neighbour (first pixel of the next row); both come from the row
+// aprons every device image carries (LevelView), so window staging never branches on the border;
+// y in (rows-1, rows) reads zeros below the image (the oracle's definition of the reference's
+// out-of-buffer read).  A feature that violates (a) or (b), or whose window leaves the 32-pixel apron,
+// is appended to a deferred list and finished by the exact warp kernel; its partial work is dropped.
 #include "klt_kernels.h"
 
 namespace legoklt {
@@ -43,10 +46,12 @@ namespace legoklt {
 namespace {
 
 constexpr int LO = -3, HI = 3, P = 7, G = 9;
-constexpr int kWin2Rows = 14, kWin2Words = 8;                 // 14 rows x 32 bytes per thread
+constexpr int kWin2Rows = 14, kWin2Words = 8;                 // img2 window: 14 rows x 32 bytes per thread
 constexpr int kWin2Total = kWin2Rows * kWin2Words;            // 112 words
-constexpr int kI1Count = P * P;                               // 49 floats
-constexpr int kScratchRows = 8, kScratchW = 32;               // img1 staging tile per warp
+constexpr int kTplRows = 8;                                   // img1 window rows in the template kernel
+constexpr int kI1Count = P * P;                               // 49 floats, index y*P + x
+constexpr int kTplStride = 52;                                // floats per (feature, level): 49 + flag + pad
+constexpr int kSetupBatch = 10;                               // blocked threads per warp that trigger set-up
 
 enum : int { ST_FETCH = 0, ST_LEVEL = 1, ST_RUN = 2, ST_DONE = 3 };
 
@@ -54,8 +59,13 @@ template <int T>
 struct LaneSmem {
     uint32_t win2[kWin2Total][T + 1];
     float i1[kI1Count][T + 1];
-    alignas(16) uint8_t scratch[T / 32][kScratchRows * kScratchW];
+    float wy[2 * G][T + 1];  // per grid row: [2r] = 1-frac, [2r+1] = frac (dynamic row index in the rolled loop)
     unsigned stats[kStatCount];
+};
+
+template <int T>
+struct TemplateSmem {
+    uint32_t win[kTplRows * kWin2Words][T + 1];
 };
 
 __device__ __forceinline__ float byte_to_float(uint32_t packed, int k) {
@@ -100,7 +110,7 @@ __device__ __forceinline__ int grid_axis(float k, double d, int limit, int &orig
     const bool tie_ok = (err == 0.0) && ((__double2loint(S) & 0xF) == 0) && (fabs(S) >= 1.0);
     const double D0 = S + (double)(LO - 1);
     origin = __double2int_rd(D0);  // nominal integer coordinate of grid index 0
-    int why = 0;  // 0 = regular, else the kStatDefer* reason
+    int why = 0;                   // 0 = regular, else the kStatDefer* reason
     const float flimit = (float)limit, flast = (float)(limit - 1);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -130,46 +140,147 @@ __device__ __forceinline__ int grid_axis(float k, double d, int limit, int &orig
     return why;
 }
 
-// GetPixelValue on img1 for the cooperative template stage: taps from the warp's staged tile when all
-// four are inside it and inside the image, else the reference's flat addressing from global memory.
-__device__ __forceinline__ float sample_staged(const uint8_t *tile, int sx0, int sy0, const uint8_t *img,
-                                               const LevelView &lv, float x, float y) {
-    if (x < 0.f) x = 0.f;
-    if (y < 0.f) y = 0.f;
-    if (x >= (float)lv.cols) x = (float)(lv.cols - 1);
-    if (y >= (float)lv.rows) y = (float)(lv.rows - 1);
-    const int ix = (int)x, iy = (int)y;
-    const float xx = x - floorf(x), yy = y - floorf(y);
-    float p0, p1, p2, p3;
-    const int tx = ix - sx0, ty = iy - sy0;
-    if (ix + 1 < lv.cols && iy + 1 < lv.rows && tx >= 0 && tx + 1 < kScratchW && ty >= 0 && ty + 1 < kScratchRows) {
-        const uint8_t *p = tile + ty * kScratchW + tx;
-        p0 = (float)p[0];
-        p1 = (float)p[1];
-        p2 = (float)p[kScratchW];
-        p3 = (float)p[kScratchW + 1];
-    } else if (ix + 1 < lv.cols && iy + 1 < lv.rows) {
-        const uint8_t *p = img + (size_t)iy * lv.pitch + ix;
-        p0 = (float)__ldg(p);
-        p1 = (float)__ldg(p + 1);
-        p2 = (float)__ldg(p + lv.pitch);
-        p3 = (float)__ldg(p + lv.pitch + 1);
-    } else {
-        const long long f = (long long)iy * lv.step + ix;
-        p0 = fetch_flat(img, lv, f);
-        p1 = fetch_flat(img, lv, f + 1);
-        p2 = fetch_flat(img, lv, f + lv.step);
-        p3 = fetch_flat(img, lv, f + lv.step + 1);
-    }
-    return bilerp(1.f - xx, xx, 1.f - yy, yy, p0, p1, p2, p3);
+// kx + c exact in fp32 for c in [LO, HI]: the end of larger magnitude decides (condition (a)).
+__device__ __forceinline__ bool offsets_exact(float k) {
+    const double kd = (double)k;
+    return ((double)(k + (float)LO) == kd + (double)LO) && ((double)(k + (float)HI) == kd + (double)HI);
 }
 
+// The calling thread stages ROWS x 32 bytes of `img`, nominal origin (wx0 16-aligned, wy0), into its own
+// column `dst` of a word-interleaved window (row r, word w at dst[(r*8 + w) * WS]).  Rows are clamped to
+// the image; columns outside [0, cols) come from the row aprons (LevelView), so every load is an aligned
+// 16-byte load.  The caller guarantees window_in_apron(lv, wx0).
+__device__ __forceinline__ bool window_in_apron(const LevelView &lv, int wx0) {
+    return wx0 >= -kApronL && wx0 + kWin2Words * 4 <= lv.pitch - kApronL;
+}
+
+template <int ROWS, int WS>
+__device__ __forceinline__ void stage_own_window(const uint8_t *img, const LevelView &lv, int wx0, int wy0,
+                                                 uint32_t *dst) {
+    constexpr int kBatch = (ROWS + 1) / 2;
+#pragma unroll
+    for (int base = 0; base < ROWS; base += kBatch) {
+        uint4 v[kBatch][2];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            if (base + i < ROWS) {
+                const int ry = min(max(wy0 + base + i, 0), lv.rows - 1);
+                const uint4 *rp = reinterpret_cast<const uint4 *>(img + (ptrdiff_t)ry * lv.pitch + wx0);
+                v[i][0] = __ldg(rp);
+                v[i][1] = __ldg(rp + 1);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            if (base + i < ROWS) {
+                uint32_t *d = dst + (base + i) * kWin2Words * WS;
+                d[0] = v[i][0].x;
+                d[WS] = v[i][0].y;
+                d[2 * WS] = v[i][0].z;
+                d[3 * WS] = v[i][0].w;
+                d[4 * WS] = v[i][1].x;
+                d[5 * WS] = v[i][1].y;
+                d[6 * WS] = v[i][1].z;
+                d[7 * WS] = v[i][1].w;
+            }
+        }
+    }
+}
+
+// Ten consecutive window pixels of row i (starting at the footprint's first column) as floats.
+template <int WS>
+__device__ __forceinline__ void load_row10(const uint32_t *wp, int i, int sh, float (&row)[G + 1]) {
+    const uint32_t *p = wp + i * kWin2Words * WS;
+    const uint32_t w0 = p[0], w1 = p[WS], w2 = p[2 * WS], w3 = p[3 * WS];
+    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
+    row[0] = byte_to_float(b0, 0);
+    row[1] = byte_to_float(b0, 1);
+    row[2] = byte_to_float(b0, 2);
+    row[3] = byte_to_float(b0, 3);
+    row[4] = byte_to_float(b1, 0);
+    row[5] = byte_to_float(b1, 1);
+    row[6] = byte_to_float(b1, 2);
+    row[7] = byte_to_float(b1, 3);
+    row[8] = byte_to_float(b2, 0);
+    row[9] = byte_to_float(b2, 1);
+}
+
+// Level-l coordinate of a level-0 keypoint coordinate (src/algorithm.cpp:160-169 then :194 repeatedly):
+// float(k * 2^-(L-1)), then exact doublings.
+__device__ __forceinline__ float level_coord(float k0, int L, int level) {
+    float k = (float)(k0 * (1.0 / (double)(1 << (L - 1))));
+    for (int l = L - 1; l > level; --l) k = (float)((double)k / 0.5);
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Template kernel: I1 patch of every (feature, level).  Item i -> level = L-1 - i / n_total (coarse
+// levels first), feature = i % n_total, so a warp works on neighbouring features of one level.
+// ------------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T)
+klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TemplateSmem<T> &sm = *reinterpret_cast<TemplateSmem<T> *>(smem_raw);
+    constexpr int WS = T + 1;
+    const int tid = threadIdx.x;
+    const int L = pyr.levels;
+    const long long item = (long long)blockIdx.x * T + tid;
+    if (item >= (long long)args.n_total * L) return;
+    const int level = L - 1 - (int)(item / args.n_total);
+    const int f = (int)(item % args.n_total);
+    const int img = f / args.n_per_pair;
+    const LevelView &lv = pyr.lv[level];
+    const float2 k0 = args.kp1[f];
+    const float kx = level_coord(k0.x, L, level), ky = level_coord(k0.y, L, level);
+    float4 *out = reinterpret_cast<float4 *>(args.templates + ((size_t)f * L + level) * kTplStride);
+
+    float xx[G], omx[G], yy[G], omy[G];
+    int ixn = 0, iyn = 0;
+    bool regular = offsets_exact(kx) && offsets_exact(ky);
+    if (regular) {
+        // with (a), float(kx + c) == (double)kx + c exactly: the template grid is the d = 0 grid
+        regular = (grid_axis<false>(kx, 0.0, lv.cols, ixn, xx, omx) | grid_axis<true>(ky, 0.0, lv.rows, iyn, yy, omy)) == 0;
+    }
+    float buf[kTplStride];
+#pragma unroll
+    for (int i = 0; i < kTplStride; ++i) buf[i] = 0.f;
+    if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15);
+    if (regular) {
+        // the 7x7 centre of the 9x9 grid needs window rows iyn+1 .. iyn+8 and columns ixn+1 .. ixn+8
+        const int wx0 = (ixn - 2) & ~15, wy0 = iyn + 1;
+        uint32_t *col = &sm.win[0][tid];
+        stage_own_window<kTplRows, WS>(lv.base[0] + (size_t)img * lv.slot, lv, wx0, wy0, col);
+        const int ox = ixn - wx0;
+        const int sh = (ox & 3) * 8;
+        const uint32_t *wp = col + (ox >> 2) * WS;
+        float rowA[G + 1], rowB[G + 1];
+        load_row10<WS>(wp, 0, sh, rowA);
+#pragma unroll
+        for (int y = 0; y < P; ++y) {
+            load_row10<WS>(wp, y + 1, sh, rowB);
+#pragma unroll
+            for (int x = 0; x < P; ++x)
+                buf[y * P + x] = bilerp(omx[x + 1], xx[x + 1], omy[y + 1], yy[y + 1], rowA[x + 1], rowA[x + 2], rowB[x + 1],
+                                        rowB[x + 2]);
+#pragma unroll
+            for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
+        }
+        buf[kI1Count] = 1.f;  // regularity flag
+    }
+#pragma unroll
+    for (int i = 0; i < kTplStride / 4; ++i) out[i] = make_float4(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solver kernel.
+// ------------------------------------------------------------------------------------------------
 template <int T, int MIN_CTAS>
 __global__ void __launch_bounds__(T, MIN_CTAS)
 klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LaneSmem<T> &sm = *reinterpret_cast<LaneSmem<T> *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int WS = T + 1;  // word stride between consecutive window words of one thread
 
@@ -178,7 +289,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
     const int L = pyr.levels;
     const double scale_top = 1.0 / (double)(1 << (L - 1));
-    uint8_t *tile = sm.scratch[warp];
 
     // ---- per-thread (per-feature) state ----
     int state = ST_FETCH, feat = -1, level = 0, iter = 0;
@@ -189,7 +299,16 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     unsigned iters_packed = 0, nan_count = 0;
     int img = 0;
     int wx0 = 0, wy0 = 0;
-    bool win_ok = false, need_i1 = false;
+    bool need_win = false;
+
+    auto defer_feature = [&](int why) {
+        const int di = atomicAdd(args.defer_count, 1);
+        args.defer_list[di] = feat;
+        atomicAdd(&sm.stats[kStatDeferred], 1u);
+        atomicAdd(&sm.stats[why], 1u);
+        state = ST_FETCH;
+        need_win = false;
+    };
 
     for (;;) {
         // ------------------------------------------------------------------ fetch new features
@@ -224,136 +343,84 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             if (__all_sync(FULL, state == ST_DONE)) break;
         }
 
-        bool defer = false;
-        int defer_why = kStatDeferInexact;
-
-        // ------------------------------------------------------------------ level setup (scalar)
-        if (state == ST_LEVEL) {
-            const bool has_initial = (level == L - 1) ? (args.has_initial != 0) : true;  // :185-189
-            kx = k1.x;
-            ky = k1.y;
-            dx = dy = 0;
-            if (has_initial) {  // :47-50
-                dx = (double)(k2.x - kx);
-                dy = (double)(k2.y - ky);
+        // ------------------------------------------------------------------ batched per-thread set-up
+        {
+            const bool blocked = (state == ST_LEVEL) || (state == ST_RUN && need_win);
+            const int n_blocked = __popc(__ballot_sync(FULL, blocked));
+            const int n_runnable = __popc(__ballot_sync(FULL, state == ST_RUN && !need_win));
+            if (n_blocked > 0 && (n_blocked >= kSetupBatch || n_runnable == 0) && blocked) {
+                const LevelView &lv = pyr.lv[level];
+                bool ok = true;
+                if (state == ST_LEVEL) {
+                    const bool has_initial = (level == L - 1) ? (args.has_initial != 0) : true;  // :185-189
+                    kx = k1.x;
+                    ky = k1.y;
+                    dx = dy = 0;
+                    if (has_initial) {  // :47-50
+                        dx = (double)(k2.x - kx);
+                        dy = (double)(k2.y - ky);
+                    }
+                    iter = 0;
+                    lastCost = 0;
+                    succ = true;
+                    // template patch of this (feature, level): 49 floats + regularity flag
+                    const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)feat * L + level) * kTplStride);
+                    float4 t[kTplStride / 4];
+#pragma unroll
+                    for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
+                    float *ip = &sm.i1[0][tid];
+#pragma unroll
+                    for (int i = 0; i < kTplStride / 4; ++i) {
+                        if (4 * i < kI1Count) ip[(4 * i) * WS] = t[i].x;
+                        if (4 * i + 1 < kI1Count) ip[(4 * i + 1) * WS] = t[i].y;
+                        if (4 * i + 2 < kI1Count) ip[(4 * i + 2) * WS] = t[i].z;
+                        if (4 * i + 3 < kI1Count) ip[(4 * i + 3) * WS] = t[i].w;
+                    }
+                    ok = t[kI1Count / 4].y != 0.f;  // element 49
+                    if (!ok) defer_feature(kStatDeferInexact);
+                }
+                if (ok) {
+                    const double Sx = (double)kx + dx, Sy = (double)ky + dy;
+                    if (!(fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6)) {
+                        defer_feature(kStatDeferRange);
+                    } else {
+                        const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
+                        wx0 = (ixn - 2) & ~15;
+                        wy0 = iyn - 2;
+                        if (!window_in_apron(lv, wx0)) {
+                            defer_feature(kStatDeferRange);
+                        } else {
+                            stage_own_window<kWin2Rows, WS>(lv.base[1] + (size_t)img * lv.slot, lv, wx0, wy0, &sm.win2[0][tid]);
+                            need_win = false;
+                            state = ST_RUN;
+                        }
+                    }
+                }
             }
-            iter = 0;
-            lastCost = 0;
-            succ = true;
-            win_ok = false;
-            need_i1 = true;
-            // (a) kx+c, ky+c exact for c in [LO,HI]: the end of larger magnitude decides
-            const double kxd = (double)kx, kyd = (double)ky;
-            const bool exact = ((double)(kx + (float)LO) == kxd + (double)LO) && ((double)(kx + (float)HI) == kxd + (double)HI) &&
-                               ((double)(ky + (float)LO) == kyd + (double)LO) && ((double)(ky + (float)HI) == kyd + (double)HI);
-            if (!exact) defer = true;
-            state = ST_RUN;
         }
 
         // ------------------------------------------------------------------ grid coordinates
-        const bool live = (state == ST_RUN) && !defer;
-        float xx[G], omx[G], yy[G], omy[G];
+        bool run = (state == ST_RUN) && !need_win;
+        float xx[G], omx[G];
         int ixn = 0, iyn = 0;
-        bool need_win = false;
-        if (live) {
+        if (run) {
             const LevelView &lv = pyr.lv[level];
+            float yy[G], omy[G];
             const int whyx = grid_axis<false>(kx, dx, lv.cols, ixn, xx, omx);
             const int whyy = grid_axis<true>(ky, dy, lv.rows, iyn, yy, omy);
             if (whyx | whyy) {
-                defer = true;
-                defer_why = whyx ? whyx : whyy;
+                defer_feature(whyx ? whyx : whyy);
+                run = false;
+            } else if (!(ixn >= wx0 && ixn + (G + 1) <= wx0 + kWin2Words * 4 && iyn >= wy0 && iyn + (G + 1) <= wy0 + kWin2Rows)) {
+                need_win = true;  // footprint drifted out of the staged window: wait for the next set-up
+                run = false;
             } else {
-                const bool covered = win_ok && ixn >= wx0 && ixn + (G + 1) <= wx0 + kWin2Words * 4 && iyn >= wy0 &&
-                                     iyn + (G + 1) <= wy0 + kWin2Rows;
-                if (!covered) {
-                    wx0 = (ixn - 2) & ~15;
-                    wy0 = iyn - 2;
-                    need_win = true;
-                    win_ok = true;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    sm.wy[2 * g][tid] = omy[g];
+                    sm.wy[2 * g + 1][tid] = yy[g];
                 }
             }
-        }
-
-        if (defer) {
-            const int di = atomicAdd(args.defer_count, 1);
-            args.defer_list[di] = feat;
-            atomicAdd(&sm.stats[kStatDeferred], 1u);
-            atomicAdd(&sm.stats[defer_why], 1u);
-            state = ST_FETCH;
-            need_i1 = false;
-        }
-        const bool run = (state == ST_RUN);
-
-        // ------------------------------------------------------------------ cooperative staging
-        {
-            unsigned pending = __ballot_sync(FULL, run && (need_i1 || need_win));
-            while (pending) {
-                const int j = __ffs(pending) - 1;
-                pending &= pending - 1;
-                const int j_level = __shfl_sync(FULL, level, j);
-                const int j_img = __shfl_sync(FULL, img, j);
-                const int j_flags = __shfl_sync(FULL, (need_i1 ? 1 : 0) | (need_win ? 2 : 0), j);
-                const LevelView &lv = pyr.lv[j_level];
-                const int jt = (tid & ~31) + j;  // the staged thread's column in the interleaved arrays
-                if (j_flags & 1) {
-                    const float jkx = __shfl_sync(FULL, kx, j), jky = __shfl_sync(FULL, ky, j);
-                    const uint8_t *img1 = lv.base[0] + (size_t)j_img * lv.slot;
-                    const int sx0 = max(0, (int)floorf(jkx + (float)LO)) & ~15;
-                    const int sy0 = max(0, (int)floorf(jky + (float)LO));
-                    if (lane < 2 * kScratchRows) {
-                        const int row = sy0 + (lane >> 1), qx = sx0 + 16 * (lane & 1);
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                        if (row < lv.rows && qx + 16 <= lv.pitch)
-                            v = __ldg(reinterpret_cast<const uint4 *>(img1 + (size_t)row * lv.pitch + qx));
-                        *reinterpret_cast<uint4 *>(tile + (lane >> 1) * kScratchW + 16 * (lane & 1)) = v;
-                    }
-                    __syncwarp();
-                    for (int p = lane; p < kI1Count; p += 32) {
-                        const float fx = jkx + (float)(LO + p / P), fy = jky + (float)(LO + p % P);  // :65
-                        sm.i1[p][jt] = sample_staged(tile, sx0, sy0, img1, lv, fx, fy);
-                    }
-                    __syncwarp();
-                }
-                if (j_flags & 2) {
-                    const int jwx = __shfl_sync(FULL, wx0, j), jwy = __shfl_sync(FULL, wy0, j);
-                    const uint8_t *img2 = lv.base[1] + (size_t)j_img * lv.slot;
-                    if (lane < 2 * kWin2Rows) {
-                        const int row = lane >> 1, half = lane & 1;
-                        const int ry = min(max(jwy + row, 0), lv.rows - 1);
-                        const int qx = jwx + 16 * half;
-                        const uint8_t *rp = img2 + (size_t)ry * lv.pitch;
-                        uint4 v;
-                        if (qx >= 0 && qx + 16 <= lv.cols) {
-                            v = __ldg(reinterpret_cast<const uint4 *>(rp + qx));
-                        } else {  // image border: replicate left/right, flat-address wrap pixel at column `cols`
-                            uint32_t w[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t acc = 0;
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) {
-                                    const int n = qx + 4 * q + b;
-                                    uint32_t px;
-                                    if (n == lv.cols)  // data[ry*step + (cols-1) + 1] of algorithm.h:48,53
-                                        px = (uint32_t)fetch_flat(img2, lv, (long long)ry * lv.step + lv.cols);
-                                    else
-                                        px = (uint32_t)__ldg(rp + min(max(n, 0), lv.cols - 1));
-                                    acc |= px << (8 * b);
-                                }
-                                w[q] = acc;
-                            }
-                            v = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                        uint32_t *dst = &sm.win2[row * kWin2Words + half * 4][jt];
-                        dst[0] = v.x;
-                        dst[WS] = v.y;
-                        dst[2 * WS] = v.z;
-                        dst[3 * WS] = v.w;
-                    }
-                }
-                __syncwarp();
-            }
-            need_i1 = false;
         }
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
@@ -363,56 +430,55 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const int sh = (ox & 3) * 8;
             const uint32_t *wp = &sm.win2[(iyn - wy0) * kWin2Words + (ox >> 2)][tid];
             const float *i1p = &sm.i1[0][tid];
+            const float *wyp = &sm.wy[0][tid];
 
             double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
             float rowA[G + 1], rowB[G + 1];
-            float S[3][G];
+            float Sa[G], Sb[G], Sc[G];  // sample rows r-2, r-1, r (rotated by register moves)
 
-            auto load_row = [&](int i, float (&row)[G + 1]) {
-                const uint32_t *p = wp + i * kWin2Words * WS;
-                const uint32_t w0 = p[0], w1 = p[WS], w2 = p[2 * WS], w3 = p[3 * WS];
-                const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh),
-                               b2 = __funnelshift_r(w2, w3, sh);
-                row[0] = byte_to_float(b0, 0);
-                row[1] = byte_to_float(b0, 1);
-                row[2] = byte_to_float(b0, 2);
-                row[3] = byte_to_float(b0, 3);
-                row[4] = byte_to_float(b1, 0);
-                row[5] = byte_to_float(b1, 1);
-                row[6] = byte_to_float(b1, 2);
-                row[7] = byte_to_float(b1, 3);
-                row[8] = byte_to_float(b2, 0);
-                row[9] = byte_to_float(b2, 1);
+            // One grid row of samples: out[g] for g = 0..G-1 from pixel rows rowA (top) / rowB (bottom).
+            auto sample_row = [&](int r, float (&out)[G]) {
+                const float omy_r = wyp[(2 * r) * WS], yy_r = wyp[(2 * r + 1) * WS];
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    out[g] = bilerp(omx[g], xx[g], omy_r, yy_r, rowA[g], rowA[g + 1], rowB[g], rowB[g + 1]);
             };
 
-            load_row(0, rowA);
+            // The row loop is deliberately NOT unrolled: the unrolled pass (1785 SASS instructions) did
+            // not fit the instruction cache and the kernel was fetch-bound (profiles/r01_lane_v1.md).
+            load_row10<WS>(wp, 0, sh, rowA);
+            load_row10<WS>(wp, 1, sh, rowB);
+            sample_row(0, Sa);
 #pragma unroll
-            for (int r = 0; r < G; ++r) {
-                load_row(r + 1, rowB);
+            for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
+            load_row10<WS>(wp, 2, sh, rowB);
+            sample_row(1, Sb);
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    // the four corner samples of the grid are never used
-                    if ((r == 0 || r == G - 1) && (g == 0 || g == G - 1)) continue;
-                    S[r % 3][g] = bilerp(omx[g], xx[g], omy[r], yy[r], rowA[g], rowA[g + 1], rowB[g], rowB[g + 1]);
-                }
+            for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
+#pragma unroll 1
+            for (int r = 2; r < G; ++r) {
+                load_row10<WS>(wp, r + 1, sh, rowB);
+                sample_row(r, Sc);
 #pragma unroll
                 for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
-                if (r >= 2) {
-                    const int y = r - 2;  // patch row (offset LO + y), centre samples live in grid row r-1
+                const float *i1row = i1p + ((r - 2) * P) * WS;  // patch row y = r-2; centre samples = grid row r-1 = Sb
 #pragma unroll
-                    for (int x = 0; x < P; ++x) {
-                        const int g = x + 1;
-                        const float i1v = i1p[(x * P + y) * WS];
-                        const double e = (double)__fadd_rn(i1v, -S[(r - 1) % 3][g]);                       // :65-66
-                        const double gx = (double)__fadd_rn(S[(r - 1) % 3][g + 1], -S[(r - 1) % 3][g - 1]);  // :70-71
-                        const double gy = (double)__fadd_rn(S[r % 3][g], -S[(r - 2) % 3][g]);              // :72-73
-                        sb0 = fma(e, gx, sb0);
-                        sb1 = fma(e, gy, sb1);
-                        sc = fma(e, e, sc);
-                        s00 = fma(gx, gx, s00);
-                        s01 = fma(gx, gy, s01);
-                        s11 = fma(gy, gy, s11);
-                    }
+                for (int x = 0; x < P; ++x) {
+                    const int g = x + 1;
+                    const double e = (double)__fadd_rn(i1row[x * WS], -Sb[g]);  // :65-66
+                    const double gx = (double)__fadd_rn(Sb[g + 1], -Sb[g - 1]);  // :70-71
+                    const double gy = (double)__fadd_rn(Sc[g], -Sa[g]);          // :72-73
+                    sb0 = fma(e, gx, sb0);
+                    sb1 = fma(e, gy, sb1);
+                    sc = fma(e, e, sc);
+                    s00 = fma(gx, gx, s00);
+                    s01 = fma(gx, gy, s01);
+                    s11 = fma(gy, gy, s11);
+                }
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    Sa[g] = Sb[g];
+                    Sb[g] = Sc[g];
                 }
             }
 
@@ -473,6 +539,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
 constexpr int kLaneThreads = 128;
 constexpr int kLaneMinCtas = 2;
+constexpr int kTplThreads = 128;
 
 }  // namespace
 
@@ -480,8 +547,19 @@ bool lane_kernel_supports(const SolverArgs &args) {
     return args.patch_lo == LO && args.patch_hi == HI && !args.inverse && args.max_iters >= 1 && args.max_iters <= 15;
 }
 
+size_t lane_template_bytes(int n_total, int levels) { return (size_t)n_total * levels * kTplStride * sizeof(float); }
+
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
+    {
+        auto kernel = klt_template_kernel<kTplThreads>;
+        const size_t smem = sizeof(TemplateSmem<kTplThreads>);
+        const long long items = (long long)args.n_total * pyr.levels;
+        const int grid = (int)((items + kTplThreads - 1) / kTplThreads);
+        kernel<<<grid, kTplThreads, smem, stream>>>(pyr, args);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
     auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas>;
     const size_t smem = sizeof(LaneSmem<kLaneThreads>);
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -70,6 +70,7 @@ struct lego_klt_batch {
     long long runs = 0;
     int *d_work = nullptr;         // [0] work counter, [1] deferred count (LANE kernel)
     int *d_defer_list = nullptr;   // [B * n_cap]
+    float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
     bool uploaded = false, ran = false, pyramids_valid = false;
     lego_klt_params last_params;
 };
@@ -123,15 +124,15 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
         lv.cols = lc[l];
         lv.rows = lr[l];
         lv.step = (l == 0) ? (int)step : lc[l];
-        pitch[l] = (int)align_up((size_t)lv.step, 16);
+        pitch[l] = kApronL + (int)align_up((size_t)lv.step, 16) + kApronR;
         lv.pitch = pitch[l];
         lv.slot = (unsigned long long)lr[l] * pitch[l];
         for (int s = 0; s < 2; ++s) {
-            off[l][s] = total;
-            total += align_up((size_t)B * lv.slot, 256);
+            off[l][s] = total;  // base = off + kApronL; the pyramid kernel's band copies run 32 bytes past the set
+            total += align_up((size_t)B * lv.slot + 2 * kApronL + 64, 256);
         }
     }
-    total += 256;
+    total += 4096;
     auto cleanup = [&](int code) {
         lego_klt_batch_destroy(b);
         return code;
@@ -141,7 +142,7 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
     e = cudaMemsetAsync(b->d_images, 0, total, ctx->stream);
     if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMemset images: %s", cudaGetErrorString(e)));
     for (int l = 0; l < levels; ++l)
-        for (int s = 0; s < 2; ++s) b->view.lv[l].base[s] = b->d_images + off[l][s];
+        for (int s = 0; s < 2; ++s) b->view.lv[l].base[s] = b->d_images + off[l][s] + kApronL;
 
     const size_t nt = (size_t)B * (size_t)(n > 0 ? n : 1);
     if ((e = cudaMalloc(&b->d_kp1, nt * sizeof(float2))) != cudaSuccess ||
@@ -188,6 +189,7 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
     CU_TRY(cudaEventRecord(ring[0], st));
     CU_TRY(launch_pyramid(b->plan, b->view, st));
+    CU_TRY(launch_aprons(b->view, st));
     b->pyramids_valid = true;
     CU_TRY(cudaEventRecord(b->ev[EV_PYR], st));
     CU_TRY(cudaEventRecord(ring[1], st));
@@ -214,6 +216,7 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     a.work_counter = b->d_work;
     a.defer_count = b->d_work + 1;
     a.defer_list = b->d_defer_list;
+    a.templates = nullptr;
     int kernel = params->kernel;
     if (kernel == LEGO_KLT_KERNEL_AUTO) kernel = lane_kernel_supports(a) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
@@ -223,6 +226,11 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
     } else {
+        if (!b->d_templates) {
+            const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
+            CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
+        }
+        a.templates = b->d_templates;
         CU_TRY(launch_klt_lane(b->view, a, ctx->sm_count, st));
         // features the LANE kernel deferred (border slivers, inexact kx+c, ...) are finished exactly
         a.list = b->d_defer_list;
@@ -388,6 +396,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
             if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
     cudaFree(b->d_work);
     cudaFree(b->d_defer_list);
+    cudaFree(b->d_templates);
     cudaFree(b->d_images);
     cudaFree(b->d_kp1);
     cudaFree(b->d_kp2_init);
@@ -547,6 +556,7 @@ int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int 
     CU_TRY(upload_set(b, 0, ctx->pinned, step));
     CU_TRY(upload_set(b, 1, ctx->pinned, step));
     CU_TRY(launch_pyramid(b->plan, b->view, st));
+    CU_TRY(launch_aprons(b->view, st));
     size_t off = 0;
     for (int l = 0; l < levels; ++l) {
         const LevelView &lv = b->view.lv[l];

@@ -165,7 +165,44 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
     }
 }
 
+// Row aprons: one thread per (level, set, image, row).  Tiny next to the pyramid itself (80-odd bytes
+// per row) and it lets the solver stage windows with unconditional aligned 16-byte loads.
+__global__ void __launch_bounds__(128) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows_total) return;
+    int level = 0, r = t;
+    while (r >= pyr.lv[level].rows * 2 * pyr.n_images) {
+        r -= pyr.lv[level].rows * 2 * pyr.n_images;
+        ++level;
+    }
+    const LevelView &lv = pyr.lv[level];
+    const int row = r % lv.rows;
+    const int k = (r / lv.rows) % pyr.n_images, set = r / (lv.rows * pyr.n_images);
+    uint8_t *img = lv.base[set] + (size_t)k * lv.slot;
+    uint8_t *rp = img + (size_t)row * lv.pitch;
+    const uint32_t first = rp[0], last = rp[lv.cols - 1];
+    // data[row*step + cols] of the reference's flat addressing
+    uint32_t wrap;
+    if (lv.step == lv.cols)
+        wrap = (row + 1 < lv.rows) ? rp[lv.pitch] : 0u;
+    else
+        wrap = rp[lv.cols];  // inside the caller's row padding, which was uploaded with the row
+    const uint4 f4 = make_uint4(first * 0x01010101u, first * 0x01010101u, first * 0x01010101u, first * 0x01010101u);
+    reinterpret_cast<uint4 *>(rp - kApronL)[0] = f4;
+    reinterpret_cast<uint4 *>(rp - kApronL)[1] = f4;
+    rp[lv.cols] = (uint8_t)wrap;
+    for (int c = lv.cols + 1; c < lv.pitch - kApronL; ++c) rp[c] = (uint8_t)last;
+}
+
 }  // namespace
+
+cudaError_t launch_aprons(const PyramidView &pyr, cudaStream_t stream) {
+    int rows_total = 0;
+    for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * 2 * pyr.n_images;
+    if (rows_total <= 0) return cudaSuccess;
+    apron_kernel<<<(rows_total + 127) / 128, 128, 0, stream>>>(pyr, rows_total);
+    return cudaGetLastError();
+}
 
 cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan) {
     *plan = PyramidPlan();
