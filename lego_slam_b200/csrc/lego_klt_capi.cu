@@ -61,6 +61,7 @@ struct lego_klt_batch {
     PyramidView view;
     WarpKernelMaps *maps = nullptr;
     uint8_t *d_images = nullptr;  // all levels, both sets
+    uint8_t *d_tight = nullptr;   // H2D landing buffer: 2 sets of B tight images
     float2 *d_kp1 = nullptr, *d_kp2_init = nullptr, *d_kp2_out = nullptr;
     uint8_t *d_success = nullptr;
     unsigned long long *d_stats = nullptr;
@@ -143,6 +144,8 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
     if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMemset images: %s", cudaGetErrorString(e)));
     for (int l = 0; l < levels; ++l)
         for (int s = 0; s < 2; ++s) b->view.lv[l].base[s] = b->d_images + off[l][s] + kApronL;
+    e = cudaMalloc(&b->d_tight, 2 * ((size_t)B * rows * step + 256));
+    if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMalloc landing buffer: %s", cudaGetErrorString(e)));
 
     const size_t nt = (size_t)B * (size_t)(n > 0 ? n : 1);
     if ((e = cudaMalloc(&b->d_kp1, nt * sizeof(float2))) != cudaSuccess ||
@@ -171,9 +174,12 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
 
 // H2D of level 0 of one image set: rows of `step` bytes into the pitched device layout.
 cudaError_t upload_set(lego_klt_batch *b, int set, const uint8_t *src, size_t src_step) {
-    const LevelView &l0 = b->view.lv[0];
-    return cudaMemcpy2DAsync(l0.base[set], (size_t)l0.pitch, src, src_step, src_step,
-                             (size_t)b->B * (size_t)b->rows, cudaMemcpyHostToDevice, b->ctx->stream);
+    (void)src_step;
+    const size_t bytes = (size_t)b->B * b->rows * b->step;
+    uint8_t *landing = b->d_tight + (size_t)set * (bytes + 256);
+    cudaError_t e = cudaMemcpyAsync(landing, src, bytes, cudaMemcpyHostToDevice, b->ctx->stream);
+    if (e != cudaSuccess) return e;
+    return launch_ingest(landing, b->view.lv[0], set, b->B, b->ctx->stream);
 }
 
 int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
@@ -398,6 +404,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     cudaFree(b->d_defer_list);
     cudaFree(b->d_templates);
     cudaFree(b->d_images);
+    cudaFree(b->d_tight);
     cudaFree(b->d_kp1);
     cudaFree(b->d_kp2_init);
     cudaFree(b->d_kp2_out);

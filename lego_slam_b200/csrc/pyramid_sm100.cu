@@ -194,7 +194,40 @@ __global__ void __launch_bounds__(128) apron_kernel(const __grid_constant__ Pyra
     for (int c = lv.cols + 1; c < lv.pitch - kApronL; ++c) rp[c] = (uint8_t)last;
 }
 
+// Ingest: level 0 arrives from the host as tight rows (`step` bytes each, arbitrary alignment -- KITTI's
+// 1241 is odd); a strided cudaMemcpy2D into the pitched layout ran at ~9 GB/s, a plain copy runs at PCIe
+// speed, so rows are re-pitched on the device.  One warp per row chunk: aligned 4-byte loads, funnel
+// shift by the row's misalignment, aligned 4-byte stores.
+__global__ void __launch_bounds__(256)
+ingest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst_base, int step, int pitch, long long n_rows,
+              int rows_per_image, unsigned long long slot) {
+    const int words = (step + 3) >> 2;
+    const long long total = n_rows * words;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / words;
+        const int w = (int)(i - row * words);
+        const size_t s = (size_t)row * step + 4 * (size_t)w;      // byte offset of this word in the tight buffer
+        const size_t sa = s & ~(size_t)3;
+        const int sh = (int)(s & 3) * 8;
+        const uint32_t lo = *reinterpret_cast<const uint32_t *>(src + sa);
+        const uint32_t hi = sh ? *reinterpret_cast<const uint32_t *>(src + sa + 4) : 0u;
+        const long long img = row / rows_per_image;
+        const int r = (int)(row - img * rows_per_image);
+        *reinterpret_cast<uint32_t *>(dst_base + (size_t)img * slot + (size_t)r * pitch + 4 * (size_t)w) =
+            __funnelshift_r(lo, hi, sh);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int n_images, cudaStream_t stream) {
+    const long long n_rows = (long long)n_images * l0.rows;
+    if (n_rows <= 0) return cudaSuccess;
+    const long long total = n_rows * ((l0.step + 3) >> 2);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    ingest_kernel<<<grid, 256, 0, stream>>>(tight, l0.base[set], l0.step, l0.pitch, n_rows, l0.rows, l0.slot);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_aprons(const PyramidView &pyr, cudaStream_t stream) {
     int rows_total = 0;
