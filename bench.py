@@ -253,6 +253,7 @@ def run_ours(args):
     _, _, st = batch.download(kp2_io, succ)
     iters = [int(v) for v in st.gn_iters][:LEVELS]
     slow, deferred, n_success = int(st.n_slow_path), int(st.n_deferred), int(st.n_success)
+    defer_reason = [int(v) for v in st.defer_reason]
 
     # ---------------- end to end: host buffers -> lego_klt_track_batched -> host buffers ----------------
     for _ in range(min(args.warmup, 3)):
@@ -335,7 +336,7 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": ms_pyr},
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "solver": {"n_success": n_success, "n_slow_path_passes": slow, "n_deferred_features": deferred,
+        "solver": {"n_success": n_success, "n_slow_path_passes": slow, "n_deferred_features": deferred, "defer_reason[inexact,margin,nominal,range]": defer_reason,
                    "kernel": {0: "auto (lane + warp for deferred)", 1: "exact", 2: "warp", 3: "lane"}[int(args.kernel)]},
     }
     print(json.dumps(line), flush=True)

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblego_klt.so")
+LIB_PATH = os.environ.get("LEGO_KLT_LIB") or os.path.join(HERE, "liblego_klt.so")
 MAX_LEVELS = 8
 
 # names every build must export (tests/test_abi.py checks them against include/lego_klt.h)

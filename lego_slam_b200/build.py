@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "liblego_klt.so")
+LIB = os.environ.get("LEGO_KLT_LIB") or os.path.join(HERE, "liblego_klt.so")  # override: tuning experiments only
 SOURCES = ["lego_klt_capi.cu", "pyramid_sm100.cu", "klt_solver_exact.cu", "klt_solver_warp.cu",
            "klt_solver_lane.cu"]
 NVCC_FLAGS = [
@@ -41,7 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    defs = os.environ.get("LEGO_KLT_NVCC_DEFS", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout + res.stderr)

@@ -83,6 +83,7 @@ struct SolverArgs {
     const int *list_count;
     // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
     float *templates;         // [n_total][levels][52]: I1 patches + regularity flag (template kernel)
+    int *feat_flag;           // [n_total]: 1 = feature handed to the warp kernel by the template kernel
     int *work_counter;
     int *defer_list;
     int *defer_count;

@@ -49,10 +49,12 @@ void warp_maps_destroy(WarpKernelMaps *maps);
 cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, const SolverArgs &args,
                             int sm_count, cudaStream_t stream);
 
-// LANE kernel (klt_solver_lane.cu): thread per feature, 7x7 forward only; defers irregular features to
-// args.defer_list (to be finished by launch_klt_warp with args.list = defer_list).
+// LANE path (klt_solver_lane.cu), 7x7 forward only: launch_klt_template computes the I1 patches and puts
+// irregular features on args.defer_list (solve them with launch_klt_warp, args.list = defer_list, which may
+// run concurrently with launch_klt_lane: the two touch disjoint features).
 bool lane_kernel_supports(const SolverArgs &args);
 size_t lane_template_bytes(int n_total, int levels);
+cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
 
 }  // namespace legoklt

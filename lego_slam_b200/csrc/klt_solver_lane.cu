@@ -51,7 +51,16 @@ constexpr int kWin2Total = kWin2Rows * kWin2Words;            // 112 words
 constexpr int kTplRows = 8;                                   // img1 window rows in the template kernel
 constexpr int kI1Count = P * P;                               // 49 floats, index y*P + x
 constexpr int kTplStride = 52;                                // floats per (feature, level): 49 + flag + pad
-constexpr int kSetupBatch = 10;                               // blocked threads per warp that trigger set-up
+#ifndef LANE_BATCH
+#define LANE_BATCH 10
+#endif
+#ifndef LANE_T
+#define LANE_T 128
+#endif
+#ifndef LANE_CTAS
+#define LANE_CTAS 2
+#endif
+constexpr int kSetupBatch = LANE_BATCH;                       // blocked threads per warp that trigger set-up
 
 enum : int { ST_FETCH = 0, ST_LEVEL = 1, ST_RUN = 2, ST_DONE = 3 };
 
@@ -205,6 +214,41 @@ __device__ __forceinline__ void load_row10(const uint32_t *wp, int i, int sh, fl
     row[9] = byte_to_float(b2, 1);
 }
 
+__device__ __noinline__ float sample_flat_cold(const uint8_t *img, const LevelView &lv, float x, float y) {
+    return sample_flat(img, lv, x, y);
+}
+
+// Exact per-pixel pass in the reference formulation (src/algorithm.cpp:63-88: 5 GetPixelValue per pixel,
+// flat addressing), for the rare pass whose shared sample grid cannot be proven bit-identical.  Cold code:
+// kept out of line so that the hot loop stays inside the instruction cache.
+__device__ __noinline__ void exact_pass(const uint8_t *img2, const LevelView &lv, const float *i1p, int ws, float kx,
+                                        float ky, double dx, double dy, double (&sums)[6]) {
+    double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
+#pragma unroll 1
+    for (int p = 0; p < kI1Count; ++p) {
+        const int y = p / P, x = p - y * P;
+        const float fx = kx + (float)(LO + x), fy = ky + (float)(LO + y);
+        const double cx = (double)fx + dx, cy = (double)fy + dy;
+        const double e = (double)(i1p[p * ws] - sample_flat_cold(img2, lv, (float)cx, (float)cy));
+        const double gx = (double)(sample_flat_cold(img2, lv, (float)(cx + 1), (float)cy) -
+                                   sample_flat_cold(img2, lv, (float)(cx - 1), (float)cy));
+        const double gy = (double)(sample_flat_cold(img2, lv, (float)cx, (float)(cy + 1)) -
+                                   sample_flat_cold(img2, lv, (float)cx, (float)(cy - 1)));
+        sb0 = fma(e, gx, sb0);
+        sb1 = fma(e, gy, sb1);
+        sc = fma(e, e, sc);
+        s00 = fma(gx, gx, s00);
+        s01 = fma(gx, gy, s01);
+        s11 = fma(gy, gy, s11);
+    }
+    sums[0] = sb0;
+    sums[1] = sb1;
+    sums[2] = sc;
+    sums[3] = s00;
+    sums[4] = s01;
+    sums[5] = s11;
+}
+
 // Level-l coordinate of a level-0 keypoint coordinate (src/algorithm.cpp:160-169 then :194 repeatedly):
 // float(k * 2^-(L-1)), then exact doublings.
 __device__ __forceinline__ float level_coord(float k0, int L, int level) {
@@ -246,6 +290,14 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 #pragma unroll
     for (int i = 0; i < kTplStride; ++i) buf[i] = 0.f;
     if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15);
+    if (!regular) {
+        // the whole feature goes to the exact warp kernel (which runs concurrently with the lane kernel)
+        if (atomicExch(&args.feat_flag[f], 1) == 0) {
+            args.defer_list[atomicAdd(args.defer_count, 1)] = f;
+            atomicAdd(&args.stats[kStatDeferred], 1ull);
+            atomicAdd(&args.stats[kStatDeferInexact], 1ull);
+        }
+    }
     if (regular) {
         // the 7x7 centre of the 9x9 grid needs window rows iyn+1 .. iyn+8 and columns ixn+1 .. ixn+8
         const int wx0 = (ixn - 2) & ~15, wy0 = iyn + 1;
@@ -299,16 +351,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     unsigned iters_packed = 0, nan_count = 0;
     int img = 0;
     int wx0 = 0, wy0 = 0;
-    bool need_win = false;
-
-    auto defer_feature = [&](int why) {
-        const int di = atomicAdd(args.defer_count, 1);
-        args.defer_list[di] = feat;
-        atomicAdd(&sm.stats[kStatDeferred], 1u);
-        atomicAdd(&sm.stats[why], 1u);
-        state = ST_FETCH;
-        need_win = false;
-    };
+    bool need_win = false, no_window = false;
 
     for (;;) {
         // ------------------------------------------------------------------ fetch new features
@@ -321,7 +364,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 base = __shfl_sync(FULL, base, leader);
                 if (state == ST_FETCH) {
                     const int id = base + __popc(m & ((1u << lane) - 1u));
-                    if (id < args.n_total) {
+                    if (id < args.n_total && args.feat_flag[id] != 0) {
+                        // irregular template (kx+c inexact, ...): the warp kernel owns this feature
+                    } else if (id < args.n_total) {
                         feat = id;
                         img = id / args.n_per_pair;
                         k1 = args.kp1[id];
@@ -350,7 +395,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const int n_runnable = __popc(__ballot_sync(FULL, state == ST_RUN && !need_win));
             if (n_blocked > 0 && (n_blocked >= kSetupBatch || n_runnable == 0) && blocked) {
                 const LevelView &lv = pyr.lv[level];
-                bool ok = true;
                 if (state == ST_LEVEL) {
                     const bool has_initial = (level == L - 1) ? (args.has_initial != 0) : true;  // :185-189
                     kx = k1.x;
@@ -363,7 +407,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     iter = 0;
                     lastCost = 0;
                     succ = true;
-                    // template patch of this (feature, level): 49 floats + regularity flag
+                    // template patch of this (feature, level): 49 floats (+ regularity flag, checked at fetch)
                     const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)feat * L + level) * kTplStride);
                     float4 t[kTplStride / 4];
 #pragma unroll
@@ -376,31 +420,26 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         if (4 * i + 2 < kI1Count) ip[(4 * i + 2) * WS] = t[i].z;
                         if (4 * i + 3 < kI1Count) ip[(4 * i + 3) * WS] = t[i].w;
                     }
-                    ok = t[kI1Count / 4].y != 0.f;  // element 49
-                    if (!ok) defer_feature(kStatDeferInexact);
                 }
-                if (ok) {
-                    const double Sx = (double)kx + dx, Sy = (double)ky + dy;
-                    if (!(fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6)) {
-                        defer_feature(kStatDeferRange);
-                    } else {
-                        const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
-                        wx0 = (ixn - 2) & ~15;
-                        wy0 = iyn - 2;
-                        if (!window_in_apron(lv, wx0)) {
-                            defer_feature(kStatDeferRange);
-                        } else {
-                            stage_own_window<kWin2Rows, WS>(lv.base[1] + (size_t)img * lv.slot, lv, wx0, wy0, &sm.win2[0][tid]);
-                            need_win = false;
-                            state = ST_RUN;
-                        }
+                const double Sx = (double)kx + dx, Sy = (double)ky + dy;
+                no_window = true;  // estimate far outside the image / its apron: exact per-pixel passes
+                if (fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6) {
+                    const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
+                    wx0 = (ixn - 2) & ~15;
+                    wy0 = iyn - 2;
+                    if (window_in_apron(lv, wx0)) {
+                        stage_own_window<kWin2Rows, WS>(lv.base[1] + (size_t)img * lv.slot, lv, wx0, wy0, &sm.win2[0][tid]);
+                        no_window = false;
                     }
                 }
+                need_win = false;
+                state = ST_RUN;
             }
         }
 
         // ------------------------------------------------------------------ grid coordinates
         bool run = (state == ST_RUN) && !need_win;
+        bool fast = false;
         float xx[G], omx[G];
         int ixn = 0, iyn = 0;
         if (run) {
@@ -409,12 +448,19 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const int whyx = grid_axis<false>(kx, dx, lv.cols, ixn, xx, omx);
             const int whyy = grid_axis<true>(ky, dy, lv.rows, iyn, yy, omy);
             if (whyx | whyy) {
-                defer_feature(whyx ? whyx : whyy);
-                run = false;
+                // cannot prove the shared grid bit-identical for this pass (rare): exact per-pixel pass
+                atomicAdd(&sm.stats[kStatSlowPath], 1u);
             } else if (!(ixn >= wx0 && ixn + (G + 1) <= wx0 + kWin2Words * 4 && iyn >= wy0 && iyn + (G + 1) <= wy0 + kWin2Rows)) {
-                need_win = true;  // footprint drifted out of the staged window: wait for the next set-up
-                run = false;
+                if (no_window) {
+                    atomicAdd(&sm.stats[kStatSlowPath], 1u);
+                } else {
+                    need_win = true;  // footprint drifted out of the staged window: wait for the next set-up
+                    run = false;
+                }
+            } else if (no_window) {
+                atomicAdd(&sm.stats[kStatSlowPath], 1u);
             } else {
+                fast = true;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     sm.wy[2 * g][tid] = omy[g];
@@ -426,13 +472,22 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         // ------------------------------------------------------------------ one Gauss-Newton pass
         if (run) {
             const LevelView &lv = pyr.lv[level];
+            const float *i1p = &sm.i1[0][tid];
+            double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
+            if (!fast) {
+                double sums[6];
+                exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, WS, kx, ky, dx, dy, sums);
+                sb0 = sums[0];
+                sb1 = sums[1];
+                sc = sums[2];
+                s00 = sums[3];
+                s01 = sums[4];
+                s11 = sums[5];
+            } else {
             const int ox = ixn - wx0;
             const int sh = (ox & 3) * 8;
             const uint32_t *wp = &sm.win2[(iyn - wy0) * kWin2Words + (ox >> 2)][tid];
-            const float *i1p = &sm.i1[0][tid];
             const float *wyp = &sm.wy[0][tid];
-
-            double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
             float rowA[G + 1], rowB[G + 1];
             float Sa[G], Sb[G], Sc[G];  // sample rows r-2, r-1, r (rotated by register moves)
 
@@ -480,6 +535,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     Sa[g] = Sb[g];
                     Sb[g] = Sc[g];
                 }
+            }
+
             }
 
             // J = -0.5 * g: rescaling the sums by exact powers of two commutes with every rounding
@@ -537,8 +594,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     if (tid < kStatCount && sm.stats[tid]) atomicAdd(&args.stats[tid], (unsigned long long)sm.stats[tid]);
 }
 
-constexpr int kLaneThreads = 128;
-constexpr int kLaneMinCtas = 2;
+constexpr int kLaneThreads = LANE_T;
+constexpr int kLaneMinCtas = LANE_CTAS;
 constexpr int kTplThreads = 128;
 
 }  // namespace
@@ -549,17 +606,18 @@ bool lane_kernel_supports(const SolverArgs &args) {
 
 size_t lane_template_bytes(int n_total, int levels) { return (size_t)n_total * levels * kTplStride * sizeof(float); }
 
+cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream) {
+    if (args.n_total <= 0) return cudaSuccess;
+    auto kernel = klt_template_kernel<kTplThreads>;
+    const size_t smem = sizeof(TemplateSmem<kTplThreads>);
+    const long long items = (long long)args.n_total * pyr.levels;
+    const int grid = (int)((items + kTplThreads - 1) / kTplThreads);
+    kernel<<<grid, kTplThreads, smem, stream>>>(pyr, args);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
-    {
-        auto kernel = klt_template_kernel<kTplThreads>;
-        const size_t smem = sizeof(TemplateSmem<kTplThreads>);
-        const long long items = (long long)args.n_total * pyr.levels;
-        const int grid = (int)((items + kTplThreads - 1) / kTplThreads);
-        kernel<<<grid, kTplThreads, smem, stream>>>(pyr, args);
-        cudaError_t err = cudaGetLastError();
-        if (err != cudaSuccess) return err;
-    }
     auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas>;
     const size_t smem = sizeof(LaneSmem<kLaneThreads>);
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -72,6 +72,9 @@ struct lego_klt_batch {
     int *d_work = nullptr;         // [0] work counter, [1] deferred count (LANE kernel)
     int *d_defer_list = nullptr;   // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
+    int *d_feat_flag = nullptr;    // LANE path: per-feature 'handed to the warp kernel' flag
+    cudaStream_t side = nullptr;   // deferred features run here, concurrently with the lane kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool uploaded = false, ran = false, pyramids_valid = false;
     lego_klt_params last_params;
 };
@@ -144,7 +147,7 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
     if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMemset images: %s", cudaGetErrorString(e)));
     for (int l = 0; l < levels; ++l)
         for (int s = 0; s < 2; ++s) b->view.lv[l].base[s] = b->d_images + off[l][s] + kApronL;
-    e = cudaMalloc(&b->d_tight, 2 * ((size_t)B * rows * step + 256));
+    e = cudaMalloc(&b->d_tight, 2 * align_up((size_t)B * rows * step + 256, 256));
     if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMalloc landing buffer: %s", cudaGetErrorString(e)));
 
     const size_t nt = (size_t)B * (size_t)(n > 0 ? n : 1);
@@ -176,7 +179,7 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
 cudaError_t upload_set(lego_klt_batch *b, int set, const uint8_t *src, size_t src_step) {
     (void)src_step;
     const size_t bytes = (size_t)b->B * b->rows * b->step;
-    uint8_t *landing = b->d_tight + (size_t)set * (bytes + 256);
+    uint8_t *landing = b->d_tight + (size_t)set * align_up(bytes + 256, 256);
     cudaError_t e = cudaMemcpyAsync(landing, src, bytes, cudaMemcpyHostToDevice, b->ctx->stream);
     if (e != cudaSuccess) return e;
     return launch_ingest(landing, b->view.lv[0], set, b->B, b->ctx->stream);
@@ -223,6 +226,7 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     a.defer_count = b->d_work + 1;
     a.defer_list = b->d_defer_list;
     a.templates = nullptr;
+    a.feat_flag = nullptr;
     int kernel = params->kernel;
     if (kernel == LEGO_KLT_KERNEL_AUTO) kernel = lane_kernel_supports(a) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
@@ -232,16 +236,29 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
     } else {
+        const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
         if (!b->d_templates) {
-            const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
             CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
+            CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
+            CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
         }
         a.templates = b->d_templates;
+        a.feat_flag = b->d_feat_flag;
+        CU_TRY(cudaMemsetAsync(b->d_feat_flag, 0, (size_t)a.n_total * sizeof(int), st));
+        CU_TRY(launch_klt_template(b->view, a, st));
+        // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
+        // kernel on a second stream while the lane kernel solves the rest
+        CU_TRY(cudaEventRecord(b->ev_fork, st));
+        CU_TRY(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
+        SolverArgs aw = a;
+        aw.list = b->d_defer_list;
+        aw.list_count = b->d_work + 1;
+        CU_TRY(launch_klt_warp(b->view, b->maps, aw, ctx->sm_count, b->side));
+        CU_TRY(cudaEventRecord(b->ev_join, b->side));
         CU_TRY(launch_klt_lane(b->view, a, ctx->sm_count, st));
-        // features the LANE kernel deferred (border slivers, inexact kx+c, ...) are finished exactly
-        a.list = b->d_defer_list;
-        a.list_count = b->d_work + 1;
-        CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
+        CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
     }
     CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
     CU_TRY(cudaEventRecord(ring[2], st));
@@ -403,6 +420,10 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     cudaFree(b->d_work);
     cudaFree(b->d_defer_list);
     cudaFree(b->d_templates);
+    cudaFree(b->d_feat_flag);
+    if (b->side) cudaStreamDestroy(b->side);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     cudaFree(b->d_images);
     cudaFree(b->d_tight);
     cudaFree(b->d_kp1);

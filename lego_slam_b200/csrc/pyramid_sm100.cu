@@ -121,37 +121,54 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
         uint8_t *D = smem + kp.smem_off[k];
         const ResizeTables &tb = kp.tab[k];
         const int nr = hi[k] - lo[k];
-        const int ng = ld.pitch >> 2;  // 4-pixel groups per row (covers the padded pitch)
+        const int ng = (ld.cols + 3) >> 2;  // 4-pixel groups per row
         const int src_last = ls.cols - 1;
-        for (int i = tid; i < nr * ng; i += nthreads) {
-            const int r = i / ng, g = i - r * ng;
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+        // a warp owns whole rows (row tables read once per row), its lanes stride over the 4-pixel groups
+        for (int r = warp; r < nr; r += nwarps) {
             const int R = lo[k] + r;
             const int yo = __ldg(tb.yofs + R);
             const short2 b = __ldg(tb.ycoef + R);
+            const int b0 = b.x, b1 = b.y;
             const uint8_t *s0 = S + (d_clip(yo, ls.rows) - lo[k - 1]) * ls.pitch;
             const uint8_t *s1 = S + (d_clip(yo + 1, ls.rows) - lo[k - 1]) * ls.pitch;
-            uint32_t packed = 0;
-            const int c0 = 4 * g;
-            if (c0 < ld.cols) {
-                const int4 xo = __ldg(reinterpret_cast<const int4 *>(tb.xofs) + g);
-                const uint4 xc = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
-                const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
-                const uint32_t cs[4] = {xc.x, xc.y, xc.z, xc.w};
+            uint32_t *drow = reinterpret_cast<uint32_t *>(D + r * ld.pitch);
+            for (int g = lane; g < ng; g += 32) {
+                const int c0 = 4 * g;
+                uint32_t packed = 0;
+                if (tb.x_exact2 && c0 + 3 < ld.cols) {
+                    // exact halving in x: taps 2c, 2c+1 with weights 1024/1024 -> 8 consecutive source bytes
+                    const uint2 t0 = *reinterpret_cast<const uint2 *>(s0 + 2 * c0);
+                    const uint2 t1 = *reinterpret_cast<const uint2 *>(s1 + 2 * c0);
+                    const uint32_t w0[2] = {t0.x, t0.y}, w1[2] = {t1.x, t1.y};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (c0 + j < ld.cols) {
-                        const int sx = xs[j];
-                        const int sx1 = min(sx + 1, src_last);
-                        const int a0 = (int)(short)(cs[j] & 0xffffu), a1 = (int)(short)(cs[j] >> 16);
-                        const int h0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1;
-                        const int h1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
-                        int v = ((((int)b.x * (h0 >> 4)) >> 16) + (((int)b.y * (h1 >> 4)) >> 16) + 2) >> 2;
-                        v = min(max(v, 0), 255);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t p0 = w0[j >> 1] >> (16 * (j & 1)), p1 = w1[j >> 1] >> (16 * (j & 1));
+                        const int h0 = (int)((p0 & 0xffu) + ((p0 >> 8) & 0xffu)) << 10;
+                        const int h1 = (int)((p1 & 0xffu) + ((p1 >> 8) & 0xffu)) << 10;
+                        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
                         packed |= (uint32_t)v << (8 * j);
                     }
+                } else {
+                    const int4 xo = __ldg(reinterpret_cast<const int4 *>(tb.xofs) + g);
+                    const uint4 xc = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
+                    const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
+                    const uint32_t cs[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (c0 + j < ld.cols) {
+                            const int sx = xs[j];
+                            const int sx1 = min(sx + 1, src_last);
+                            const int a0 = (int)(short)(cs[j] & 0xffffu), a1 = (int)(short)(cs[j] >> 16);
+                            const int h0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1;
+                            const int h1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
+                            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                            packed |= (uint32_t)v << (8 * j);
+                        }
+                    }
                 }
+                drow[g] = packed;
             }
-            *reinterpret_cast<uint32_t *>(D + r * ld.pitch + c0) = packed;
         }
         __syncthreads();
         // Write this level's band back: contiguous, 16-byte vectors.
@@ -165,10 +182,11 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
     }
 }
 
-// Row aprons: one thread per (level, set, image, row).  Tiny next to the pyramid itself (80-odd bytes
-// per row) and it lets the solver stage windows with unconditional aligned 16-byte loads.
-__global__ void __launch_bounds__(128) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// Row aprons: one WARP per (level, set, image, row): 32 + ~50 bytes per row, lanes write them in parallel.
+// Tiny next to the pyramid itself, and it lets the solver stage windows with unconditional aligned loads.
+__global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= rows_total) return;
     int level = 0, r = t;
     while (r >= pyr.lv[level].rows * 2 * pyr.n_images) {
@@ -178,8 +196,7 @@ __global__ void __launch_bounds__(128) apron_kernel(const __grid_constant__ Pyra
     const LevelView &lv = pyr.lv[level];
     const int row = r % lv.rows;
     const int k = (r / lv.rows) % pyr.n_images, set = r / (lv.rows * pyr.n_images);
-    uint8_t *img = lv.base[set] + (size_t)k * lv.slot;
-    uint8_t *rp = img + (size_t)row * lv.pitch;
+    uint8_t *rp = lv.base[set] + (size_t)k * lv.slot + (size_t)row * lv.pitch;
     const uint32_t first = rp[0], last = rp[lv.cols - 1];
     // data[row*step + cols] of the reference's flat addressing
     uint32_t wrap;
@@ -187,11 +204,8 @@ __global__ void __launch_bounds__(128) apron_kernel(const __grid_constant__ Pyra
         wrap = (row + 1 < lv.rows) ? rp[lv.pitch] : 0u;
     else
         wrap = rp[lv.cols];  // inside the caller's row padding, which was uploaded with the row
-    const uint4 f4 = make_uint4(first * 0x01010101u, first * 0x01010101u, first * 0x01010101u, first * 0x01010101u);
-    reinterpret_cast<uint4 *>(rp - kApronL)[0] = f4;
-    reinterpret_cast<uint4 *>(rp - kApronL)[1] = f4;
-    rp[lv.cols] = (uint8_t)wrap;
-    for (int c = lv.cols + 1; c < lv.pitch - kApronL; ++c) rp[c] = (uint8_t)last;
+    if (lane < kApronL / 4) reinterpret_cast<uint32_t *>(rp - kApronL)[lane] = first * 0x01010101u;
+    for (int c = lv.cols + lane; c < lv.pitch - kApronL; c += 32) rp[c] = (uint8_t)(c == lv.cols ? wrap : last);
 }
 
 // Ingest: level 0 arrives from the host as tight rows (`step` bytes each, arbitrary alignment -- KITTI's
@@ -233,7 +247,7 @@ cudaError_t launch_aprons(const PyramidView &pyr, cudaStream_t stream) {
     int rows_total = 0;
     for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * 2 * pyr.n_images;
     if (rows_total <= 0) return cudaSuccess;
-    apron_kernel<<<(rows_total + 127) / 128, 128, 0, stream>>>(pyr, rows_total);
+    apron_kernel<<<(rows_total + 7) / 8, 256, 0, stream>>>(pyr, rows_total);
     return cudaGetLastError();
 }
 
