@@ -1,0 +1,119 @@
+// algorithm_shim.h -- C++ drop-in for the reference's KLT entry points, on top of the C ABI.
+//
+// Same names, same signatures, same argument meaning as
+//   /root/reference include/legoslam/algorithm.h:123-128   legoslam::LKOpticalFlow1Layer
+//   /root/reference include/legoslam/algorithm.h:131-136   legoslam::LKOpticalFlow4Layer
+// so the two call sites (src/frontend_g2o.cpp:473, :515; identical in src/frontend_lego.cpp:486,528)
+// compile unchanged when this header is included instead of the reference's definitions:
+//
+//     #include <opencv2/core.hpp>                 // cv::Mat, cv::KeyPoint (any OpenCV >= 3.2)
+//     #include "legoslam_gpu/algorithm_shim.h"
+//     ...
+//     legoslam::LKOpticalFlow4Layer(last_frame_->left_img_, current_frame_->left_img_,
+//                                   kps_last, kps_current, status, false, true);
+//
+// Header only; needs liblego_klt.so (include/lego_klt.h) at link time.  It is templated on the matrix /
+// keypoint types only so that it can be compiled and tested without OpenCV headers (tests/shim/ uses
+// look-alike PODs); with OpenCV present the non-template overloads at the bottom bind cv::Mat /
+// cv::KeyPoint.
+//
+// Behaviour kept from the reference (src/algorithm.cpp):
+//   * kp2 and success are resized to kp1.size() (:17-18, :158); kp2[i].pt is overwritten, every other
+//     cv::KeyPoint field of kp2[i] (size = 7 at the call sites, angle, ...) is preserved (:121);
+//   * has_initial == false ignores the incoming kp2 positions on the coarsest level (:47-50, :185-189);
+//   * inverse == true is the reference's inverse mode including its stale-Jacobian behaviour.
+// Differences: errors are reported (std::runtime_error with the library's message) instead of being
+// impossible / UB; nothing is printed on NaN (the reference prints "Update is NaN or INF.", :97).
+#ifndef LEGOSLAM_GPU_ALGORITHM_SHIM_H
+#define LEGOSLAM_GPU_ALGORITHM_SHIM_H
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../lego_klt.h"
+
+namespace legoslam {
+namespace gpu {
+
+// One context per calling thread (the reference calls the KLT synchronously from the frontend thread).
+inline lego_klt_ctx *thread_context(int device = 0) {
+    struct Holder {
+        lego_klt_ctx *ctx = nullptr;
+        ~Holder() { lego_klt_destroy(ctx); }
+    };
+    static thread_local Holder holder;
+    if (!holder.ctx) {
+        int rc = lego_klt_create(device, &holder.ctx);
+        if (rc != LEGO_KLT_OK) throw std::runtime_error(std::string("lego_klt_create: ") + lego_klt_last_error());
+    }
+    return holder.ctx;
+}
+
+// MatT needs: data (uint8_t*), cols, rows, step (convertible to size_t), channels()/type are the
+// caller's business (the reference passes CV_8UC1).  KeyPointT needs: pt.x, pt.y (float).
+template <class MatT, class KeyPointT>
+void LKOpticalFlowNLayer(const MatT &img1, const MatT &img2, const std::vector<KeyPointT> &kp1,
+                         std::vector<KeyPointT> &kp2, std::vector<bool> &success, bool inverse, bool has_initial,
+                         int levels) {
+    const size_t n = kp1.size();
+    kp2.resize(n);       // src/algorithm.cpp:17,158
+    success.resize(n);   // :18
+    if (img1.cols != img2.cols || img1.rows != img2.rows || (size_t)img1.step != (size_t)img2.step)
+        throw std::runtime_error("LKOpticalFlow: img1 and img2 must have the same size and step");
+    std::vector<float> a(2 * n), b(2 * n);
+    std::vector<uint8_t> ok(n ? n : 1);
+    for (size_t i = 0; i < n; ++i) {
+        a[2 * i] = kp1[i].pt.x;
+        a[2 * i + 1] = kp1[i].pt.y;
+        b[2 * i] = kp2[i].pt.x;
+        b[2 * i + 1] = kp2[i].pt.y;
+    }
+    lego_klt_params p;
+    lego_klt_default_params(&p);
+    p.levels = levels;
+    p.inverse = inverse ? 1 : 0;
+    p.has_initial = has_initial ? 1 : 0;
+    int rc = lego_klt_track(thread_context(), &p, img1.data, img2.data, img1.cols, img1.rows, (size_t)img1.step,
+                            a.data(), b.data(), ok.data(), (int)n, nullptr);
+    if (rc != LEGO_KLT_OK) throw std::runtime_error(std::string("lego_klt_track: ") + lego_klt_last_error());
+    for (size_t i = 0; i < n; ++i) {
+        kp2[i].pt.x = b[2 * i];   // :121 -- only pt changes
+        kp2[i].pt.y = b[2 * i + 1];
+        success[i] = ok[i] != 0;  // :119,123
+    }
+}
+
+}  // namespace gpu
+
+// ---- the reference's entry points -------------------------------------------------------------------
+template <class MatT, class KeyPointT>
+void LKOpticalFlow1Layer(const MatT &img1, const MatT &img2, const std::vector<KeyPointT> &kp1,
+                         std::vector<KeyPointT> &kp2, std::vector<bool> &success, bool inverse = false,
+                         bool has_initial = true) {
+    gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 1);
+}
+
+template <class MatT, class KeyPointT>
+void LKOpticalFlow4Layer(const MatT &img1, const MatT &img2, const std::vector<KeyPointT> &kp1,
+                         std::vector<KeyPointT> &kp2, std::vector<bool> &success, bool inverse = false,
+                         bool has_initial = true) {
+    gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 4);  // :135 pyramids = 4
+}
+
+#ifdef OPENCV_CORE_HPP  // OpenCV present: exact reference signatures (include/legoslam/algorithm.h:123-136)
+inline void LKOpticalFlow1Layer(const cv::Mat &img1, const cv::Mat &img2, const std::vector<cv::KeyPoint> &kp1,
+                                std::vector<cv::KeyPoint> &kp2, std::vector<bool> &success, bool inverse = false,
+                                bool has_initial = true) {
+    gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 1);
+}
+inline void LKOpticalFlow4Layer(const cv::Mat &img1, const cv::Mat &img2, const std::vector<cv::KeyPoint> &kp1,
+                                std::vector<cv::KeyPoint> &kp2, std::vector<bool> &success, bool inverse = false,
+                                bool has_initial = true) {
+    gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 4);
+}
+#endif
+
+}  // namespace legoslam
+#endif  // LEGOSLAM_GPU_ALGORITHM_SHIM_H
