@@ -71,7 +71,8 @@ struct SolverArgs {
     uint8_t *success;         // [B*n]
     unsigned long long *stats;  // [kStatCount]
     int n_per_pair;
-    int n_total;
+    int n_total;              // features in this launch: global ids f0 .. f0 + n_total - 1
+    int f0;                   // first global feature id (chunked batches); image = id / n_per_pair
     int patch_lo, patch_hi;
     int max_iters;
     int inverse;

@@ -12,8 +12,9 @@ namespace legoklt {
 
 __global__ void __launch_bounds__(128)
 klt_exact_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= args.n_total) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= args.n_total) return;
+    const int i = args.f0 + t;
     const int img = i / args.n_per_pair;
     const int L = pyr.levels;
     const bool inverse = args.inverse != 0;

@@ -272,7 +272,7 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     const long long item = (long long)blockIdx.x * T + tid;
     if (item >= (long long)args.n_total * L) return;
     const int level = L - 1 - (int)(item / args.n_total);
-    const int f = (int)(item % args.n_total);
+    const int f = args.f0 + (int)(item % args.n_total);
     const int img = f / args.n_per_pair;
     const LevelView &lv = pyr.lv[level];
     const float2 k0 = args.kp1[f];
@@ -363,10 +363,11 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 if (lane == leader) base = atomicAdd(args.work_counter, __popc(m));
                 base = __shfl_sync(FULL, base, leader);
                 if (state == ST_FETCH) {
-                    const int id = base + __popc(m & ((1u << lane) - 1u));
-                    if (id < args.n_total && args.feat_flag[id] != 0) {
+                    const int local = base + __popc(m & ((1u << lane) - 1u));
+                    const int id = args.f0 + local;
+                    if (local < args.n_total && args.feat_flag[id] != 0) {
                         // irregular template (kx+c inexact, ...): the warp kernel owns this feature
-                    } else if (id < args.n_total) {
+                    } else if (local < args.n_total) {
                         feat = id;
                         img = id / args.n_per_pair;
                         k1 = args.kp1[id];

@@ -156,7 +156,7 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     const int warps_total = gridDim.x * kWarpsPerCta;
     const int n_work = args.list ? *args.list_count : args.n_total;
     for (int wi = blockIdx.x * kWarpsPerCta + warp; wi < n_work; wi += warps_total) {
-        const int f = args.list ? args.list[wi] : wi;
+        const int f = args.list ? args.list[wi] : args.f0 + wi;
         const int img = f / args.n_per_pair;
         float2 k1 = args.kp1[f], k2 = args.kp2_init[f];
         k1.x = (float)(k1.x * scale_top);  // src/algorithm.cpp:160-169

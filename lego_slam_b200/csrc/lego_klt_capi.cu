@@ -40,6 +40,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
 constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings)
+constexpr int kMaxChunks = 16;  // chunks of the overlapped end-to-end path (lego_klt_track_batched)
 
 }  // namespace
 
@@ -75,7 +76,10 @@ struct lego_klt_batch {
     int *d_feat_flag = nullptr;    // LANE path: per-feature 'handed to the warp kernel' flag
     cudaStream_t side = nullptr;   // deferred features run here, concurrently with the lane kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool uploaded = false, ran = false, pyramids_valid = false;
+    cudaStream_t copy = nullptr;   // chunked end-to-end path: H2D of chunk c+1 overlaps compute of chunk c
+    cudaEvent_t ev_chunk[kMaxChunks] = {};
+    cudaEvent_t ev_compute_done = nullptr;
+    bool uploaded = false, ran = false, pyramids_valid = false, last_chunked = false;
     lego_klt_params last_params;
 };
 
@@ -156,7 +160,7 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
         (e = cudaMalloc(&b->d_kp2_out, nt * sizeof(float2))) != cudaSuccess ||
         (e = cudaMalloc(&b->d_success, nt)) != cudaSuccess ||
         (e = cudaMalloc(&b->d_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_work, 4 * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_work, 4 * kMaxChunks * sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc(&b->d_defer_list, nt * sizeof(int))) != cudaSuccess ||
         (e = cudaMallocHost(&b->h_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess)
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "allocating keypoint buffers: %s", cudaGetErrorString(e)));
@@ -175,33 +179,47 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
     return LEGO_KLT_OK;
 }
 
-// H2D of level 0 of one image set: rows of `step` bytes into the pitched device layout.
-cudaError_t upload_set(lego_klt_batch *b, int set, const uint8_t *src, size_t src_step) {
-    (void)src_step;
-    const size_t bytes = (size_t)b->B * b->rows * b->step;
-    uint8_t *landing = b->d_tight + (size_t)set * align_up(bytes + 256, 256);
-    cudaError_t e = cudaMemcpyAsync(landing, src, bytes, cudaMemcpyHostToDevice, b->ctx->stream);
-    if (e != cudaSuccess) return e;
-    return launch_ingest(landing, b->view.lv[0], set, b->B, b->ctx->stream);
+// H2D of level 0 of images [img0, img0+nimg) of one image set: a plain contiguous copy into the landing
+// buffer on `copy_stream`, then (after `ready`, if given) the re-pitch kernel on `kernel_stream`.
+cudaError_t upload_set(lego_klt_batch *b, int set, const uint8_t *src, int img0, int nimg, cudaStream_t copy_stream) {
+    const size_t img_bytes = (size_t)b->rows * b->step;
+    const size_t set_bytes = align_up((size_t)b->B * img_bytes + 256, 256);
+    uint8_t *landing = b->d_tight + (size_t)set * set_bytes + (size_t)img0 * img_bytes;
+    return cudaMemcpyAsync(landing, src + (size_t)img0 * img_bytes, (size_t)nimg * img_bytes, cudaMemcpyHostToDevice,
+                           copy_stream);
 }
 
-int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
-    int rc = validate_params(params, b->levels);
-    if (rc) return rc;
-    if (!b->uploaded) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_run before upload");
+cudaError_t ingest_set(lego_klt_batch *b, int set, int img0, int nimg, cudaStream_t stream) {
+    const size_t img_bytes = (size_t)b->rows * b->step;
+    const size_t set_bytes = align_up((size_t)b->B * img_bytes + 256, 256);
+    const uint8_t *landing = b->d_tight + (size_t)set * set_bytes + (size_t)img0 * img_bytes;
+    // the funnel-shift loads need a 4-byte aligned base: pass the set base and let the kernel index rows from img0
+    (void)landing;
+    return launch_ingest(b->d_tight + (size_t)set * set_bytes, b->view.lv[0], set, img0, nimg, stream);
+}
+
+int ensure_lane_buffers(lego_klt_batch *b) {
+    if (b->d_templates) return LEGO_KLT_OK;
+    const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
+    CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
+    CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
+    CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    return LEGO_KLT_OK;
+}
+
+// Pyramids + aprons + solver for images [img0, img0+nimg) (features f0 = img0*n .. ), on the context stream.
+// `chunk` selects the set of device work counters; `ring` (3 events) is recorded around the kernels if given.
+int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int nimg, int chunk, cudaEvent_t *ring) {
     lego_klt_ctx *ctx = b->ctx;
-    CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
-    CU_TRY(cudaMemsetAsync(b->d_work, 0, 4 * sizeof(int), st));
-    cudaEvent_t *ring = b->ring[b->runs % kRing];
-    CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
-    CU_TRY(cudaEventRecord(ring[0], st));
-    CU_TRY(launch_pyramid(b->plan, b->view, st));
-    CU_TRY(launch_aprons(b->view, st));
-    b->pyramids_valid = true;
-    CU_TRY(cudaEventRecord(b->ev[EV_PYR], st));
-    CU_TRY(cudaEventRecord(ring[1], st));
+    int *work = b->d_work + 4 * chunk;
+    CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
+    if (ring) CU_TRY(cudaEventRecord(ring[0], st));
+    CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
+    CU_TRY(launch_aprons(b->view, img0, nimg, st));
+    if (ring) CU_TRY(cudaEventRecord(ring[1], st));
     SolverArgs a;
     a.kp1 = b->d_kp1;
     a.kp2_init = b->d_kp2_init;
@@ -209,7 +227,8 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     a.success = b->d_success;
     a.stats = b->d_stats;
     a.n_per_pair = b->n_active > 0 ? b->n_active : 1;
-    a.n_total = b->B * b->n_active;
+    a.n_total = nimg * b->n_active;
+    a.f0 = img0 * b->n_active;
     a.patch_lo = params->patch_lo;
     a.patch_hi = params->patch_hi;
     a.max_iters = params->max_iters;
@@ -222,9 +241,9 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     }
     a.list = nullptr;
     a.list_count = nullptr;
-    a.work_counter = b->d_work;
-    a.defer_count = b->d_work + 1;
-    a.defer_list = b->d_defer_list;
+    a.work_counter = work;
+    a.defer_count = work + 1;
+    a.defer_list = b->d_defer_list + a.f0;
     a.templates = nullptr;
     a.feat_flag = nullptr;
     int kernel = params->kernel;
@@ -235,33 +254,44 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
         CU_TRY(launch_klt_exact(b->view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
-    } else {
-        const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
-        if (!b->d_templates) {
-            CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
-            CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
-            CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
-            CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
-        }
+    } else if (a.n_total > 0) {
+        int rc = ensure_lane_buffers(b);
+        if (rc) return rc;
         a.templates = b->d_templates;
         a.feat_flag = b->d_feat_flag;
-        CU_TRY(cudaMemsetAsync(b->d_feat_flag, 0, (size_t)a.n_total * sizeof(int), st));
+        CU_TRY(cudaMemsetAsync(b->d_feat_flag + a.f0, 0, (size_t)a.n_total * sizeof(int), st));
         CU_TRY(launch_klt_template(b->view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
         CU_TRY(cudaEventRecord(b->ev_fork, st));
         CU_TRY(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
         SolverArgs aw = a;
-        aw.list = b->d_defer_list;
-        aw.list_count = b->d_work + 1;
+        aw.list = a.defer_list;
+        aw.list_count = a.defer_count;
         CU_TRY(launch_klt_warp(b->view, b->maps, aw, ctx->sm_count, b->side));
         CU_TRY(cudaEventRecord(b->ev_join, b->side));
         CU_TRY(launch_klt_lane(b->view, a, ctx->sm_count, st));
         CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
     }
+    if (ring) CU_TRY(cudaEventRecord(ring[2], st));
+    return LEGO_KLT_OK;
+}
+
+int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
+    int rc = validate_params(params, b->levels);
+    if (rc) return rc;
+    if (!b->uploaded) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_run before upload");
+    lego_klt_ctx *ctx = b->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    cudaEvent_t *ring = b->ring[b->runs % kRing];
+    CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
+    rc = run_range(b, params, 0, b->B, 0, ring);
+    if (rc) return rc;
+    b->pyramids_valid = true;
+    CU_TRY(cudaEventRecord(b->ev[EV_PYR], ctx->stream));  // kept for the stats struct; see fill_stats
     CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
-    CU_TRY(cudaEventRecord(ring[2], st));
     ++b->runs;
     b->ran = true;
     b->last_params = *params;
@@ -281,8 +311,13 @@ void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     for (int l = 0; l < kMaxLevels; ++l) s->gn_iters[l] = b->h_stats[kStatIters0 + l];
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev[EV_START], b->ev[EV_H2D]) == cudaSuccess) s->ms_h2d = ms;
-    if (cudaEventElapsedTime(&ms, b->ev[EV_H2D], b->ev[EV_PYR]) == cudaSuccess) s->ms_pyramid = ms;
-    if (cudaEventElapsedTime(&ms, b->ev[EV_PYR], b->ev[EV_SOLVE]) == cudaSuccess) s->ms_solver = ms;
+    if (b->runs > 0 && !b->last_chunked) {
+        cudaEvent_t *ring = b->ring[(b->runs - 1) % kRing];
+        if (cudaEventElapsedTime(&ms, ring[0], ring[1]) == cudaSuccess) s->ms_pyramid = ms;
+        if (cudaEventElapsedTime(&ms, ring[1], ring[2]) == cudaSuccess) s->ms_solver = ms;
+    } else if (cudaEventElapsedTime(&ms, b->ev[EV_H2D], b->ev[EV_SOLVE]) == cudaSuccess) {
+        s->ms_solver = ms;  // chunked run: copies and kernels overlap, only the total is meaningful
+    }
     if (cudaEventElapsedTime(&ms, b->ev[EV_SOLVE], b->ev[EV_D2H]) == cudaSuccess) s->ms_d2h = ms;
     cudaGetLastError();  // events not recorded yet (run without upload) are not an error of this call
 }
@@ -424,6 +459,10 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     if (b->side) cudaStreamDestroy(b->side);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->copy) cudaStreamDestroy(b->copy);
+    for (int i = 0; i < kMaxChunks; ++i)
+        if (b->ev_chunk[i]) cudaEventDestroy(b->ev_chunk[i]);
+    if (b->ev_compute_done) cudaEventDestroy(b->ev_compute_done);
     cudaFree(b->d_images);
     cudaFree(b->d_tight);
     cudaFree(b->d_kp1);
@@ -445,14 +484,17 @@ int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t
     CU_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
     CU_TRY(cudaEventRecord(b->ev[EV_START], st));
-    CU_TRY(upload_set(b, 0, imgs1, b->step));
-    CU_TRY(upload_set(b, 1, imgs2, b->step));
+    CU_TRY(upload_set(b, 0, imgs1, 0, b->B, st));
+    CU_TRY(upload_set(b, 1, imgs2, 0, b->B, st));
+    CU_TRY(ingest_set(b, 0, 0, b->B, st));
+    CU_TRY(ingest_set(b, 1, 0, b->B, st));
     if (nt) {
         CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
     }
     b->uploaded = true;
     b->pyramids_valid = false;
+    b->last_chunked = false;
     return LEGO_KLT_OK;
 }
 
@@ -502,10 +544,61 @@ int lego_klt_batch_timings(lego_klt_batch *b, int last_n, float *ms_pyramid_avg,
 int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, const uint8_t *imgs1,
                            const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success,
                            lego_klt_stats *stats) {
-    int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    // Small batches: plain upload -> run -> download.
+    const int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
+    if (n_chunks == 1) {
+        int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
+        if (rc) return rc;
+        rc = lego_klt_batch_run(b, params);
+        if (rc) return rc;
+        return lego_klt_batch_download(b, kp2_xy, success, stats);
+    }
+    // Large batches: the batch is cut into chunks of pairs; the H2D copy of chunk c+1 (copy stream) overlaps
+    // the kernels of chunk c (context stream).  PCIe is the end-to-end bound (933 KB per 1241x376 pair).
+    if (!imgs1 || !imgs2) return fail(LEGO_KLT_ERR_BAD_ARG, "image pointer is null");
+    const size_t nt = (size_t)b->B * (size_t)b->n_active;
+    if (nt && (!kp1_xy || !kp2_xy || !success)) return fail(LEGO_KLT_ERR_BAD_ARG, "keypoint pointer is null");
+    int rc = validate_params(params, b->levels);
     if (rc) return rc;
-    rc = lego_klt_batch_run(b, params);
-    if (rc) return rc;
+    lego_klt_ctx *ctx = b->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (!b->copy) {
+        CU_TRY(cudaStreamCreateWithFlags(&b->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) CU_TRY(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&b->ev_compute_done, cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventRecord(b->ev[EV_START], st));
+    CU_TRY(cudaStreamWaitEvent(b->copy, b->ev[EV_START], 0));  // the copy stream starts after earlier work
+    CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
+    const int n = b->n_active;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int img0 = (int)((long long)b->B * c / n_chunks), img1 = (int)((long long)b->B * (c + 1) / n_chunks);
+        const int nimg = img1 - img0;
+        if (nimg <= 0) continue;
+        CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));
+        CU_TRY(upload_set(b, 1, imgs2, img0, nimg, b->copy));
+        if (n) {
+            const size_t off = (size_t)img0 * n, cnt = (size_t)nimg * n;
+            CU_TRY(cudaMemcpyAsync(b->d_kp1 + off, kp1_xy + 2 * off, cnt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
+            CU_TRY(cudaMemcpyAsync(b->d_kp2_init + off, kp2_xy + 2 * off, cnt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
+        }
+        CU_TRY(cudaEventRecord(b->ev_chunk[c], b->copy));
+        CU_TRY(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
+        CU_TRY(ingest_set(b, 0, img0, nimg, st));
+        CU_TRY(ingest_set(b, 1, img0, nimg, st));
+        rc = run_range(b, params, img0, nimg, c, nullptr);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
+    b->uploaded = true;
+    b->pyramids_valid = true;
+    b->ran = true;
+    b->last_chunked = true;
+    b->last_params = *params;
+    ++b->runs;
     return lego_klt_batch_download(b, kp2_xy, success, stats);
 }
 
@@ -581,10 +674,12 @@ int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int 
     memset(ctx->pinned + valid, 0, img_bytes - valid);
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    CU_TRY(upload_set(b, 0, ctx->pinned, step));
-    CU_TRY(upload_set(b, 1, ctx->pinned, step));
-    CU_TRY(launch_pyramid(b->plan, b->view, st));
-    CU_TRY(launch_aprons(b->view, st));
+    CU_TRY(upload_set(b, 0, ctx->pinned, 0, 1, st));
+    CU_TRY(upload_set(b, 1, ctx->pinned, 0, 1, st));
+    CU_TRY(ingest_set(b, 0, 0, 1, st));
+    CU_TRY(ingest_set(b, 1, 0, 1, st));
+    CU_TRY(launch_pyramid(b->plan, b->view, 0, 1, st));
+    CU_TRY(launch_aprons(b->view, 0, 1, st));
     size_t off = 0;
     for (int l = 0; l < levels; ++l) {
         const LevelView &lv = b->view.lv[l];

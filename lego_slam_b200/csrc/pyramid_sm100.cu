@@ -67,6 +67,7 @@ struct PyrKernelParams {
     ResizeTables tab[kMaxLevels];
     int smem_off[kMaxLevels];
     int top_rows;
+    int img0, nimg;  // image range of this launch (chunked batches)
 };
 
 __device__ __forceinline__ int d_clip(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
@@ -75,8 +76,8 @@ __global__ void __launch_bounds__(256)
 pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ PyrKernelParams kp) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int L = pyr.levels;
-    const int set = blockIdx.y / pyr.n_images;
-    const int img = blockIdx.y - set * pyr.n_images;
+    const int set = blockIdx.y / kp.nimg;
+    const int img = kp.img0 + (blockIdx.y - set * kp.nimg);
     const int tid = threadIdx.x, nthreads = blockDim.x;
 
     // Row bands [lo, hi) at every level for this CTA's top-level rows.  A band must contain the rows
@@ -184,18 +185,19 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
 
 // Row aprons: one WARP per (level, set, image, row): 32 + ~50 bytes per row, lanes write them in parallel.
 // Tiny next to the pyramid itself, and it lets the solver stage windows with unconditional aligned loads.
-__global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total) {
+__global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total, int img0,
+                                                    int nimg) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= rows_total) return;
     int level = 0, r = t;
-    while (r >= pyr.lv[level].rows * 2 * pyr.n_images) {
-        r -= pyr.lv[level].rows * 2 * pyr.n_images;
+    while (r >= pyr.lv[level].rows * 2 * nimg) {
+        r -= pyr.lv[level].rows * 2 * nimg;
         ++level;
     }
     const LevelView &lv = pyr.lv[level];
     const int row = r % lv.rows;
-    const int k = (r / lv.rows) % pyr.n_images, set = r / (lv.rows * pyr.n_images);
+    const int k = img0 + (r / lv.rows) % nimg, set = r / (lv.rows * nimg);
     uint8_t *rp = lv.base[set] + (size_t)k * lv.slot + (size_t)row * lv.pitch;
     const uint32_t first = rp[0], last = rp[lv.cols - 1];
     // data[row*step + cols] of the reference's flat addressing
@@ -213,13 +215,14 @@ __global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ Pyra
 // speed, so rows are re-pitched on the device.  One warp per row chunk: aligned 4-byte loads, funnel
 // shift by the row's misalignment, aligned 4-byte stores.
 __global__ void __launch_bounds__(256)
-ingest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst_base, int step, int pitch, long long n_rows,
-              int rows_per_image, unsigned long long slot) {
+ingest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst_base, int step, int pitch, long long row0,
+              long long n_rows, int rows_per_image, unsigned long long slot) {
     const int words = (step + 3) >> 2;
     const long long total = n_rows * words;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long row = i / words;
-        const int w = (int)(i - row * words);
+        const long long lrow = i / words;
+        const int w = (int)(i - lrow * words);
+        const long long row = row0 + lrow;                         // row index within the whole image set
         const size_t s = (size_t)row * step + 4 * (size_t)w;      // byte offset of this word in the tight buffer
         const size_t sa = s & ~(size_t)3;
         const int sh = (int)(s & 3) * 8;
@@ -234,20 +237,22 @@ ingest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst_base, i
 
 }  // namespace
 
-cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int n_images, cudaStream_t stream) {
+cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int img0, int n_images,
+                          cudaStream_t stream) {
     const long long n_rows = (long long)n_images * l0.rows;
     if (n_rows <= 0) return cudaSuccess;
     const long long total = n_rows * ((l0.step + 3) >> 2);
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    ingest_kernel<<<grid, 256, 0, stream>>>(tight, l0.base[set], l0.step, l0.pitch, n_rows, l0.rows, l0.slot);
+    ingest_kernel<<<grid, 256, 0, stream>>>(tight, l0.base[set], l0.step, l0.pitch, (long long)img0 * l0.rows, n_rows,
+                                            l0.rows, l0.slot);
     return cudaGetLastError();
 }
 
-cudaError_t launch_aprons(const PyramidView &pyr, cudaStream_t stream) {
+cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream) {
     int rows_total = 0;
-    for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * 2 * pyr.n_images;
+    for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * 2 * nimg;
     if (rows_total <= 0) return cudaSuccess;
-    apron_kernel<<<(rows_total + 7) / 8, 256, 0, stream>>>(pyr, rows_total);
+    apron_kernel<<<(rows_total + 7) / 8, 256, 0, stream>>>(pyr, rows_total, img0, nimg);
     return cudaGetLastError();
 }
 
@@ -330,14 +335,16 @@ void pyramid_plan_destroy(PyramidPlan *plan) {
     *plan = PyramidPlan();
 }
 
-cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, cudaStream_t stream) {
-    if (plan.levels <= 1 || pyr.n_images <= 0) return cudaSuccess;
+cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream) {
+    if (plan.levels <= 1 || nimg <= 0) return cudaSuccess;
     PyrKernelParams kp;
     for (int l = 0; l < kMaxLevels; ++l) {
         kp.tab[l] = plan.tab[l];
         kp.smem_off[l] = plan.smem_off[l];
     }
     kp.top_rows = plan.top_rows_per_cta;
+    kp.img0 = img0;
+    kp.nimg = nimg;
     static thread_local size_t configured = 0;
     if (plan.smem_bytes > 48 * 1024 && plan.smem_bytes > configured) {
         cudaError_t err = cudaFuncSetAttribute(pyramid_fused_kernel,
@@ -347,7 +354,7 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, cuda
         configured = plan.smem_bytes;
     }
     const int top = plan.levels - 1;
-    dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, 2 * pyr.n_images);
+    dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, 2 * nimg);
     pyramid_fused_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
     return cudaGetLastError();
 }

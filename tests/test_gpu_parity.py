@@ -135,7 +135,7 @@ def _make_batch(B, rows, cols, n, seed0):
 
 @pytest.mark.parametrize("kernel", FAST_KERNELS)
 def test_config3_batched_pairs_match_oracle_per_pair(tracker, oracle, kernel):
-    B, rows, cols, n = 6, 376, 1241, 2000
+    B, rows, cols, n = 9, 376, 1241, 2000  # >= 8 pairs: exercises the chunked copy/compute overlap
     imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 1000)
     guess = kp2.copy()
     succ = klt.pinned_empty((B, n), np.uint8)
