@@ -163,37 +163,39 @@ __device__ __forceinline__ bool window_in_apron(const LevelView &lv, int wx0) {
     return wx0 >= -kApronL && wx0 + kWin2Words * 4 <= lv.pitch - kApronL;
 }
 
+template <int ROWS>
+__device__ __forceinline__ void window_load(const uint8_t *img, const LevelView &lv, int wx0, int wy0, uint4 (&v)[ROWS][2]) {
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+        const uint4 *rp = reinterpret_cast<const uint4 *>(img + (ptrdiff_t)ry * lv.pitch + wx0);
+        v[i][0] = __ldg(rp);
+        v[i][1] = __ldg(rp + 1);
+    }
+}
+
+template <int ROWS, int WS>
+__device__ __forceinline__ void window_store(const uint4 (&v)[ROWS][2], uint32_t *dst) {
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+        uint32_t *d = dst + i * kWin2Words * WS;
+        d[0] = v[i][0].x;
+        d[WS] = v[i][0].y;
+        d[2 * WS] = v[i][0].z;
+        d[3 * WS] = v[i][0].w;
+        d[4 * WS] = v[i][1].x;
+        d[5 * WS] = v[i][1].y;
+        d[6 * WS] = v[i][1].z;
+        d[7 * WS] = v[i][1].w;
+    }
+}
+
 template <int ROWS, int WS>
 __device__ __forceinline__ void stage_own_window(const uint8_t *img, const LevelView &lv, int wx0, int wy0,
                                                  uint32_t *dst) {
-    constexpr int kBatch = (ROWS + 1) / 2;
-#pragma unroll
-    for (int base = 0; base < ROWS; base += kBatch) {
-        uint4 v[kBatch][2];
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            if (base + i < ROWS) {
-                const int ry = min(max(wy0 + base + i, 0), lv.rows - 1);
-                const uint4 *rp = reinterpret_cast<const uint4 *>(img + (ptrdiff_t)ry * lv.pitch + wx0);
-                v[i][0] = __ldg(rp);
-                v[i][1] = __ldg(rp + 1);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            if (base + i < ROWS) {
-                uint32_t *d = dst + (base + i) * kWin2Words * WS;
-                d[0] = v[i][0].x;
-                d[WS] = v[i][0].y;
-                d[2 * WS] = v[i][0].z;
-                d[3 * WS] = v[i][0].w;
-                d[4 * WS] = v[i][1].x;
-                d[5 * WS] = v[i][1].y;
-                d[6 * WS] = v[i][1].z;
-                d[7 * WS] = v[i][1].w;
-            }
-        }
-    }
+    uint4 v[ROWS][2];
+    window_load<ROWS>(img, lv, wx0, wy0, v);
+    window_store<ROWS, WS>(v, dst);
 }
 
 // Ten consecutive window pixels of row i (starting at the footprint's first column) as floats.
@@ -396,7 +398,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const int n_runnable = __popc(__ballot_sync(FULL, state == ST_RUN && !need_win));
             if (n_blocked > 0 && (n_blocked >= kSetupBatch || n_runnable == 0) && blocked) {
                 const LevelView &lv = pyr.lv[level];
-                if (state == ST_LEVEL) {
+                const bool new_level = (state == ST_LEVEL);
+                if (new_level) {
                     const bool has_initial = (level == L - 1) ? (args.has_initial != 0) : true;  // :185-189
                     kx = k1.x;
                     ky = k1.y;
@@ -408,11 +411,28 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     iter = 0;
                     lastCost = 0;
                     succ = true;
-                    // template patch of this (feature, level): 49 floats (+ regularity flag, checked at fetch)
+                }
+                const double Sx = (double)kx + dx, Sy = (double)ky + dy;
+                no_window = true;  // estimate far outside the image / its apron: exact per-pixel passes
+                if (fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6) {
+                    const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
+                    wx0 = (ixn - 2) & ~15;
+                    wy0 = iyn - 2;
+                    no_window = !window_in_apron(lv, wx0);
+                }
+                // The template (13 x 16 B) and the first half of the window (14 x 16 B) are loaded before the
+                // first store, then the second half: two memory round trips per set-up instead of three.
+                constexpr int kHalf = kWin2Rows / 2;
+                const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
+                float4 t[kTplStride / 4];
+                uint4 wv[kHalf][2];
+                if (new_level) {
                     const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)feat * L + level) * kTplStride);
-                    float4 t[kTplStride / 4];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
+                }
+                if (!no_window) window_load<kHalf>(img2, lv, wx0, wy0, wv);
+                if (new_level) {
                     float *ip = &sm.i1[0][tid];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) {
@@ -422,16 +442,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         if (4 * i + 3 < kI1Count) ip[(4 * i + 3) * WS] = t[i].w;
                     }
                 }
-                const double Sx = (double)kx + dx, Sy = (double)ky + dy;
-                no_window = true;  // estimate far outside the image / its apron: exact per-pixel passes
-                if (fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6) {
-                    const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
-                    wx0 = (ixn - 2) & ~15;
-                    wy0 = iyn - 2;
-                    if (window_in_apron(lv, wx0)) {
-                        stage_own_window<kWin2Rows, WS>(lv.base[1] + (size_t)img * lv.slot, lv, wx0, wy0, &sm.win2[0][tid]);
-                        no_window = false;
-                    }
+                if (!no_window) {
+                    window_store<kHalf, WS>(wv, &sm.win2[0][tid]);
+                    window_load<kHalf>(img2, lv, wx0, wy0 + kHalf, wv);
+                    window_store<kHalf, WS>(wv, &sm.win2[kHalf * kWin2Words][tid]);
                 }
                 need_win = false;
                 state = ST_RUN;
