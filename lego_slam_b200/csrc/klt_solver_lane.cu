@@ -50,6 +50,7 @@ constexpr int kWin2Rows = 14, kWin2Words = 8;                 // img2 window: 14
 constexpr int kWin2Total = kWin2Rows * kWin2Words;            // 112 words
 constexpr int kTplRows = 8;                                   // img1 window rows in the template kernel
 constexpr int kI1Count = P * P;                               // 49 floats, index y*P + x
+constexpr int kQueue = 64;                                    // feature ring entries per warp
 constexpr int kTplStride = 52;                                // floats per (feature, level): 49 + flag + pad
 #ifndef LANE_BATCH
 #define LANE_BATCH 10
@@ -69,6 +70,9 @@ struct LaneSmem {
     uint32_t win2[kWin2Total][T + 1];
     float i1[kI1Count][T + 1];
     float wy[2 * G][T + 1];  // per grid row: [2r] = 1-frac, [2r+1] = frac (dynamic row index in the rolled loop)
+    // per-warp ring of fetched features: one global atomic + coalesced keypoint loads per 32 features
+    float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
+    int q_id[T / 32][kQueue];
     unsigned stats[kStatCount];
 };
 
@@ -126,23 +130,18 @@ __device__ __forceinline__ int grid_axis(float k, double d, int limit, int &orig
         const double D = S + (double)(LO - 1 + g);
         const float X = (float)D;
         // (b) distance of D's discarded mantissa bits from the fp32 rounding midpoint
-        const int low = __double2loint(D) & 0x1FFFFFFF;
-        const int dist = low - 0x10000000;
-        if (dist == 0 ? !tie_ok : (abs(dist) <= 16)) why = kStatDeferMargin;
-        const bool clamp_lo = X < 0.f, clamp_hi = X >= flimit;
-        float f = __fadd_rn(X, -(float)(origin + g));
-        float o = __fadd_rn(1.f, -f);
-        if (clamp_lo) {
-            f = 0.f;
-            o = 1.f;
-        } else if (clamp_hi) {
-            const bool at_wrap = !IS_ROW && (origin + g == limit);
-            f = at_wrap ? 1.f : 0.f;
-            o = at_wrap ? 0.f : 1.f;
-        } else {
-            if (!((f >= 0.f) && (f <= 1.f))) why = kStatDeferNominal;
-            if (IS_ROW && X > flast) f = 0.f;  // taps below the last row read zeros
-        }
+        const int dist = (__double2loint(D) & 0x1FFFFFFF) - 0x10000000;
+        const bool margin_bad = (dist == 0) ? !tie_ok : (abs(dist) <= 16);
+        const bool clamp_lo = X < 0.f, clamp_hi = X >= flimit, clamped = clamp_lo || clamp_hi;
+        const float f_raw = __fadd_rn(X, -(float)(origin + g));
+        const bool nominal_bad = !clamped && !((f_raw >= 0.f) && (f_raw <= 1.f));
+        why = margin_bad ? kStatDeferMargin : why;
+        why = nominal_bad ? kStatDeferNominal : why;
+        // selects only (no branches): clamped -> (om, fr) = (1, 0), or (0, 1) at the wrap column
+        const bool at_wrap = !IS_ROW && clamp_hi && (origin + g == limit);
+        float f = clamped ? (at_wrap ? 1.f : 0.f) : f_raw;
+        const float o = clamped ? (at_wrap ? 0.f : 1.f) : __fadd_rn(1.f, -f_raw);
+        if (IS_ROW) f = (!clamped && X > flast) ? 0.f : f;  // taps below the last row read zeros
         fr[g] = f;
         om[g] = o;
     }
@@ -334,9 +333,11 @@ __global__ void __launch_bounds__(T, MIN_CTAS)
 klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LaneSmem<T> &sm = *reinterpret_cast<LaneSmem<T> *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int WS = T + 1;  // word stride between consecutive window words of one thread
+    int q_head = 0, q_tail = 0;  // warp-uniform ring positions
+    bool global_done = false;
 
     if (tid < kStatCount) sm.stats[tid] = 0u;
     __syncthreads();
@@ -360,20 +361,42 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         {
             const unsigned m = __ballot_sync(FULL, state == ST_FETCH);
             if (m) {
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(args.work_counter, __popc(m));
-                base = __shfl_sync(FULL, base, leader);
+                const int need = __popc(m);
+                int avail = q_tail - q_head;
+                if (avail < need && !global_done) {
+                    // refill: 32 consecutive feature ids, coalesced loads, compacted into the warp's ring
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(args.work_counter, 32);
+                    base = __shfl_sync(FULL, base, 0);
+                    const int local = base + lane;
+                    bool keep = local < args.n_total;
+                    float2 a1 = make_float2(0.f, 0.f), a2 = a1;
+                    const int gid = args.f0 + local;
+                    if (keep) {
+                        keep = args.feat_flag[gid] == 0;  // irregular template: the warp kernel owns this feature
+                        a1 = args.kp1[gid];
+                        a2 = args.kp2_init[gid];
+                    }
+                    const unsigned km = __ballot_sync(FULL, keep);
+                    if (keep) {
+                        const int pos = (q_tail + __popc(km & ((1u << lane) - 1u))) & (kQueue - 1);
+                        sm.q_k1[warp][pos] = a1;
+                        sm.q_k2[warp][pos] = a2;
+                        sm.q_id[warp][pos] = gid;
+                    }
+                    q_tail += __popc(km);
+                    if (base + 32 >= args.n_total) global_done = true;
+                    __syncwarp();
+                    avail = q_tail - q_head;
+                }
                 if (state == ST_FETCH) {
-                    const int local = base + __popc(m & ((1u << lane) - 1u));
-                    const int id = args.f0 + local;
-                    if (local < args.n_total && args.feat_flag[id] != 0) {
-                        // irregular template (kx+c inexact, ...): the warp kernel owns this feature
-                    } else if (local < args.n_total) {
-                        feat = id;
-                        img = id / args.n_per_pair;
-                        k1 = args.kp1[id];
-                        k2 = args.kp2_init[id];
+                    const int rank = __popc(m & ((1u << lane) - 1u));
+                    if (rank < avail) {
+                        const int pos = (q_head + rank) & (kQueue - 1);
+                        feat = sm.q_id[warp][pos];
+                        img = feat / args.n_per_pair;
+                        k1 = sm.q_k1[warp][pos];
+                        k2 = sm.q_k2[warp][pos];
                         k1.x = (float)(k1.x * scale_top);  // src/algorithm.cpp:160-169
                         k1.y = (float)(k1.y * scale_top);
                         k2.x = (float)(k2.x * scale_top);
@@ -383,10 +406,12 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         nan_count = 0;
                         flag = true;
                         state = ST_LEVEL;
-                    } else {
+                    } else if (global_done) {
                         state = ST_DONE;
                     }
                 }
+                q_head += min(need, avail);
+                __syncwarp();
             }
             if (__all_sync(FULL, state == ST_DONE)) break;
         }
