@@ -84,7 +84,8 @@ struct SolverArgs {
     const int *list_count;
     // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
     float *templates;         // [n_total][levels][52]: I1 patches + regularity flag (template kernel)
-    int *feat_flag;           // [n_total]: 1 = feature handed to the warp kernel by the template kernel
+    int *feat_flag;           // [n_total]: == epoch -> feature handed to the warp kernel by the template kernel
+    int epoch;                // run counter (>= 1): flags from earlier runs are stale, no memset needed
     int *work_counter;
     int *defer_list;
     int *defer_count;

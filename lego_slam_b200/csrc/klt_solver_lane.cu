@@ -293,7 +293,7 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15);
     if (!regular) {
         // the whole feature goes to the exact warp kernel (which runs concurrently with the lane kernel)
-        if (atomicExch(&args.feat_flag[f], 1) == 0) {
+        if (atomicExch(&args.feat_flag[f], args.epoch) != args.epoch) {
             args.defer_list[atomicAdd(args.defer_count, 1)] = f;
             atomicAdd(&args.stats[kStatDeferred], 1ull);
             atomicAdd(&args.stats[kStatDeferInexact], 1ull);
@@ -373,7 +373,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     float2 a1 = make_float2(0.f, 0.f), a2 = a1;
                     const int gid = args.f0 + local;
                     if (keep) {
-                        keep = args.feat_flag[gid] == 0;  // irregular template: the warp kernel owns this feature
+                        keep = args.feat_flag[gid] != args.epoch;  // irregular template: the warp kernel owns this feature
                         a1 = args.kp1[gid];
                         a2 = args.kp2_init[gid];
                     }
@@ -455,6 +455,11 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)feat * L + level) * kTplStride);
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
+                    if (level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
+                        const char *nxt = reinterpret_cast<const char *>(tp) - kTplStride * sizeof(float);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+                    }
                 }
                 if (!no_window) window_load<kHalf>(img2, lv, wx0, wy0, wv);
                 if (new_level) {

@@ -203,6 +203,7 @@ int ensure_lane_buffers(lego_klt_batch *b) {
     const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
     CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
     CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
+    CU_TRY(cudaMemset(b->d_feat_flag, 0, cap * sizeof(int)));
     CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
@@ -246,6 +247,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.defer_list = b->d_defer_list + a.f0;
     a.templates = nullptr;
     a.feat_flag = nullptr;
+    a.epoch = 0;
     int kernel = params->kernel;
     if (kernel == LEGO_KLT_KERNEL_AUTO) kernel = lane_kernel_supports(a) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
@@ -259,7 +261,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         if (rc) return rc;
         a.templates = b->d_templates;
         a.feat_flag = b->d_feat_flag;
-        CU_TRY(cudaMemsetAsync(b->d_feat_flag + a.f0, 0, (size_t)a.n_total * sizeof(int), st));
+        a.epoch = (int)((b->runs % 0x3fffffff) + 1);
         CU_TRY(launch_klt_template(b->view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
