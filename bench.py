@@ -191,7 +191,8 @@ def workload_config(args):
             "patch": [PATCH_LO, PATCH_HI], "distinct_pairs": min(args.distinct, args.pairs),
             "l2_policy": "inputs larger than L2 (level-0 images of one step: %.0f MB > 126 MB)"
                          % (2 * args.pairs * ROWS * COLS / 1e6),
-            "sharding": "block partition of pairs, one process per GPU, no data-path collective"}
+            "sharding": "block partition of pairs, one process per GPU, no data-path collective",
+            "batches_in_flight": max(1, args.streams)}
 
 
 def run_ours(args):
@@ -217,39 +218,55 @@ def run_ours(args):
 
     B, n = args.pairs, args.features
     base = make_workload(B, n, args.distinct, 1000 + rank * B)
-    trk = klt.Tracker(local)
-    stream = torch.cuda.Stream(device=local)
-    trk.set_stream(stream.cuda_stream)
     imgs1, imgs2, kp1, kp2 = fill_batch(base, B, n, klt.pinned_empty)
     kp2_io = klt.pinned_empty((B, n, 2), np.float32)
     succ = klt.pinned_empty((B, n), np.uint8)
-    batch = trk.batch(B, ROWS, COLS, n, levels=LEVELS)
     params = klt.make_params(levels=LEVELS, patch_lo=PATCH_LO, patch_hi=PATCH_HI, kernel=args.kernel)
     n_tracks = B * n
+    # `--streams S` batches in flight: S device-resident batch objects (same inputs), each on its own
+    # stream, stepped round-robin -- the small kernels of one batch (pyramid, aprons, templates) fill
+    # the issue slots the persistent solver kernel of the other leaves idle.
+    S = max(1, args.streams)
+    trks = [klt.Tracker(local) for _ in range(S)]
+    streams = [torch.cuda.Stream(device=local) for _ in range(S)]
+    batches = []
+    for t, st_ in zip(trks, streams):
+        t.set_stream(st_.cuda_stream)
+        batches.append(t.batch(B, ROWS, COLS, n, levels=LEVELS))
+    trk, stream, batch = trks[0], streams[0], batches[0]
 
     # ---------------- device-resident: inputs already in HBM, results stay in HBM ----------------
-    batch.upload(imgs1, imgs2, kp1, kp2)
-    for _ in range(args.warmup):
-        batch.run(params)
-    trk.sync()
+    for b_ in batches:
+        b_.upload(imgs1, imgs2, kp1, kp2)
+    for i in range(args.warmup * S):
+        batches[i % S].run(params)
+    for t in trks:
+        t.sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        batch.run(params)
-    ev1.record(stream)
+    ev0.record(streams[0])
+    for st_ in streams[1:]:
+        st_.wait_event(ev0)
+    for i in range(args.steps):
+        batches[i % S].run(params)
+    for st_ in streams[1:]:
+        streams[0].wait_stream(st_)
+    ev1.record(streams[0])
     torch.cuda.synchronize()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel launch durations (CUDA events on the launching stream, recorded inside the library
-    # around each kernel), averaged over the same number of steps
-    ms_pyr, ms_sol = batch.timings(min(args.steps, 64))   # the timed steps above, back to back
+    # per-kernel launch durations: CUDA events recorded inside the library around each kernel group on the
+    # launching stream, over the same number of steps run back to back on ONE stream (with several batches
+    # in flight the brackets of one batch would include the other batch's kernels)
+    for _ in range(args.steps):
+        batch.run(params)
+    ms_pyr, ms_sol = batch.timings(min(args.steps, 64))
     _, _, st = batch.download(kp2_io, succ)
     iters = [int(v) for v in st.gn_iters][:LEVELS]
     slow, deferred, n_success = int(st.n_slow_path), int(st.n_deferred), int(st.n_success)
@@ -354,6 +371,7 @@ def main():
     ap.add_argument("--features", type=int, default=2000)
     ap.add_argument("--distinct", type=int, default=64, help="distinct generated pairs (tiled to --pairs)")
     ap.add_argument("--kernel", type=int, default=0, help="LEGO_KLT_KERNEL_* (0 = auto)")
+    ap.add_argument("--streams", type=int, default=1, help="device-resident batches in flight (value only)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -328,8 +328,16 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // Solver kernel.
 // ------------------------------------------------------------------------------------------------
+#ifndef LANE_MAXREG
+#define LANE_MAXREG 0
+#endif
 template <int T, int MIN_CTAS>
-__global__ void __launch_bounds__(T, MIN_CTAS)
+__global__ void
+#if LANE_MAXREG > 0
+__maxnreg__(LANE_MAXREG)
+#else
+__launch_bounds__(T, MIN_CTAS)
+#endif
 klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LaneSmem<T> &sm = *reinterpret_cast<LaneSmem<T> *>(smem_raw);
@@ -445,14 +453,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     wy0 = iyn - 2;
                     no_window = !window_in_apron(lv, wx0);
                 }
-                // The template (13 x 16 B) and the first half of the window (14 x 16 B) are loaded before the
-                // first store, then the second half: two memory round trips per set-up instead of three.
+                // Template first (13 x 16 B in flight), then the window in two halves (14 x 16 B in flight each):
+                // holding all 41 loads in flight needs ~250 registers and did not pay (profiles/README.md).
                 constexpr int kHalf = kWin2Rows / 2;
                 const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
-                float4 t[kTplStride / 4];
-                uint4 wv[kHalf][2];
                 if (new_level) {
                     const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)feat * L + level) * kTplStride);
+                    float4 t[kTplStride / 4];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
                     if (level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
@@ -460,9 +467,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
                     }
-                }
-                if (!no_window) window_load<kHalf>(img2, lv, wx0, wy0, wv);
-                if (new_level) {
                     float *ip = &sm.i1[0][tid];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) {
@@ -473,6 +477,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     }
                 }
                 if (!no_window) {
+                    uint4 wv[kHalf][2];
+                    window_load<kHalf>(img2, lv, wx0, wy0, wv);
                     window_store<kHalf, WS>(wv, &sm.win2[0][tid]);
                     window_load<kHalf>(img2, lv, wx0, wy0 + kHalf, wv);
                     window_store<kHalf, WS>(wv, &sm.win2[kHalf * kWin2Words][tid]);
