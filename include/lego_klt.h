@@ -87,6 +87,7 @@ typedef struct lego_klt_stats {
 
 typedef struct lego_klt_ctx lego_klt_ctx;       /* one per (calling thread, device)               */
 typedef struct lego_klt_batch lego_klt_batch;   /* device-resident batch of B image pairs         */
+typedef struct lego_klt_image lego_klt_image;   /* one device-resident image with its cached pyramid */
 
 int lego_klt_abi_version(void);
 const char *lego_klt_last_error(void);           /* thread-local message of the last failure       */
@@ -120,6 +121,21 @@ int lego_klt_track(lego_klt_ctx *ctx, const lego_klt_params *params,
 int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step,
                            int levels, uint8_t *out, size_t out_capacity,
                            int *level_cols, int *level_rows);
+
+/*
+ * Sequence mode: the reference rebuilds both pyramids inside every LKOpticalFlow4Layer
+ * call (src/algorithm.cpp:140-154), so in Frontend::Track the same left image is pyramided up to three
+ * times (img2 of the temporal track, img1 of the stereo match, img1 of the next temporal track).  An image
+ * handle uploads an image once and caches its pyramid; lego_klt_track_images runs the solver only and gives
+ * the same bytes as lego_klt_track on the same two images.
+ */
+int lego_klt_image_create(lego_klt_ctx *ctx, int cols, int rows, size_t step, int levels, lego_klt_image **out);
+void lego_klt_image_destroy(lego_klt_image *img);
+/* H2D + pyramid + aprons (asynchronous on the context stream; `data` is copied before returning). */
+int lego_klt_image_upload(lego_klt_image *img, const uint8_t *data);
+int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, const lego_klt_image *img1,
+                          const lego_klt_image *img2, const float *kp1_xy, float *kp2_xy, uint8_t *success, int n,
+                          lego_klt_stats *stats_or_null);
 
 /*
  * Batched path (north star (3)): B independent image pairs of one shape, n features per pair.

@@ -18,6 +18,7 @@ EXPORTS = [
     "lego_klt_build_pyramid", "lego_klt_batch_create", "lego_klt_batch_destroy", "lego_klt_batch_upload",
     "lego_klt_batch_run", "lego_klt_batch_download", "lego_klt_batch_timings", "lego_klt_track_batched",
     "lego_klt_batch_device_ptrs", "lego_klt_sync", "lego_klt_alloc_pinned", "lego_klt_free_pinned",
+    "lego_klt_image_create", "lego_klt_image_destroy", "lego_klt_image_upload", "lego_klt_track_images",
 ]
 
 
@@ -81,6 +82,11 @@ def load():
     lib.lego_klt_batch_timings.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.lego_klt_track_batched.argtypes = [vp, pp, vp, vp, vp, vp, vp, sp]
     lib.lego_klt_batch_device_ptrs.argtypes = [vp] + [C.POINTER(vp)] * 6
+    lib.lego_klt_image_create.argtypes = [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(vp)]
+    lib.lego_klt_image_destroy.argtypes = [vp]
+    lib.lego_klt_image_destroy.restype = None
+    lib.lego_klt_image_upload.argtypes = [vp, vp]
+    lib.lego_klt_track_images.argtypes = [vp, pp, vp, vp, vp, vp, vp, C.c_int, sp]
     lib.lego_klt_alloc_pinned.argtypes = [C.c_size_t]
     lib.lego_klt_alloc_pinned.restype = vp
     lib.lego_klt_free_pinned.argtypes = [vp]

@@ -111,6 +111,45 @@ class Tracker:
     def batch(self, batch: int, rows: int, cols: int, n_per_pair: int, levels: int = 4, step: int | None = None):
         return Batch(self, batch, rows, cols, n_per_pair, levels, step)
 
+    def image(self, rows: int, cols: int, levels: int = 4, step: int | None = None):
+        """Device-resident image with a cached pyramid (sequence mode)."""
+        return Image(self, rows, cols, levels, step)
+
+    def track_images(self, img1: "Image", img2: "Image", kp1, kp2, params: Params | None = None):
+        """lego_klt_track_images: solver only, on two uploaded images."""
+        params = params or make_params(img1.levels)
+        kp1 = np.ascontiguousarray(kp1, np.float32).reshape(-1, 2)
+        out = np.ascontiguousarray(kp2, np.float32).reshape(-1, 2).copy()
+        n = kp1.shape[0]
+        succ = np.zeros(max(n, 1), np.uint8)
+        st = Stats()
+        _lib.check(self._lib.lego_klt_track_images(self._h, C.byref(params), img1._h, img2._h, kp1.ctypes.data,
+                                                   out.ctypes.data, succ.ctypes.data, n, C.byref(st)),
+                   "lego_klt_track_images")
+        return out, succ[:n], st
+
+
+class Image:
+    """lego_klt_image: one uploaded image and its cached pyramid."""
+
+    def __init__(self, tracker: Tracker, rows: int, cols: int, levels: int = 4, step: int | None = None):
+        self._lib = tracker._lib
+        self.rows, self.cols, self.levels, self.step = rows, cols, levels, step or cols
+        h = C.c_void_p()
+        _lib.check(self._lib.lego_klt_image_create(tracker._h, cols, rows, self.step, levels, C.byref(h)),
+                   "lego_klt_image_create")
+        self._h = h
+        self._fin = weakref.finalize(self, self._lib.lego_klt_image_destroy, h)
+
+    def upload(self, img: np.ndarray):
+        if _img_args(img) != (self.rows, self.cols, self.step):
+            raise ValueError("image shape/step does not match the handle")
+        _lib.check(self._lib.lego_klt_image_upload(self._h, img.ctypes.data), "lego_klt_image_upload")
+        return self
+
+    def close(self):
+        self._fin()
+
 
 class Batch:
     """Device-resident batch of B independent image pairs (lego_klt_batch)."""

@@ -33,13 +33,14 @@ bool pyramid_level_sizes(int cols, int rows, int levels, int *lcols, int *lrows)
 cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan);
 void pyramid_plan_destroy(PyramidPlan *plan);
 // Builds levels 1..L-1 of images [img0, img0 + nimg) of both image sets from level 0, one fused launch.
-cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream);
+cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
+                           int n_sets = 2);
 // Re-pitches tight level-0 rows (`step` bytes per row, all images of the set back to back starting at the
 // 4-byte aligned `tight`, buffer padded by >= 8 bytes) of images [img0, img0+n_images) into the device layout.
 cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int img0, int n_images,
                           cudaStream_t stream);
 // Writes the row aprons (see LevelView) of every level of both image sets; run after launch_pyramid.
-cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream);
+cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream, int n_sets = 2);
 
 // ---- solver kernels ---------------------------------------------------------------------------
 cudaError_t launch_klt_exact(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);

@@ -83,6 +83,18 @@ struct lego_klt_batch {
     lego_klt_params last_params;
 };
 
+struct lego_klt_image {
+    lego_klt_ctx *ctx = nullptr;
+    int cols = 0, rows = 0, levels = 0;
+    size_t step = 0;
+    PyramidPlan plan;
+    PyramidView view;              // base[0] == base[1] == this image's levels
+    WarpKernelMaps *maps = nullptr;  // TMA descriptors for the role "img2"
+    uint8_t *d_levels = nullptr;
+    uint8_t *d_tight = nullptr;
+    bool valid = false;
+};
+
 namespace {
 
 int validate_params(const lego_klt_params *p, int levels_of_batch) {
@@ -212,14 +224,19 @@ int ensure_lane_buffers(lego_klt_batch *b) {
 
 // Pyramids + aprons + solver for images [img0, img0+nimg) (features f0 = img0*n .. ), on the context stream.
 // `chunk` selects the set of device work counters; `ring` (3 events) is recorded around the kernels if given.
-int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int nimg, int chunk, cudaEvent_t *ring) {
+int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int nimg, int chunk, cudaEvent_t *ring,
+              const PyramidView *view_override = nullptr, const WarpKernelMaps *maps_override = nullptr) {
     lego_klt_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
+    const PyramidView &view = view_override ? *view_override : b->view;   // cached pyramids of image handles
+    const WarpKernelMaps *maps = maps_override ? maps_override : b->maps;
     int *work = b->d_work + 4 * chunk;
     CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
     if (ring) CU_TRY(cudaEventRecord(ring[0], st));
-    CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
-    CU_TRY(launch_aprons(b->view, img0, nimg, st));
+    if (!view_override) {
+        CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
+        CU_TRY(launch_aprons(b->view, img0, nimg, st));
+    }
     if (ring) CU_TRY(cudaEventRecord(ring[1], st));
     SolverArgs a;
     a.kp1 = b->d_kp1;
@@ -253,16 +270,16 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
         return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the 7x7 forward configuration only");
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
-        CU_TRY(launch_klt_exact(b->view, a, st));
+        CU_TRY(launch_klt_exact(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
-        CU_TRY(launch_klt_warp(b->view, b->maps, a, ctx->sm_count, st));
+        CU_TRY(launch_klt_warp(view, maps, a, ctx->sm_count, st));
     } else if (a.n_total > 0) {
         int rc = ensure_lane_buffers(b);
         if (rc) return rc;
         a.templates = b->d_templates;
         a.feat_flag = b->d_feat_flag;
         a.epoch = (int)((b->runs % 0x3fffffff) + 1);
-        CU_TRY(launch_klt_template(b->view, a, st));
+        CU_TRY(launch_klt_template(view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
         CU_TRY(cudaEventRecord(b->ev_fork, st));
@@ -270,9 +287,9 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         SolverArgs aw = a;
         aw.list = a.defer_list;
         aw.list_count = a.defer_count;
-        CU_TRY(launch_klt_warp(b->view, b->maps, aw, ctx->sm_count, b->side));
+        CU_TRY(launch_klt_warp(view, maps, aw, ctx->sm_count, b->side));
         CU_TRY(cudaEventRecord(b->ev_join, b->side));
-        CU_TRY(launch_klt_lane(b->view, a, ctx->sm_count, st));
+        CU_TRY(launch_klt_lane(view, a, ctx->sm_count, st));
         CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
     }
     if (ring) CU_TRY(cudaEventRecord(ring[2], st));
@@ -658,6 +675,129 @@ int lego_klt_track(lego_klt_ctx *ctx, const lego_klt_params *params, const uint8
         memcpy(success, hs, (size_t)n);
     }
     return LEGO_KLT_OK;
+}
+
+int lego_klt_image_create(lego_klt_ctx *ctx, int cols, int rows, size_t step, int levels, lego_klt_image **out) {
+    if (out) *out = nullptr;
+    if (!ctx || !out) return fail(LEGO_KLT_ERR_BAD_ARG, "null ctx/out");
+    if (cols <= 0 || rows <= 0 || step < (size_t)cols || levels < 1 || levels > kMaxLevels)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "bad image shape");
+    int lc[kMaxLevels], lr[kMaxLevels];
+    if (!pyramid_level_sizes(cols, rows, levels, lc, lr))
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "pyramid level would be empty for %dx%d, %d levels", cols, rows, levels);
+    CU_TRY(cudaSetDevice(ctx->device));
+    lego_klt_image *im = new (std::nothrow) lego_klt_image();
+    if (!im) return fail(LEGO_KLT_ERR_BAD_ARG, "out of host memory");
+    im->ctx = ctx;
+    im->cols = cols;
+    im->rows = rows;
+    im->step = step;
+    im->levels = levels;
+    memset(&im->view, 0, sizeof(im->view));
+    im->view.levels = levels;
+    im->view.n_images = 1;
+    int pitch[kMaxLevels];
+    size_t total = 0, off[kMaxLevels];
+    for (int l = 0; l < levels; ++l) {
+        LevelView &lv = im->view.lv[l];
+        lv.cols = lc[l];
+        lv.rows = lr[l];
+        lv.step = (l == 0) ? (int)step : lc[l];
+        pitch[l] = kApronL + (int)align_up((size_t)lv.step, 16) + kApronR;
+        lv.pitch = pitch[l];
+        lv.slot = (unsigned long long)lr[l] * pitch[l];
+        off[l] = total;
+        total += align_up((size_t)lv.slot + 2 * kApronL + 64, 256);
+    }
+    total += 4096;
+    auto cleanup = [&](int code) {
+        lego_klt_image_destroy(im);
+        return code;
+    };
+    cudaError_t e = cudaMalloc(&im->d_levels, total);
+    if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMalloc image levels: %s", cudaGetErrorString(e)));
+    e = cudaMemsetAsync(im->d_levels, 0, total, ctx->stream);
+    if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMemset image: %s", cudaGetErrorString(e)));
+    for (int l = 0; l < levels; ++l) im->view.lv[l].base[0] = im->view.lv[l].base[1] = im->d_levels + off[l] + kApronL;
+    e = cudaMalloc(&im->d_tight, align_up((size_t)rows * step + 256, 256));
+    if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMalloc landing buffer: %s", cudaGetErrorString(e)));
+    if ((e = pyramid_plan_create(cols, rows, levels, pitch, &im->plan)) != cudaSuccess)
+        return cleanup(fail(LEGO_KLT_ERR_CUDA, "pyramid plan: %s", cudaGetErrorString(e)));
+    if ((e = warp_maps_create(im->view, &im->maps)) != cudaSuccess)
+        return cleanup(fail(LEGO_KLT_ERR_CUDA, "TMA descriptor creation failed: %s", cudaGetErrorString(e)));
+    *out = im;
+    return LEGO_KLT_OK;
+}
+
+void lego_klt_image_destroy(lego_klt_image *im) {
+    if (!im) return;
+    cudaSetDevice(im->ctx->device);
+    cudaStreamSynchronize(im->ctx->stream);
+    if (im->maps) warp_maps_destroy(im->maps);
+    pyramid_plan_destroy(&im->plan);
+    cudaFree(im->d_levels);
+    cudaFree(im->d_tight);
+    cudaGetLastError();
+    delete im;
+}
+
+int lego_klt_image_upload(lego_klt_image *im, const uint8_t *data) {
+    if (!im || !data) return fail(LEGO_KLT_ERR_BAD_ARG, "null image/data");
+    lego_klt_ctx *ctx = im->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t img_bytes = (size_t)im->rows * im->step;
+    int rc = ensure_pinned(ctx, 2 * img_bytes);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
+    const size_t valid = (size_t)(im->rows - 1) * im->step + (size_t)im->cols;  // what a cv::Mat guarantees
+    memcpy(ctx->pinned, data, valid);
+    memset(ctx->pinned + valid, 0, img_bytes - valid);
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemcpyAsync(im->d_tight, ctx->pinned, img_bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(launch_ingest(im->d_tight, im->view.lv[0], 0, 0, 1, st));
+    CU_TRY(launch_pyramid(im->plan, im->view, 0, 1, st, 1));
+    CU_TRY(launch_aprons(im->view, 0, 1, st, 1));
+    im->valid = true;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, const lego_klt_image *img1,
+                          const lego_klt_image *img2, const float *kp1_xy, float *kp2_xy, uint8_t *success, int n,
+                          lego_klt_stats *stats) {
+    if (!ctx || !params || !img1 || !img2) return fail(LEGO_KLT_ERR_BAD_ARG, "null argument");
+    if (img1->ctx != ctx || img2->ctx != ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "image belongs to another context");
+    if (!img1->valid || !img2->valid) return fail(LEGO_KLT_ERR_STATE, "lego_klt_track_images before lego_klt_image_upload");
+    if (img1->cols != img2->cols || img1->rows != img2->rows || img1->step != img2->step || img1->levels != img2->levels)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "img1 and img2 must have the same shape, step and levels");
+    if (params->levels != img1->levels)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "params->levels (%d) != cached pyramid levels (%d)", params->levels, img1->levels);
+    if (n < 0 || (n > 0 && (!kp1_xy || !kp2_xy || !success))) return fail(LEGO_KLT_ERR_BAD_ARG, "bad keypoint arguments");
+    int rc = ensure_single(ctx, img1->cols, img1->rows, img1->step, n, params->levels);  // keypoint / scratch buffers
+    if (rc) return rc;
+    lego_klt_batch *b = ctx->single;
+    rc = validate_params(params, b->levels);
+    if (rc) return rc;
+    b->n_active = n;
+    const size_t kp_bytes = (size_t)n * sizeof(float2);
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaSetDevice(ctx->device));
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, kp_bytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, kp_bytes, cudaMemcpyHostToDevice, st));
+    }
+    PyramidView view = img1->view;
+    for (int l = 0; l < view.levels; ++l) view.lv[l].base[1] = img2->view.lv[l].base[0];
+    CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    CU_TRY(cudaEventRecord(b->ev[EV_START], st));
+    CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
+    cudaEvent_t *ring = b->ring[b->runs % kRing];
+    rc = run_range(b, params, 0, 1, 0, ring, &view, img2->maps);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
+    ++b->runs;
+    b->ran = true;
+    b->last_chunked = false;
+    return lego_klt_batch_download(b, kp2_xy, success, stats);
 }
 
 int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step, int levels,

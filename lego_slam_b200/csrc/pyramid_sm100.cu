@@ -186,13 +186,13 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
 // Row aprons: one WARP per (level, set, image, row): 32 + ~50 bytes per row, lanes write them in parallel.
 // Tiny next to the pyramid itself, and it lets the solver stage windows with unconditional aligned loads.
 __global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total, int img0,
-                                                    int nimg) {
+                                                    int nimg, int n_sets) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= rows_total) return;
     int level = 0, r = t;
-    while (r >= pyr.lv[level].rows * 2 * nimg) {
-        r -= pyr.lv[level].rows * 2 * nimg;
+    while (r >= pyr.lv[level].rows * n_sets * nimg) {
+        r -= pyr.lv[level].rows * n_sets * nimg;
         ++level;
     }
     const LevelView &lv = pyr.lv[level];
@@ -238,7 +238,7 @@ ingest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst_base, i
 }  // namespace
 
 cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int img0, int n_images,
-                          cudaStream_t stream) {
+                          cudaStream_t stream) {  // (single-image handles pass set = 0)
     const long long n_rows = (long long)n_images * l0.rows;
     if (n_rows <= 0) return cudaSuccess;
     const long long total = n_rows * ((l0.step + 3) >> 2);
@@ -248,11 +248,11 @@ cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, in
     return cudaGetLastError();
 }
 
-cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream) {
+cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream, int n_sets) {
     int rows_total = 0;
-    for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * 2 * nimg;
+    for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * n_sets * nimg;
     if (rows_total <= 0) return cudaSuccess;
-    apron_kernel<<<(rows_total + 7) / 8, 256, 0, stream>>>(pyr, rows_total, img0, nimg);
+    apron_kernel<<<(rows_total + 7) / 8, 256, 0, stream>>>(pyr, rows_total, img0, nimg, n_sets);
     return cudaGetLastError();
 }
 
@@ -335,7 +335,8 @@ void pyramid_plan_destroy(PyramidPlan *plan) {
     *plan = PyramidPlan();
 }
 
-cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream) {
+cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
+                           int n_sets) {
     if (plan.levels <= 1 || nimg <= 0) return cudaSuccess;
     PyrKernelParams kp;
     for (int l = 0; l < kMaxLevels; ++l) {
@@ -354,7 +355,7 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int 
         configured = plan.smem_bytes;
     }
     const int top = plan.levels - 1;
-    dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, 2 * nimg);
+    dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, n_sets * nimg);
     pyramid_fused_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
     return cudaGetLastError();
 }

@@ -220,6 +220,31 @@ def test_subpixel_keypoints_and_deferred_features(tracker, oracle):
             assert 0 < int(st.n_deferred) < n // 2, int(st.n_deferred)
 
 
+def test_sequence_mode_image_handles_equal_pairwise_calls(tracker, oracle):
+    """SURVEY.md 8f N1: Frontend::Track does temporal (last-left -> cur-left) and stereo (cur-left -> cur-right)
+    tracking per frame; with image handles every image is uploaded and pyramided once, and the results are the
+    same bytes as the pairwise entry point (which the oracle parity tests cover)."""
+    rows, cols, n = 376, 1241, 2000
+    lefts = [synth.next_frame(rows, cols, 2, f)[0] for f in range(3)]
+    rights = [np.ascontiguousarray(np.roll(img, -7, axis=1)) for img in lefts]
+    h_left = [tracker.image(rows, cols, 4).upload(img) for img in lefts]
+    h_right = [tracker.image(rows, cols, 4).upload(img) for img in rights]
+    kp = synth.detect_features(lefts[0], n, min_dist=5, seed=3)
+    for f in (1, 2):
+        for kernel in (klt.KERNEL_AUTO, klt.KERNEL_WARP):
+            p = klt.make_params(kernel=kernel)
+            a, sa, st_a = tracker.track_images(h_left[f - 1], h_left[f], kp, kp, p)        # temporal
+            b, sb, st_b = tracker.track(lefts[f - 1], lefts[f], kp, kp, p)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(sa, sb)
+            assert _iters(st_a, 4) == _iters(st_b, 4)
+            c, sc, _ = tracker.track_images(h_left[f], h_right[f], a, a, p)               # stereo on tracked points
+            d, sd, _ = tracker.track(lefts[f], rights[f], a, a, p)
+            assert np.array_equal(c.view(np.uint32), d.view(np.uint32)) and np.array_equal(sc, sd)
+        ref, rs, _ = oracle.track(lefts[f - 1], lefts[f], kp, kp, threads=8)
+        assert_parity(a, sa, ref, rs, cols, rows, f"sequence frame {f}")
+        kp = a  # tracked (sub-pixel) points feed the next frame, like the reference's frontend
+
+
 def test_lane_kernel_rejects_unsupported_configurations(tracker):
     from lego_slam_b200 import _lib
     img = np.zeros((64, 64), np.uint8)
