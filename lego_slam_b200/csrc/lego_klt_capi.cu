@@ -565,7 +565,11 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
                            lego_klt_stats *stats) {
     if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
     // Small batches: plain upload -> run -> download.
+    // Equal chunks: more / smaller chunks shorten the pipeline tail but cost launches and solver efficiency
+    // (10 chunks with a fine tail measured 6 % slower than 8 equal ones).
+    int bounds[kMaxChunks + 1];
     const int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
+    for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
     if (n_chunks == 1) {
         int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
         if (rc) return rc;
@@ -594,7 +598,7 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
     const int n = b->n_active;
     for (int c = 0; c < n_chunks; ++c) {
-        const int img0 = (int)((long long)b->B * c / n_chunks), img1 = (int)((long long)b->B * (c + 1) / n_chunks);
+        const int img0 = bounds[c], img1 = bounds[c + 1];
         const int nimg = img1 - img0;
         if (nimg <= 0) continue;
         CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));

@@ -183,21 +183,23 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
     }
 }
 
-// Row aprons: one WARP per (level, set, image, row): 32 + ~50 bytes per row, lanes write them in parallel.
-// Tiny next to the pyramid itself, and it lets the solver stage windows with unconditional aligned loads.
-__global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ PyramidView pyr, int rows_total, int img0,
-                                                    int nimg, int n_sets) {
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (t >= rows_total) return;
-    int level = 0, r = t;
-    while (r >= pyr.lv[level].rows * n_sets * nimg) {
-        r -= pyr.lv[level].rows * n_sets * nimg;
-        ++level;
+// Row aprons: one WARP per row; grid = (row blocks of all levels, image * set) so that no thread divides by a run-time
+// size (the first version spent 180 instructions per row on index arithmetic: profiles/README.md).  32 + ~50
+// bytes per row, written by the lanes in parallel; tiny next to the pyramid itself, and it lets the solver
+// stage windows with unconditional aligned loads.
+__global__ void __launch_bounds__(256) apron_kernel(const __grid_constant__ PyramidView pyr, int img0, int nimg) {
+    int level = 0, rb = blockIdx.x;  // blockIdx.x runs over the row blocks of all levels, level 0 first
+    for (; level < pyr.levels - 1; ++level) {
+        const int nb = (pyr.lv[level].rows + 7) >> 3;
+        if (rb < nb) break;
+        rb -= nb;
     }
     const LevelView &lv = pyr.lv[level];
-    const int row = r % lv.rows;
-    const int k = img0 + (r / lv.rows) % nimg, set = r / (lv.rows * nimg);
+    const int row = rb * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= lv.rows) return;
+    const int set = blockIdx.y >= nimg ? 1 : 0;
+    const int k = img0 + blockIdx.y - set * nimg;
     uint8_t *rp = lv.base[set] + (size_t)k * lv.slot + (size_t)row * lv.pitch;
     const uint32_t first = rp[0], last = rp[lv.cols - 1];
     // data[row*step + cols] of the reference's flat addressing
@@ -249,10 +251,11 @@ cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, in
 }
 
 cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream, int n_sets) {
-    int rows_total = 0;
-    for (int l = 0; l < pyr.levels; ++l) rows_total += pyr.lv[l].rows * n_sets * nimg;
-    if (rows_total <= 0) return cudaSuccess;
-    apron_kernel<<<(rows_total + 7) / 8, 256, 0, stream>>>(pyr, rows_total, img0, nimg, n_sets);
+    if (nimg <= 0 || pyr.levels <= 0) return cudaSuccess;
+    int row_blocks = 0;
+    for (int l = 0; l < pyr.levels; ++l) row_blocks += (pyr.lv[l].rows + 7) / 8;
+    dim3 grid(row_blocks, n_sets * nimg);
+    apron_kernel<<<grid, 256, 0, stream>>>(pyr, img0, nimg);
     return cudaGetLastError();
 }
 
