@@ -76,11 +76,6 @@ struct LaneSmem {
     unsigned stats[kStatCount];
 };
 
-template <int T>
-struct TemplateSmem {
-    uint32_t win[kTplRows * kWin2Words][T + 1];
-};
-
 __device__ __forceinline__ float byte_to_float(uint32_t packed, int k) {
     // place byte k in the low mantissa of 2^23 and subtract 2^23: exact, ALU + FADD, no XU convert
     return __fadd_rn(__uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7440u + k)), -8388608.0f);
@@ -262,12 +257,37 @@ __device__ __forceinline__ float level_coord(float k0, int L, int level) {
 // Template kernel: I1 patch of every (feature, level).  Item i -> level = L-1 - i / n_total (coarse
 // levels first), feature = i % n_total, so a warp works on neighbouring features of one level.
 // ------------------------------------------------------------------------------------------------
+// Ten consecutive pixels starting at byte `ox` (0..22) of a 32-byte row held in two uint4 registers: the
+// word offset ox>>2 (0..5) is applied with a 3-stage select network (registers cannot be indexed
+// dynamically), the byte offset with funnel shifts.  No shared memory: the first version of this kernel
+// bounced every row through shared memory and was MIO-throttled (profiles/README.md).
+__device__ __forceinline__ void row10_from_regs(const uint4 &q0, const uint4 &q1, int k, int sh, float (&row)[G + 1]) {
+    const uint32_t w[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0u};
+    const bool k4 = (k & 4) != 0, k2 = (k & 2) != 0, k1 = (k & 1) != 0;
+    uint32_t t[5], o[4];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const uint32_t a = w[j], b2 = w[min(j + 2, 8)], b4 = w[min(j + 4, 8)];
+        t[j] = k4 ? b4 : (k2 ? b2 : a);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = k1 ? t[j + 1] : t[j];
+    const uint32_t b0 = __funnelshift_r(o[0], o[1], sh), b1 = __funnelshift_r(o[1], o[2], sh), b2 = __funnelshift_r(o[2], o[3], sh);
+    row[0] = byte_to_float(b0, 0);
+    row[1] = byte_to_float(b0, 1);
+    row[2] = byte_to_float(b0, 2);
+    row[3] = byte_to_float(b0, 3);
+    row[4] = byte_to_float(b1, 0);
+    row[5] = byte_to_float(b1, 1);
+    row[6] = byte_to_float(b1, 2);
+    row[7] = byte_to_float(b1, 3);
+    row[8] = byte_to_float(b2, 0);
+    row[9] = byte_to_float(b2, 1);
+}
+
 template <int T>
 __global__ void __launch_bounds__(T)
 klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TemplateSmem<T> &sm = *reinterpret_cast<TemplateSmem<T> *>(smem_raw);
-    constexpr int WS = T + 1;
     const int tid = threadIdx.x;
     const int L = pyr.levels;
     const long long item = (long long)blockIdx.x * T + tid;
@@ -300,18 +320,24 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         }
     }
     if (regular) {
-        // the 7x7 centre of the 9x9 grid needs window rows iyn+1 .. iyn+8 and columns ixn+1 .. ixn+8
+        // the 7x7 centre of the 9x9 grid needs image rows iyn+1 .. iyn+8 and columns ixn+1 .. ixn+8
         const int wx0 = (ixn - 2) & ~15, wy0 = iyn + 1;
-        uint32_t *col = &sm.win[0][tid];
-        stage_own_window<kTplRows, WS>(lv.base[0] + (size_t)img * lv.slot, lv, wx0, wy0, col);
         const int ox = ixn - wx0;
-        const int sh = (ox & 3) * 8;
-        const uint32_t *wp = col + (ox >> 2) * WS;
+        const int k = ox >> 2, sh = (ox & 3) * 8;
+        const uint8_t *img1 = lv.base[0] + (size_t)img * lv.slot;
+        uint4 q[kTplRows][2];
+#pragma unroll
+        for (int i = 0; i < kTplRows; ++i) {  // all 16 loads in flight; rows clamped, columns from the aprons
+            const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+            const uint4 *rp = reinterpret_cast<const uint4 *>(img1 + (ptrdiff_t)ry * lv.pitch + wx0);
+            q[i][0] = __ldg(rp);
+            q[i][1] = __ldg(rp + 1);
+        }
         float rowA[G + 1], rowB[G + 1];
-        load_row10<WS>(wp, 0, sh, rowA);
+        row10_from_regs(q[0][0], q[0][1], k, sh, rowA);
 #pragma unroll
         for (int y = 0; y < P; ++y) {
-            load_row10<WS>(wp, y + 1, sh, rowB);
+            row10_from_regs(q[y + 1][0], q[y + 1][1], k, sh, rowB);
 #pragma unroll
             for (int x = 0; x < P; ++x)
                 buf[y * P + x] = bilerp(omx[x + 1], xx[x + 1], omy[y + 1], yy[y + 1], rowA[x + 1], rowA[x + 2], rowB[x + 1],
@@ -660,10 +686,9 @@ size_t lane_template_bytes(int n_total, int levels) { return (size_t)n_total * l
 cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
     auto kernel = klt_template_kernel<kTplThreads>;
-    const size_t smem = sizeof(TemplateSmem<kTplThreads>);
     const long long items = (long long)args.n_total * pyr.levels;
     const int grid = (int)((items + kTplThreads - 1) / kTplThreads);
-    kernel<<<grid, kTplThreads, smem, stream>>>(pyr, args);
+    kernel<<<grid, kTplThreads, 0, stream>>>(pyr, args);
     return cudaGetLastError();
 }
 
