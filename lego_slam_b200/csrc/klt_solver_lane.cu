@@ -16,12 +16,14 @@
 // feature (no shuffles, no idle lanes in the solve).  Divergence in iteration counts (1..10 per level)
 // is removed by a state machine: each trip of the main loop is exactly one pass for every runnable
 // thread; a thread that converges moves to its next level / next feature while its neighbours keep
-// iterating.  Level set-up (template fetch + img2 window staging) is per thread but BATCHED: threads
-// wait until enough of the warp needs set-up, so the divergent set-up code is issued rarely.
+// iterating.  Level set-up (template fetch + img2 window staging) is a per-thread, divergent section run
+// whenever at least LANE_BATCH threads of the warp need it (measured best: 1 with three CTAs per SM, whose
+// 12 warps hide the set-up's memory round trips; 10 with two CTAs).
 //
 // Shared memory, per thread, word-interleaved  [word][T+1]  (bank = (word + thread) % 32, so a warp
-// reading "its" word w is conflict-free):  img2 window 32x14 bytes (16-byte aligned origin, border
-// semantics baked in by the stager), template 49 floats, 18 row weights.
+// reading "its" word w is conflict-free):  img2 window 24x12 bytes (8-byte aligned origin; the border
+// semantics come from the row aprons), template 49 floats, 18 row weights -- 556 bytes per thread, so that
+// three CTAs of 128 threads fit an SM.
 //
 // Bit-fidelity contract (same as the warp kernel): every fp32 value entering the sums is bit-identical
 // to the reference's; only the ORDER of the fp64 additions differs (row-major here, x-outer there; all
@@ -46,20 +48,39 @@ namespace legoklt {
 namespace {
 
 constexpr int LO = -3, HI = 3, P = 7, G = 9;
-constexpr int kWin2Rows = 14, kWin2Words = 8;                 // img2 window: 14 rows x 32 bytes per thread
+#ifndef LANE_WROWS
+#define LANE_WROWS 12
+#endif
+#ifndef LANE_WWORDS
+#define LANE_WWORDS 6
+#endif
+#ifndef LANE_PAD
+#define LANE_PAD 0
+#endif
+#ifndef LANE_QUEUE
+#define LANE_QUEUE 32
+#endif
+// img2 window per thread: LANE_WROWS rows x LANE_WWORDS*4 bytes.  8 words: origin aligned to 16 bytes (two 16-byte
+// loads per row); 6 words: origin aligned to 8 bytes (three 8-byte loads per row) -- the smaller footprint lets
+// three CTAs of 128 threads share an SM.
+constexpr int kWin2Rows = LANE_WROWS, kWin2Words = LANE_WWORDS;
+constexpr int kWinAlign = (LANE_WWORDS == 8) ? 16 : 8;
+constexpr int kWinSlackL = (LANE_WWORDS == 8) ? 2 : 3;         // footprint starts kWinSlackL..kWinSlackL+kWinAlign-1 bytes in
+constexpr int kWinSlackT = (LANE_WROWS - (G + 1)) / 2;         // rows above the footprint
 constexpr int kWin2Total = kWin2Rows * kWin2Words;            // 112 words
 constexpr int kTplRows = 8;                                   // img1 window rows in the template kernel
 constexpr int kI1Count = P * P;                               // 49 floats, index y*P + x
-constexpr int kQueue = 64;                                    // feature ring entries per warp
+constexpr int kQueue = LANE_QUEUE;                            // feature ring entries per warp (power of two, >= 32)
+static_assert(kQueue >= 32 && (kQueue & (kQueue - 1)) == 0, "ring size");
 constexpr int kTplStride = 52;                                // floats per (feature, level): 49 + flag + pad
 #ifndef LANE_BATCH
-#define LANE_BATCH 10
+#define LANE_BATCH 1
 #endif
 #ifndef LANE_T
 #define LANE_T 128
 #endif
 #ifndef LANE_CTAS
-#define LANE_CTAS 2
+#define LANE_CTAS 3
 #endif
 constexpr int kSetupBatch = LANE_BATCH;                       // blocked threads per warp that trigger set-up
 
@@ -67,9 +88,11 @@ enum : int { ST_FETCH = 0, ST_LEVEL = 1, ST_RUN = 2, ST_DONE = 3 };
 
 template <int T>
 struct LaneSmem {
-    uint32_t win2[kWin2Total][T + 1];
-    float i1[kI1Count][T + 1];
-    float wy[2 * G][T + 1];  // per grid row: [2r] = 1-frac, [2r+1] = frac (dynamic row index in the rolled loop)
+    // word stride T + LANE_PAD: with per-thread stores and loads the bank is decided by the thread index alone,
+    // so the padding (needed by the first, warp-cooperative stager) is optional
+    uint32_t win2[kWin2Total][T + LANE_PAD];
+    float i1[kI1Count][T + LANE_PAD];
+    float wy[2 * G][T + LANE_PAD];  // per grid row: [2r] = 1-frac, [2r+1] = frac (dynamic row index in the rolled loop)
     // per-warp ring of fetched features: one global atomic + coalesced keypoint loads per 32 features
     float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
     int q_id[T / 32][kQueue];
@@ -153,43 +176,43 @@ __device__ __forceinline__ bool offsets_exact(float k) {
 // column `dst` of a word-interleaved window (row r, word w at dst[(r*8 + w) * WS]).  Rows are clamped to
 // the image; columns outside [0, cols) come from the row aprons (LevelView), so every load is an aligned
 // 16-byte load.  The caller guarantees window_in_apron(lv, wx0).
-__device__ __forceinline__ bool window_in_apron(const LevelView &lv, int wx0) {
-    return wx0 >= -kApronL && wx0 + kWin2Words * 4 <= lv.pitch - kApronL;
+__device__ __forceinline__ bool window_in_apron(const LevelView &lv, int wx0, int width_bytes = kWin2Words * 4) {
+    return wx0 >= -kApronL && wx0 + width_bytes <= lv.pitch - kApronL;
 }
 
 template <int ROWS>
-__device__ __forceinline__ void window_load(const uint8_t *img, const LevelView &lv, int wx0, int wy0, uint4 (&v)[ROWS][2]) {
+__device__ __forceinline__ void window_load(const uint8_t *img, const LevelView &lv, int wx0, int wy0,
+                                            uint32_t (&v)[ROWS][kWin2Words]) {
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) {
         const int ry = min(max(wy0 + i, 0), lv.rows - 1);
-        const uint4 *rp = reinterpret_cast<const uint4 *>(img + (ptrdiff_t)ry * lv.pitch + wx0);
-        v[i][0] = __ldg(rp);
-        v[i][1] = __ldg(rp + 1);
-    }
-}
-
-template <int ROWS, int WS>
-__device__ __forceinline__ void window_store(const uint4 (&v)[ROWS][2], uint32_t *dst) {
+        const uint8_t *rp = img + (ptrdiff_t)ry * lv.pitch + wx0;
+        if (kWinAlign == 16) {
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) {
-        uint32_t *d = dst + i * kWin2Words * WS;
-        d[0] = v[i][0].x;
-        d[WS] = v[i][0].y;
-        d[2 * WS] = v[i][0].z;
-        d[3 * WS] = v[i][0].w;
-        d[4 * WS] = v[i][1].x;
-        d[5 * WS] = v[i][1].y;
-        d[6 * WS] = v[i][1].z;
-        d[7 * WS] = v[i][1].w;
+            for (int q = 0; q < kWin2Words / 4; ++q) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(rp) + q);
+                v[i][4 * q] = t.x;
+                v[i][4 * q + 1] = t.y;
+                v[i][4 * q + 2] = t.z;
+                v[i][4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < kWin2Words / 2; ++q) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2 *>(rp) + q);
+                v[i][2 * q] = t.x;
+                v[i][2 * q + 1] = t.y;
+            }
+        }
     }
 }
 
 template <int ROWS, int WS>
-__device__ __forceinline__ void stage_own_window(const uint8_t *img, const LevelView &lv, int wx0, int wy0,
-                                                 uint32_t *dst) {
-    uint4 v[ROWS][2];
-    window_load<ROWS>(img, lv, wx0, wy0, v);
-    window_store<ROWS, WS>(v, dst);
+__device__ __forceinline__ void window_store(const uint32_t (&v)[ROWS][kWin2Words], uint32_t *dst) {
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+        for (int w = 0; w < kWin2Words; ++w) dst[(i * kWin2Words + w) * WS] = v[i][w];
 }
 
 // Ten consecutive window pixels of row i (starting at the footprint's first column) as floats.
@@ -310,7 +333,7 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     float buf[kTplStride];
 #pragma unroll
     for (int i = 0; i < kTplStride; ++i) buf[i] = 0.f;
-    if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15);
+    if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15, 32);
     if (!regular) {
         // the whole feature goes to the exact warp kernel (which runs concurrently with the lane kernel)
         if (atomicExch(&args.feat_flag[f], args.epoch) != args.epoch) {
@@ -354,6 +377,9 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // Solver kernel.
 // ------------------------------------------------------------------------------------------------
+#ifndef LANE_PREFETCH
+#define LANE_PREFETCH 0
+#endif
 #ifndef LANE_MAXREG
 #define LANE_MAXREG 0
 #endif
@@ -369,7 +395,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     LaneSmem<T> &sm = *reinterpret_cast<LaneSmem<T> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int WS = T + 1;  // word stride between consecutive window words of one thread
+    constexpr int WS = T + LANE_PAD;  // word stride between consecutive window words of one thread
     int q_head = 0, q_tail = 0;  // warp-uniform ring positions
     bool global_done = false;
 
@@ -398,12 +424,14 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 const int need = __popc(m);
                 int avail = q_tail - q_head;
                 if (avail < need && !global_done) {
-                    // refill: 32 consecutive feature ids, coalesced loads, compacted into the warp's ring
+                    // refill: top the ring up with consecutive feature ids (never more than its free slots),
+                    // coalesced loads, compacted into the ring
+                    const int want = min(32, kQueue - avail);
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(args.work_counter, 32);
+                    if (lane == 0) base = atomicAdd(args.work_counter, want);
                     base = __shfl_sync(FULL, base, 0);
                     const int local = base + lane;
-                    bool keep = local < args.n_total;
+                    bool keep = lane < want && local < args.n_total;
                     float2 a1 = make_float2(0.f, 0.f), a2 = a1;
                     const int gid = args.f0 + local;
                     if (keep) {
@@ -419,7 +447,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         sm.q_id[warp][pos] = gid;
                     }
                     q_tail += __popc(km);
-                    if (base + 32 >= args.n_total) global_done = true;
+                    if (base + want >= args.n_total) global_done = true;
                     __syncwarp();
                     avail = q_tail - q_head;
                 }
@@ -475,8 +503,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 no_window = true;  // estimate far outside the image / its apron: exact per-pixel passes
                 if (fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6) {
                     const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
-                    wx0 = (ixn - 2) & ~15;
-                    wy0 = iyn - 2;
+                    wx0 = (ixn - kWinSlackL) & ~(kWinAlign - 1);
+                    wy0 = iyn - kWinSlackT;
                     no_window = !window_in_apron(lv, wx0);
                 }
                 // Template first (13 x 16 B in flight), then the window in two halves (14 x 16 B in flight each):
@@ -503,7 +531,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     }
                 }
                 if (!no_window) {
-                    uint4 wv[kHalf][2];
+                    uint32_t wv[kHalf][kWin2Words];
                     window_load<kHalf>(img2, lv, wx0, wy0, wv);
                     window_store<kHalf, WS>(wv, &sm.win2[0][tid]);
                     window_load<kHalf>(img2, lv, wx0, wy0 + kHalf, wv);
@@ -654,6 +682,29 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     }
                     --level;
                     state = ST_LEVEL;
+#if LANE_PREFETCH
+                    {   // warm L1/L2 with what the next set-up will load: the template and the window rows
+                        const LevelView &nl = pyr.lv[level];
+                        const double Sx = (double)k1.x + (double)(k2.x - k1.x), Sy = (double)k1.y + (double)(k2.y - k1.y);
+                        if (fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6) {
+                            const int nix = __double2int_rd(Sx + (double)(LO - 1)), niy = __double2int_rd(Sy + (double)(LO - 1));
+                            const int pwx = (nix - kWinSlackL) & ~(kWinAlign - 1), pwy = niy - kWinSlackT;
+                            if (window_in_apron(nl, pwx)) {
+                                const uint8_t *nimg = nl.base[1] + (size_t)img * nl.slot;
+#pragma unroll
+                                for (int i = 0; i < kWin2Rows; ++i) {
+                                    const int ry = min(max(pwy + i, 0), nl.rows - 1);
+                                    const uint8_t *pa = nimg + (ptrdiff_t)ry * nl.pitch + pwx;
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + kWin2Words * 4 - 1));
+                                }
+                            }
+                        }
+                        const char *nt = reinterpret_cast<const char *>(args.templates + ((size_t)feat * L + level) * kTplStride);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nt));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nt + 128));
+                    }
+#endif
                 } else {
                     args.kp2_out[feat] = k2;
                     args.success[feat] = flag ? 1 : 0;

@@ -152,6 +152,31 @@ def test_config3_batched_pairs_match_oracle_per_pair(tracker, oracle, kernel):
     batch.close()
 
 
+def test_large_batch_fast_kernels_equal_exact_kernel(tracker):
+    """More features than resident threads (several features per thread, ring refills with leftovers): every
+    output of the fast kernels must be written and match the EXACT kernel, which is bit-identical to the oracle
+    (checked above).  Buffers are separate per kernel so an unwritten output cannot hide behind an earlier run."""
+    B, rows, cols, n = 64, 188, 620, 2000
+    base = [synth.stereo_case(rows, cols, n, seed=3000 + i) for i in range(4)]
+    imgs1 = np.stack([base[b % 4][0] for b in range(B)])
+    imgs2 = np.stack([base[b % 4][1] for b in range(B)])
+    kp1 = np.stack([base[b % 4][2] for b in range(B)])
+    kp2 = np.stack([base[b % 4][3] for b in range(B)])
+    res = {}
+    for kernel in (klt.KERNEL_EXACT, klt.KERNEL_LANE, klt.KERNEL_WARP):
+        batch = tracker.batch(B, rows, cols, n, levels=4)
+        batch.upload(imgs1, imgs2, kp1, kp2)
+        batch.run(klt.make_params(kernel=kernel))
+        o, s, st = batch.download()
+        res[kernel] = (o, s, _iters(st, 4), int(st.n_success))
+        batch.close()
+    eo, es, eit, esucc = res[klt.KERNEL_EXACT]
+    for kernel in (klt.KERNEL_LANE, klt.KERNEL_WARP):
+        o, s, it, ns = res[kernel]
+        assert_parity(o, s, eo, es, cols, rows, f"large batch kernel={kernel}")
+        assert it == eit and ns == esucc == int(es.sum())
+
+
 def test_batch_is_idempotent_and_equals_single_calls(tracker):
     """size-independent property: re-running a resident batch gives the same bytes, and each pair of
     the batch equals the single-pair entry point on that pair."""
