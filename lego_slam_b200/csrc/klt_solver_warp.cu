@@ -97,6 +97,12 @@ __device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *map,
         : "memory");
 }
 
+// Out-of-line GetPixelValue: the generic sampler inlined at ~15 call sites made the kernel 7.7k SASS
+// instructions (123 KB, far beyond the instruction cache); the fast path does not use it.
+__device__ __noinline__ float sample_flat_ool(const uint8_t *img, const LevelView &lv, float x, float y) {
+    return sample_flat(img, lv, x, y);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -130,7 +136,9 @@ __device__ __forceinline__ float grid_coord(float k, double d, int c, int lo, in
     return v;
 }
 
-template <int NR>
+// PT = compile-time patch width (0 = run-time): the generic version spent 15 % of its instructions on
+// integer divisions by the run-time patch / grid width (profiles/r01_ncu_warp_kernel.csv).
+template <int NR, int PT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ WarpKernelMaps maps,
                 const __grid_constant__ SolverArgs args) {
@@ -148,7 +156,7 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
     const int L = pyr.levels;
     const int lo = args.patch_lo, hi = args.patch_hi;
-    const int P = hi - lo + 1, G = P + 2, PP = P * P, GG = G * G;
+    const int P = PT ? PT : hi - lo + 1, G = P + 2, PP = P * P, GG = G * G;
     const bool inverse = args.inverse != 0;
     const double scale_top = 1.0 / (double)(1 << (L - 1));
     uint32_t tma_phase = 0;
@@ -187,10 +195,10 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 gx1[r] = gy1[r] = 0.f;
                 if (p < PP) {
                     const float fx = kx + (float)(lo + p / P), fy = ky + (float)(lo + p % P);
-                    I1[r] = sample_flat(img1, lv, fx, fy);
+                    I1[r] = sample_flat_ool(img1, lv, fx, fy);
                     if (inverse) {  // :74-80, evaluated on the first pass
-                        gx1[r] = sample_flat(img1, lv, fx + 1.f, fy) - sample_flat(img1, lv, fx - 1.f, fy);
-                        gy1[r] = sample_flat(img1, lv, fx, fy + 1.f) - sample_flat(img1, lv, fx, fy - 1.f);
+                        gx1[r] = sample_flat_ool(img1, lv, fx + 1.f, fy) - sample_flat_ool(img1, lv, fx - 1.f, fy);
+                        gy1[r] = sample_flat_ool(img1, lv, fx, fy + 1.f) - sample_flat_ool(img1, lv, fx, fy - 1.f);
                     }
                 }
             }
@@ -314,11 +322,11 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                             if (p < PP) {
                                 const float fx = kx + (float)(lo + p / P), fy = ky + (float)(lo + p % P);
                                 const double cx = (double)fx + dx, cy = (double)fy + dy;
-                                const double e = (double)(I1[r] - sample_flat(img2, lv, (float)cx, (float)cy));
-                                const double gx = (double)(sample_flat(img2, lv, (float)(cx + 1), (float)cy) -
-                                                           sample_flat(img2, lv, (float)(cx - 1), (float)cy));
-                                const double gy = (double)(sample_flat(img2, lv, (float)cx, (float)(cy + 1)) -
-                                                           sample_flat(img2, lv, (float)cx, (float)(cy - 1)));
+                                const double e = (double)(I1[r] - sample_flat_ool(img2, lv, (float)cx, (float)cy));
+                                const double gx = (double)(sample_flat_ool(img2, lv, (float)(cx + 1), (float)cy) -
+                                                           sample_flat_ool(img2, lv, (float)(cx - 1), (float)cy));
+                                const double gy = (double)(sample_flat_ool(img2, lv, (float)cx, (float)(cy + 1)) -
+                                                           sample_flat_ool(img2, lv, (float)cx, (float)(cy - 1)));
                                 sb0 = fma(e, gx, sb0);
                                 sb1 = fma(e, gy, sb1);
                                 sc = fma(e, e, sc);
@@ -336,7 +344,7 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         if (p < PP) {
                             const float fx = kx + (float)(lo + p / P), fy = ky + (float)(lo + p % P);
                             const double cx = (double)fx + dx, cy = (double)fy + dy;
-                            const double e = (double)(I1[r] - sample_flat(img2, lv, (float)cx, (float)cy));
+                            const double e = (double)(I1[r] - sample_flat_ool(img2, lv, (float)cx, (float)cy));
                             const double gx = (double)(iter == 0 ? gx1[r] : gxs);
                             const double gy = (double)(iter == 0 ? gy1[r] : gys);
                             sb0 = fma(e, gx, sb0);
@@ -458,12 +466,18 @@ cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, 
     int ctas_needed = (args.n_total + kWarpsPerCta - 1) / kWarpsPerCta;
     int grid = sm_count * 8;  // persistent warps, grid-stride over features
     if (grid > ctas_needed) grid = ctas_needed;
-    if (PP <= 64)
-        klt_warp_kernel<2><<<grid, block, 0, stream>>>(pyr, *maps, args);
+    if (P == 7)
+        klt_warp_kernel<2, 7><<<grid, block, 0, stream>>>(pyr, *maps, args);
+    else if (P == 8)
+        klt_warp_kernel<2, 8><<<grid, block, 0, stream>>>(pyr, *maps, args);
+    else if (P == 11)
+        klt_warp_kernel<4, 11><<<grid, block, 0, stream>>>(pyr, *maps, args);
+    else if (PP <= 64)
+        klt_warp_kernel<2, 0><<<grid, block, 0, stream>>>(pyr, *maps, args);
     else if (PP <= 128)
-        klt_warp_kernel<4><<<grid, block, 0, stream>>>(pyr, *maps, args);
+        klt_warp_kernel<4, 0><<<grid, block, 0, stream>>>(pyr, *maps, args);
     else
-        klt_warp_kernel<6><<<grid, block, 0, stream>>>(pyr, *maps, args);
+        klt_warp_kernel<6, 0><<<grid, block, 0, stream>>>(pyr, *maps, args);
     return cudaGetLastError();
 }
 
