@@ -83,6 +83,7 @@ struct SolverArgs {
     const int *list;
     const int *list_count;
     // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
+    double *scratch;          // LANE kernel: 6 doubles per resident thread (multi-family partial sums)
     float *templates;         // [n_total][levels][52]: I1 patches + regularity flag (template kernel)
     int *feat_flag;           // [n_total]: == epoch -> feature handed to the warp kernel by the template kernel
     int epoch;                // run counter (>= 1): flags from earlier runs are stale, no memset needed

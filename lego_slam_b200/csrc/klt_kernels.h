@@ -56,6 +56,7 @@ cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, 
 // run concurrently with launch_klt_lane: the two touch disjoint features).
 bool lane_kernel_supports(const SolverArgs &args);
 size_t lane_template_bytes(int n_total, int levels);
+size_t lane_scratch_bytes(int sm_count);
 cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
 

@@ -29,7 +29,11 @@
 // to the reference's; only the ORDER of the fp64 additions differs (row-major here, x-outer there; all
 // products are exact in fp64).  The (P+2)^2 sample grid is shared between "centre of pixel x+1" and
 // "+1 tap of pixel x" only when that is provably what the reference computes:
-//   (a) kx+c, ky+c are exact in fp32 for c in [-3,3] (checked per level, in the template kernel);
+//   (a) the pixel offsets c of one sub-pass share the rounding error e_c of float(kx+c) (axis_families):
+//       normally e_c = 0 for all c and a pass is one trip; near a power of two the patch splits into two
+//       families per axis, each with its own grid, and the pass takes one trip per family combination with
+//       the other pixels masked out (sub-pixel source keypoints, i.e. tracked points fed back by the
+//       reference's TrackLastFrame, hit this on ~1-6 % of their levels);
 //   (b) the double coordinate is not within 16 ulp64 of an fp32 rounding midpoint (checked per pass,
 //       per grid column/row), so the <=2 ulp64 differences between the reference's three ways of
 //       forming a coordinate cannot change the rounded float -- or it is EXACTLY on a midpoint and all
@@ -114,8 +118,9 @@ __device__ __forceinline__ float bilerp(float omx, float xx, float omy, float yy
     return r;
 }
 
-// One grid axis (columns or rows) of the shared sample grid.  S = (double)k + d; the reference forms
-// float(double(float(k+c)) + d [+-1]); under condition (a) these are S + g - 4 up to 2 ulp64.
+// One grid axis (columns or rows) of the shared sample grid.  S = kd + d, kd = double(float(k+c)) - c for the
+// pixel offsets c of one coordinate family (see axis_families); the reference forms
+// float(double(float(k+c)) + d [+-1]), which for that family is S + g - 4 up to 2 ulp64.
 // Per grid index g it yields the two bilinear factors the reference would use:
 //     om[g] = 1 - frac   (weight of the tap at the integer coordinate)
 //     fr[g] = frac       (weight of the tap at integer coordinate + 1)
@@ -129,8 +134,7 @@ __device__ __forceinline__ float bilerp(float omx, float xx, float omy, float yy
 //     the wrap pixel, true factors) or past the buffer = 0 (rows: fr := 0, om = 1 - frac).
 // Returns 0, or the reason (kStatDefer*) the pass cannot be proven bit-identical on this grid.
 template <bool IS_ROW>
-__device__ __forceinline__ int grid_axis(float k, double d, int limit, int &origin, float (&fr)[G], float (&om)[G]) {
-    const double kd = (double)k;
+__device__ __forceinline__ int grid_axis(double kd, double d, int limit, int &origin, float (&fr)[G], float (&om)[G]) {
     const double S = kd + d;
     if (!(fabs(S) < 1.0e6)) return kStatDeferRange;
     // An EXACT tie (D on an fp32 rounding midpoint) is safe when every double sum involved is exact:
@@ -166,10 +170,28 @@ __device__ __forceinline__ int grid_axis(float k, double d, int limit, int &orig
     return why;
 }
 
-// kx + c exact in fp32 for c in [LO, HI]: the end of larger magnitude decides (condition (a)).
-__device__ __forceinline__ bool offsets_exact(float k) {
+// Coordinate families of one axis (condition (a), generalised).  The reference forms the sample coordinate of
+// pixel offset c from float(k + c) (src/algorithm.cpp:65-73); near a power of two that float sum is rounded,
+// i.e. float(k + c) = k + c + e_c with e_c != 0.  Offsets with the same e_c share one sample grid.  Family A
+// (e = 0) always contains c = 0; maskB marks the offsets (bit c - LO) of family B, which share eps.
+// Returns false if more than one non-zero e_c occurs (several powers of two inside the patch: left to the
+// warp kernel).  Fast exit: if both ends are exact, every offset is (the end of larger magnitude decides).
+__device__ __forceinline__ bool axis_families(float k, unsigned &maskB, double &eps) {
     const double kd = (double)k;
-    return ((double)(k + (float)LO) == kd + (double)LO) && ((double)(k + (float)HI) == kd + (double)HI);
+    maskB = 0u;
+    eps = 0.0;
+    if ((double)(k + (float)LO) == kd + (double)LO && (double)(k + (float)HI) == kd + (double)HI) return true;
+    bool ok = true;
+#pragma unroll
+    for (int c = LO; c <= HI; ++c) {
+        const double e = (double)(k + (float)c) - (kd + (double)c);
+        if (e != 0.0) {
+            if (maskB != 0u && e != eps) ok = false;
+            eps = e;
+            maskB |= 1u << (c - LO);
+        }
+    }
+    return ok;
 }
 
 // The calling thread stages ROWS x 32 bytes of `img`, nominal origin (wx0 16-aligned, wy0), into its own
@@ -268,6 +290,30 @@ __device__ __noinline__ void exact_pass(const uint8_t *img2, const LevelView &lv
     sums[5] = s11;
 }
 
+// Sub-pass bookkeeping of a multi-family level: adds the sums parked by the earlier sub-passes, parks the
+// running total if more sub-passes follow.  Returns true when the pass is complete (sums hold the total).
+__device__ __noinline__ bool multi_family_step(double *parked, unsigned sub, unsigned nsub, double &a0, double &a1,
+                                               double &a2, double &a3, double &a4, double &a5) {
+    if (sub > 0u) {
+        a0 += parked[0];
+        a1 += parked[1];
+        a2 += parked[2];
+        a3 += parked[3];
+        a4 += parked[4];
+        a5 += parked[5];
+    }
+    if (sub + 1u < nsub) {
+        parked[0] = a0;
+        parked[1] = a1;
+        parked[2] = a2;
+        parked[3] = a3;
+        parked[4] = a4;
+        parked[5] = a5;
+        return false;
+    }
+    return true;
+}
+
 // Level-l coordinate of a level-0 keypoint coordinate (src/algorithm.cpp:160-169 then :194 repeatedly):
 // float(k * 2^-(L-1)), then exact doublings.
 __device__ __forceinline__ float level_coord(float k0, int L, int level) {
@@ -325,10 +371,35 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 
     float xx[G], omx[G], yy[G], omy[G];
     int ixn = 0, iyn = 0;
-    bool regular = offsets_exact(kx) && offsets_exact(ky);
+    unsigned mBx, mBy;
+    double ex, ey;
+    bool regular = axis_families(kx, mBx, ex) && axis_families(ky, mBy, ey);
     if (regular) {
-        // with (a), float(kx + c) == (double)kx + c exactly: the template grid is the d = 0 grid
-        regular = (grid_axis<false>(kx, 0.0, lv.cols, ixn, xx, omx) | grid_axis<true>(ky, 0.0, lv.rows, iyn, yy, omy)) == 0;
+        // float(kx + c) == (double)kx + c + e_c exactly: the template grid is the d = 0 grid of each family
+        regular = (grid_axis<false>((double)kx, 0.0, lv.cols, ixn, xx, omx) |
+                   grid_axis<true>((double)ky, 0.0, lv.rows, iyn, yy, omy)) == 0;
+    }
+    if (regular && mBx) {  // columns of family B take their factors from the grid shifted by eps
+        float xb[G], ob[G];
+        int ib = 0;
+        regular = grid_axis<false>((double)kx + ex, 0.0, lv.cols, ib, xb, ob) == 0 && ib == ixn;
+#pragma unroll
+        for (int x = 0; x < P; ++x)
+            if ((mBx >> x) & 1u) {
+                xx[x + 1] = xb[x + 1];
+                omx[x + 1] = ob[x + 1];
+            }
+    }
+    if (regular && mBy) {
+        float yb[G], ob[G];
+        int ib = 0;
+        regular = grid_axis<true>((double)ky + ey, 0.0, lv.rows, ib, yb, ob) == 0 && ib == iyn;
+#pragma unroll
+        for (int y = 0; y < P; ++y)
+            if ((mBy >> y) & 1u) {
+                yy[y + 1] = yb[y + 1];
+                omy[y + 1] = ob[y + 1];
+            }
     }
     float buf[kTplStride];
 #pragma unroll
@@ -415,6 +486,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     int img = 0;
     int wx0 = 0, wy0 = 0;
     bool need_win = false, no_window = false;
+    // coordinate families of this level: bits 0-6 x mask of family B, 8-14 y mask, 16-17 current sub-pass
+    unsigned fam = 0u;
+    double *parked = args.scratch + ((size_t)blockIdx.x * T + tid) * 6;  // partial sums between sub-passes
 
     for (;;) {
         // ------------------------------------------------------------------ fetch new features
@@ -498,6 +572,11 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     iter = 0;
                     lastCost = 0;
                     succ = true;
+                    unsigned mBx, mBy;
+                    double e0, e1;
+                    axis_families(kx, mBx, e0);  // (more than one eps per axis was filtered by the template kernel)
+                    axis_families(ky, mBy, e1);
+                    fam = mBx | (mBy << 8);
                 }
                 const double Sx = (double)kx + dx, Sy = (double)ky + dy;
                 no_window = true;  // estimate far outside the image / its apron: exact per-pixel passes
@@ -547,11 +626,27 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         bool fast = false;
         float xx[G], omx[G];
         int ixn = 0, iyn = 0;
+        unsigned pmx = 0x7fu, pmy = 0x7fu;  // pixels (columns / rows) that belong to this sub-pass
         if (run) {
             const LevelView &lv = pyr.lv[level];
             float yy[G], omy[G];
-            const int whyx = grid_axis<false>(kx, dx, lv.cols, ixn, xx, omx);
-            const int whyy = grid_axis<true>(ky, dy, lv.rows, iyn, yy, omy);
+            double kxd = (double)kx, kyd = (double)ky;
+            if (fam & 0x7f7fu) {  // this sub-pass works on one (x family, y family) combination
+                const unsigned mBx = fam & 0x7fu, mBy = (fam >> 8) & 0x7fu, sub = (fam >> 16) & 3u;
+                const bool fx = mBx && (sub & 1u), fy = mBy && (mBx ? (sub >> 1) : (sub & 1u));
+                if (fx) {
+                    const int c = LO + __ffs(mBx) - 1;
+                    kxd += (double)(kx + (float)c) - (kxd + (double)c);
+                }
+                if (fy) {
+                    const int c = LO + __ffs(mBy) - 1;
+                    kyd += (double)(ky + (float)c) - (kyd + (double)c);
+                }
+                pmx = fx ? mBx : (~mBx & 0x7fu);
+                pmy = fy ? mBy : (~mBy & 0x7fu);
+            }
+            const int whyx = grid_axis<false>(kxd, dx, lv.cols, ixn, xx, omx);
+            const int whyy = grid_axis<true>(kyd, dy, lv.rows, iyn, yy, omy);
             if (whyx | whyy) {
                 // cannot prove the shared grid bit-identical for this pass (rare): exact per-pixel pass
                 atomicAdd(&sm.stats[kStatSlowPath], 1u);
@@ -575,11 +670,14 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         }
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
+        const bool any_masked = __any_sync(FULL, run && fast && (fam & 0x7f7fu) != 0u);
         if (run) {
             const LevelView &lv = pyr.lv[level];
             const float *i1p = &sm.i1[0][tid];
             double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
+            bool solve_now = true;
             if (!fast) {
+                // the reference formulation covers the whole patch whatever its families: restart the pass
                 double sums[6];
                 exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, WS, kx, ky, dx, dy, sums);
                 sb0 = sums[0];
@@ -588,6 +686,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 s00 = sums[3];
                 s01 = sums[4];
                 s11 = sums[5];
+                fam &= 0x7f7fu;
             } else {
             const int ox = ixn - wx0;
             const int sh = (ox & 3) * 8;
@@ -622,18 +721,36 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 #pragma unroll
                 for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
                 const float *i1row = i1p + ((r - 2) * P) * WS;  // patch row y = r-2; centre samples = grid row r-1 = Sb
+                if (!any_masked) {
 #pragma unroll
-                for (int x = 0; x < P; ++x) {
-                    const int g = x + 1;
-                    const double e = (double)__fadd_rn(i1row[x * WS], -Sb[g]);  // :65-66
-                    const double gx = (double)__fadd_rn(Sb[g + 1], -Sb[g - 1]);  // :70-71
-                    const double gy = (double)__fadd_rn(Sc[g], -Sa[g]);          // :72-73
-                    sb0 = fma(e, gx, sb0);
-                    sb1 = fma(e, gy, sb1);
-                    sc = fma(e, e, sc);
-                    s00 = fma(gx, gx, s00);
-                    s01 = fma(gx, gy, s01);
-                    s11 = fma(gy, gy, s11);
+                    for (int x = 0; x < P; ++x) {
+                        const int g = x + 1;
+                        const double e = (double)__fadd_rn(i1row[x * WS], -Sb[g]);  // :65-66
+                        const double gx = (double)__fadd_rn(Sb[g + 1], -Sb[g - 1]);  // :70-71
+                        const double gy = (double)__fadd_rn(Sc[g], -Sa[g]);          // :72-73
+                        sb0 = fma(e, gx, sb0);
+                        sb1 = fma(e, gy, sb1);
+                        sc = fma(e, e, sc);
+                        s00 = fma(gx, gx, s00);
+                        s01 = fma(gx, gy, s01);
+                        s11 = fma(gy, gy, s11);
+                    }
+                } else {  // some thread of the warp is on a multi-family level: pixels outside the sub-pass add 0
+                    const bool row_on = (pmy >> (r - 2)) & 1u;
+#pragma unroll
+                    for (int x = 0; x < P; ++x) {
+                        const int g = x + 1;
+                        const bool on = row_on && ((pmx >> x) & 1u);
+                        const double e = (double)(on ? __fadd_rn(i1row[x * WS], -Sb[g]) : 0.f);
+                        const double gx = (double)(on ? __fadd_rn(Sb[g + 1], -Sb[g - 1]) : 0.f);
+                        const double gy = (double)(on ? __fadd_rn(Sc[g], -Sa[g]) : 0.f);
+                        sb0 = fma(e, gx, sb0);
+                        sb1 = fma(e, gy, sb1);
+                        sc = fma(e, e, sc);
+                        s00 = fma(gx, gx, s00);
+                        s01 = fma(gx, gy, s01);
+                        s11 = fma(gy, gy, s11);
+                    }
                 }
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
@@ -642,7 +759,16 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 }
             }
 
+            if (fam & 0x7f7fu) {
+                // multi-family level: this trip covered one (x family, y family) combination; partial sums
+                // wait in global scratch until the last combination has been added (rare, so out of line)
+                const unsigned sub = (fam >> 16) & 3u;
+                const unsigned nsub = ((fam & 0x7fu) ? 2u : 1u) * ((fam & 0x7f00u) ? 2u : 1u);
+                solve_now = multi_family_step(parked, sub, nsub, sb0, sb1, sc, s00, s01, s11);
+                fam = (fam & 0x7f7fu) | (solve_now ? 0u : ((sub + 1u) << 16));
             }
+            }
+            if (solve_now) {
 
             // J = -0.5 * g: rescaling the sums by exact powers of two commutes with every rounding
             const double b0 = 0.5 * sb0, b1 = 0.5 * sb1, cost = sc;
@@ -715,6 +841,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     state = ST_FETCH;
                 }
             }
+            }  // solve_now
         }
     }
 
@@ -733,6 +860,8 @@ bool lane_kernel_supports(const SolverArgs &args) {
 }
 
 size_t lane_template_bytes(int n_total, int levels) { return (size_t)n_total * levels * kTplStride * sizeof(float); }
+
+size_t lane_scratch_bytes(int sm_count) { return (size_t)sm_count * kLaneMinCtas * kLaneThreads * 6 * sizeof(double); }
 
 cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;

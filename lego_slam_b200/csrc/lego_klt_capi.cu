@@ -74,6 +74,7 @@ struct lego_klt_batch {
     int *d_defer_list = nullptr;   // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
     int *d_feat_flag = nullptr;    // LANE path: per-feature 'handed to the warp kernel' flag
+    double *d_scratch = nullptr;   // LANE kernel: per-thread partial sums of multi-family levels
     cudaStream_t side = nullptr;   // deferred features run here, concurrently with the lane kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t copy = nullptr;   // chunked end-to-end path: H2D of chunk c+1 overlaps compute of chunk c
@@ -215,6 +216,7 @@ int ensure_lane_buffers(lego_klt_batch *b) {
     const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
     CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
     CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
+    CU_TRY(cudaMalloc(&b->d_scratch, lane_scratch_bytes(b->ctx->sm_count)));
     CU_TRY(cudaMemset(b->d_feat_flag, 0, cap * sizeof(int)));
     CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -263,6 +265,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.defer_count = work + 1;
     a.defer_list = b->d_defer_list + a.f0;
     a.templates = nullptr;
+    a.scratch = nullptr;
     a.feat_flag = nullptr;
     a.epoch = 0;
     int kernel = params->kernel;
@@ -278,6 +281,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         if (rc) return rc;
         a.templates = b->d_templates;
         a.feat_flag = b->d_feat_flag;
+        a.scratch = b->d_scratch;
         a.epoch = (int)((b->runs % 0x3fffffff) + 1);
         CU_TRY(launch_klt_template(view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
@@ -475,6 +479,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     cudaFree(b->d_defer_list);
     cudaFree(b->d_templates);
     cudaFree(b->d_feat_flag);
+    cudaFree(b->d_scratch);
     if (b->side) cudaStreamDestroy(b->side);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);

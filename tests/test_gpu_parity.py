@@ -229,8 +229,9 @@ def test_edge_cases(tracker, oracle, kernel):
 
 
 def test_subpixel_keypoints_and_deferred_features(tracker, oracle):
-    """Tracked (sub-pixel) source points, as Frontend::TrackLastFrame feeds them: kx+c is sometimes
-    inexact in fp32 near powers of two, which the LANE kernel must hand to the exact warp kernel."""
+    """Tracked (sub-pixel) source points, as Frontend::TrackLastFrame feeds them: float(kx+c) is sometimes
+    rounded near powers of two.  The LANE kernel splits such a patch into coordinate families (one extra trip
+    per pass); only patches straddling several powers of two go to the exact warp kernel."""
     rows, cols, n = 376, 1241, 4000
     L, R, kp1, kp2, _ = synth.stereo_case(rows, cols, n, seed=21)
     rng = np.random.default_rng(5)
@@ -242,7 +243,7 @@ def test_subpixel_keypoints_and_deferred_features(tracker, oracle):
         assert_parity(out, succ, ref, rs, cols, rows, f"subpixel kernel={kernel}")
         assert _iters(st, 4) == _iters(rst, 4)
         if kernel == klt.KERNEL_LANE:
-            assert 0 < int(st.n_deferred) < n // 2, int(st.n_deferred)
+            assert int(st.n_deferred) < n // 50, int(st.n_deferred)
 
 
 def test_sequence_mode_image_handles_equal_pairwise_calls(tracker, oracle):
