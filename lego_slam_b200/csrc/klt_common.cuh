@@ -85,11 +85,13 @@ struct SolverArgs {
     // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
     double *scratch;          // LANE kernel: 6 doubles per resident thread (multi-family partial sums)
     float *templates;         // [n_total][levels][52]: I1 patches + regularity flag (template kernel)
-    int *feat_flag;           // [n_total]: == epoch -> feature handed to the warp kernel by the template kernel
+    int *feat_flag;           // [n_total]: 4*epoch+2 -> warp kernel owns the feature, 4*epoch+1 -> lane<FAMILIES>
     int epoch;                // run counter (>= 1): flags from earlier runs are stale, no memset needed
     int *work_counter;
     int *defer_list;
     int *defer_count;
+    int *fam_list;            // features with two coordinate families on some level (template kernel -> lane<true>)
+    int *fam_count;
 };
 
 #ifdef __CUDACC__

@@ -405,13 +405,20 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 #pragma unroll
     for (int i = 0; i < kTplStride; ++i) buf[i] = 0.f;
     if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15, 32);
+    // Ownership of the feature, decided by its levels with an atomicMax (values of earlier runs are smaller):
+    //   4*epoch + 2 -> exact warp kernel (irregular on some level), 4*epoch + 1 -> lane<FAMILIES> (two
+    //   coordinate families on some level), smaller -> the common lane kernel.  A feature is appended to a
+    //   list by the thread that raises its flag to that list's value; lane<FAMILIES> re-checks the flag.
     if (!regular) {
-        // the whole feature goes to the exact warp kernel (which runs concurrently with the lane kernel)
-        if (atomicExch(&args.feat_flag[f], args.epoch) != args.epoch) {
+        const int tag = 4 * args.epoch + 2;
+        if (atomicMax(&args.feat_flag[f], tag) < tag) {
             args.defer_list[atomicAdd(args.defer_count, 1)] = f;
             atomicAdd(&args.stats[kStatDeferred], 1ull);
             atomicAdd(&args.stats[kStatDeferInexact], 1ull);
         }
+    } else if (mBx | mBy) {
+        const int tag = 4 * args.epoch + 1;
+        if (atomicMax(&args.feat_flag[f], tag) < tag) args.fam_list[atomicAdd(args.fam_count, 1)] = f;
     }
     if (regular) {
         // the 7x7 centre of the 9x9 grid needs image rows iyn+1 .. iyn+8 and columns ixn+1 .. ixn+8
@@ -454,7 +461,10 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 #ifndef LANE_MAXREG
 #define LANE_MAXREG 0
 #endif
-template <int T, int MIN_CTAS>
+// FAMILIES = false: every feature has a single coordinate family per axis (the template kernel routes the
+// others to the FAMILIES = true instance, which takes its features from args.list); the family bookkeeping
+// costs the common instance nothing.
+template <int T, int MIN_CTAS, bool FAMILIES>
 __global__ void
 #if LANE_MAXREG > 0
 __maxnreg__(LANE_MAXREG)
@@ -468,6 +478,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int WS = T + LANE_PAD;  // word stride between consecutive window words of one thread
     int q_head = 0, q_tail = 0;  // warp-uniform ring positions
+    const int n_work = FAMILIES ? *args.list_count : args.n_total;
     bool global_done = false;
 
     if (tid < kStatCount) sm.stats[tid] = 0u;
@@ -487,7 +498,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     int wx0 = 0, wy0 = 0;
     bool need_win = false, no_window = false;
     // coordinate families of this level: bits 0-6 x mask of family B, 8-14 y mask, 16-17 current sub-pass
-    unsigned fam = 0u;
+    unsigned fam = 0u;  // stays 0 in the FAMILIES = false instance
     double *parked = args.scratch + ((size_t)blockIdx.x * T + tid) * 6;  // partial sums between sub-passes
 
     for (;;) {
@@ -505,11 +516,16 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     if (lane == 0) base = atomicAdd(args.work_counter, want);
                     base = __shfl_sync(FULL, base, 0);
                     const int local = base + lane;
-                    bool keep = lane < want && local < args.n_total;
+                    bool keep = lane < want && local < n_work;
                     float2 a1 = make_float2(0.f, 0.f), a2 = a1;
-                    const int gid = args.f0 + local;
+                    int gid = args.f0 + local;
                     if (keep) {
-                        keep = args.feat_flag[gid] != args.epoch;  // irregular template: the warp kernel owns this feature
+                        if (FAMILIES) {
+                            gid = args.list[local];  // the template kernel's list of multi-family features
+                            keep = args.feat_flag[gid] == 4 * args.epoch + 1;  // (not taken over by the warp kernel)
+                        } else {
+                            keep = args.feat_flag[gid] < 4 * args.epoch;  // otherwise owned by another kernel
+                        }
                         a1 = args.kp1[gid];
                         a2 = args.kp2_init[gid];
                     }
@@ -521,7 +537,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         sm.q_id[warp][pos] = gid;
                     }
                     q_tail += __popc(km);
-                    if (base + want >= args.n_total) global_done = true;
+                    if (base + want >= n_work) global_done = true;
                     __syncwarp();
                     avail = q_tail - q_head;
                 }
@@ -572,11 +588,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     iter = 0;
                     lastCost = 0;
                     succ = true;
-                    unsigned mBx, mBy;
-                    double e0, e1;
-                    axis_families(kx, mBx, e0);  // (more than one eps per axis was filtered by the template kernel)
-                    axis_families(ky, mBy, e1);
-                    fam = mBx | (mBy << 8);
+                    if (FAMILIES) {
+                        unsigned mBx, mBy;
+                        double e0, e1;
+                        axis_families(kx, mBx, e0);  // (more than one eps per axis was filtered by the template kernel)
+                        axis_families(ky, mBy, e1);
+                        fam = mBx | (mBy << 8);
+                    }
                 }
                 const double Sx = (double)kx + dx, Sy = (double)ky + dy;
                 no_window = true;  // estimate far outside the image / its apron: exact per-pixel passes
@@ -631,7 +649,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const LevelView &lv = pyr.lv[level];
             float yy[G], omy[G];
             double kxd = (double)kx, kyd = (double)ky;
-            if (fam & 0x7f7fu) {  // this sub-pass works on one (x family, y family) combination
+            if (FAMILIES && (fam & 0x7f7fu)) {  // this sub-pass works on one (x family, y family) combination
                 const unsigned mBx = fam & 0x7fu, mBy = (fam >> 8) & 0x7fu, sub = (fam >> 16) & 3u;
                 const bool fx = mBx && (sub & 1u), fy = mBy && (mBx ? (sub >> 1) : (sub & 1u));
                 if (fx) {
@@ -670,7 +688,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         }
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
-        const bool any_masked = __any_sync(FULL, run && fast && (fam & 0x7f7fu) != 0u);
+        const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & 0x7f7fu) != 0u);
         if (run) {
             const LevelView &lv = pyr.lv[level];
             const float *i1p = &sm.i1[0][tid];
@@ -759,7 +777,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 }
             }
 
-            if (fam & 0x7f7fu) {
+            if (FAMILIES && (fam & 0x7f7fu)) {
                 // multi-family level: this trip covered one (x family, y family) combination; partial sums
                 // wait in global scratch until the last combination has been added (rare, so out of line)
                 const unsigned sub = (fam >> 16) & 3u;
@@ -874,15 +892,31 @@ cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, 
 
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
-    auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas>;
     const size_t smem = sizeof(LaneSmem<kLaneThreads>);
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
     int grid = sm_count * kLaneMinCtas;
-    const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
-    if (grid > needed) grid = needed;
-    kernel<<<grid, kLaneThreads, smem, stream>>>(pyr, args);
-    return cudaGetLastError();
+    {
+        auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, false>;
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
+        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, args);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
+    {
+        // multi-family features (sub-pixel keypoints near a power of two): the list length is only known on
+        // the device, so the grid is sized for the worst case and CTAs without work exit at once
+        auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, true>;
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        SolverArgs a2 = args;
+        a2.list = args.fam_list;
+        a2.list_count = args.fam_count;
+        a2.work_counter = args.work_counter + 3;
+        const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
+        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, a2);
+        return cudaGetLastError();
+    }
 }
 
 }  // namespace legoklt

@@ -70,8 +70,10 @@ struct lego_klt_batch {
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ring[kRing][3] = {};  // run r: [0] before pyramid, [1] after pyramid, [2] after solver
     long long runs = 0;
-    int *d_work = nullptr;         // [0] work counter, [1] deferred count (LANE kernel)
+    int *d_work = nullptr;         // per chunk: [0] lane work counter, [1] deferred count, [2] family count,
+                                   // [3] lane<FAMILIES> work counter
     int *d_defer_list = nullptr;   // [B * n_cap]
+    int *d_fam_list = nullptr;     // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
     int *d_feat_flag = nullptr;    // LANE path: per-feature 'handed to the warp kernel' flag
     double *d_scratch = nullptr;   // LANE kernel: per-thread partial sums of multi-family levels
@@ -175,6 +177,7 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
         (e = cudaMalloc(&b->d_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc(&b->d_work, 4 * kMaxChunks * sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc(&b->d_defer_list, nt * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_fam_list, nt * sizeof(int))) != cudaSuccess ||
         (e = cudaMallocHost(&b->h_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess)
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "allocating keypoint buffers: %s", cudaGetErrorString(e)));
     for (int i = 0; i < EV_COUNT; ++i)
@@ -264,6 +267,8 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.work_counter = work;
     a.defer_count = work + 1;
     a.defer_list = b->d_defer_list + a.f0;
+    a.fam_list = b->d_fam_list + a.f0;
+    a.fam_count = work + 2;
     a.templates = nullptr;
     a.scratch = nullptr;
     a.feat_flag = nullptr;
@@ -282,7 +287,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         a.templates = b->d_templates;
         a.feat_flag = b->d_feat_flag;
         a.scratch = b->d_scratch;
-        a.epoch = (int)((b->runs % 0x3fffffff) + 1);
+        a.epoch = (int)((b->runs % 0x0fffffff) + 1);
         CU_TRY(launch_klt_template(view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
@@ -477,6 +482,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
             if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
     cudaFree(b->d_work);
     cudaFree(b->d_defer_list);
+    cudaFree(b->d_fam_list);
     cudaFree(b->d_templates);
     cudaFree(b->d_feat_flag);
     cudaFree(b->d_scratch);
