@@ -192,7 +192,7 @@ def workload_config(args):
             "l2_policy": "inputs larger than L2 (level-0 images of one step: %.0f MB > 126 MB)"
                          % (2 * args.pairs * ROWS * COLS / 1e6),
             "sharding": "block partition of pairs, one process per GPU, no data-path collective",
-            "batches_in_flight": max(1, args.streams)}
+            "batches_in_flight": max(1, args.streams), "subpixel_keypoints": bool(args.subpixel)}
 
 
 def run_ours(args):
@@ -219,6 +219,9 @@ def run_ours(args):
     B, n = args.pairs, args.features
     base = make_workload(B, n, args.distinct, 1000 + rank * B)
     imgs1, imgs2, kp1, kp2 = fill_batch(base, B, n, klt.pinned_empty)
+    if args.subpixel:
+        kp1 += np.random.default_rng(77 + rank).uniform(-0.5, 0.5, kp1.shape).astype(np.float32)
+        np.copyto(kp2, kp1)
     kp2_io = klt.pinned_empty((B, n, 2), np.float32)
     succ = klt.pinned_empty((B, n), np.uint8)
     params = klt.make_params(levels=LEVELS, patch_lo=PATCH_LO, patch_hi=PATCH_HI, kernel=args.kernel)
@@ -374,6 +377,8 @@ def main():
     ap.add_argument("--streams", type=int, default=1, help="device-resident batches in flight (value only)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--subpixel", action="store_true",
+                    help="jitter the source keypoints by +-0.5 px (tracked points as fed back by TrackLastFrame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
