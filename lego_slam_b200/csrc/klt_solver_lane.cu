@@ -255,6 +255,85 @@ __device__ __forceinline__ void load_row10(const uint32_t *wp, int i, int sh, fl
     row[9] = byte_to_float(b2, 1);
 }
 
+// ---- packed FP32x2 variant of the row load / sample row (sm_100 FMUL2 / FADD2: two IEEE-rounded fp32 operations
+// per instruction, bit-identical to the scalar ones).  A pixel row is kept as five even pairs (0,1)(2,3)..(8,9)
+// and five odd pairs (1,2)(3,4)..(9,10), so that both taps of two adjacent samples are register pairs.
+struct Row2 {
+    float2 e[5], o[5];
+};
+
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen with the __fmul2_rn/__fadd2_rn intrinsics and with
+// explicit .rn PTX, -fmad=false notwithstanding: 12 % of the features lost bit-identity, like any FMA contraction,
+// SURVEY.md F9).  A sum whose addend is a product is therefore written as fma(product, 1.0, acc): the product is
+// already rounded, product * 1.0 is exact, and an FMA cannot absorb a second multiplication.
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+    return c;
+}
+
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+    unsigned long long ra, rb, rc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+    return c;
+}
+
+// acc + prod with one rounding, where prod is an already rounded product (see above).  `one` is 1.0f read from the
+// kernel arguments: with a literal 1.0 ptxas simplifies fma(mul(a,b), 1, acc) to fma(a, b, acc), i.e. contracts.
+__device__ __forceinline__ float2 add2_product(float2 acc, float2 prod, float one) {
+    unsigned long long ra, rp, rc, one2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(one2) : "f"(one));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rp) : "f"(prod.x), "f"(prod.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rc) : "l"(rp), "l"(one2), "l"(ra));
+    float2 c;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+    return c;
+}
+
+__device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, int ka, uint32_t wb, int kb) {
+    float2 p;
+    p.x = __uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7440u + ka));
+    p.y = __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7440u + kb));
+    return add2_rn(p, make_float2(-8388608.0f, -8388608.0f));
+}
+
+template <int WS>
+__device__ __forceinline__ void load_row10_packed(const uint32_t *wp, int i, int sh, Row2 &row) {
+    const uint32_t *p = wp + i * kWin2Words * WS;
+    const uint32_t w0 = p[0], w1 = p[WS], w2 = p[2 * WS], w3 = p[3 * WS];
+    const uint32_t b[3] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh)};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        row.e[j] = bytes_to_float2(b[(2 * j) >> 2], (2 * j) & 3, b[(2 * j + 1) >> 2], (2 * j + 1) & 3);
+        row.o[j] = bytes_to_float2(b[(2 * j + 1) >> 2], (2 * j + 1) & 3, b[(2 * j + 2) >> 2], (2 * j + 2) & 3);
+    }
+}
+
+// Samples g = 2j, 2j+1 of one grid row (algorithm.h:51-56 per sample, products and sums individually rounded).
+__device__ __forceinline__ void sample_row_packed(const float2 (&OMX)[5], const float2 (&XX)[5], float omy_r, float yy_r,
+                                                  const Row2 &A, const Row2 &B, float one, float2 (&out)[5]) {
+    const float2 omy2 = make_float2(omy_r, omy_r), yy2 = make_float2(yy_r, yy_r);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        float2 r = mul2_rn(mul2_rn(OMX[j], omy2), A.e[j]);
+        r = add2_product(r, mul2_rn(mul2_rn(XX[j], omy2), A.o[j]), one);
+        r = add2_product(r, mul2_rn(mul2_rn(OMX[j], yy2), B.e[j]), one);
+        r = add2_product(r, mul2_rn(mul2_rn(XX[j], yy2), B.o[j]), one);
+        out[j] = r;
+    }
+}
+
+__device__ __forceinline__ float pick(const float2 (&S)[5], int g) { return (g & 1) ? S[g >> 1].y : S[g >> 1].x; }
+
 __device__ __noinline__ float sample_flat_cold(const uint8_t *img, const LevelView &lv, float x, float y) {
     return sample_flat(img, lv, x, y);
 }
@@ -710,70 +789,50 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const int sh = (ox & 3) * 8;
             const uint32_t *wp = &sm.win2[(iyn - wy0) * kWin2Words + (ox >> 2)][tid];
             const float *wyp = &sm.wy[0][tid];
-            float rowA[G + 1], rowB[G + 1];
-            float Sa[G], Sb[G], Sc[G];  // sample rows r-2, r-1, r (rotated by register moves)
-
-            // One grid row of samples: out[g] for g = 0..G-1 from pixel rows rowA (top) / rowB (bottom).
-            auto sample_row = [&](int r, float (&out)[G]) {
-                const float omy_r = wyp[(2 * r) * WS], yy_r = wyp[(2 * r + 1) * WS];
+            Row2 rowA, rowB;
+            float2 Sa[5], Sb[5], Sc[5];  // sample rows r-2, r-1, r as pairs (2j, 2j+1); rotated by register moves
+            float2 OMX[5], XX[5];
 #pragma unroll
-                for (int g = 0; g < G; ++g)
-                    out[g] = bilerp(omx[g], xx[g], omy_r, yy_r, rowA[g], rowA[g + 1], rowB[g], rowB[g + 1]);
-            };
+            for (int j = 0; j < 5; ++j) {
+                OMX[j] = make_float2(omx[2 * j], 2 * j + 1 < G ? omx[2 * j + 1] : 0.f);
+                XX[j] = make_float2(xx[2 * j], 2 * j + 1 < G ? xx[2 * j + 1] : 0.f);
+            }
 
             // The row loop is deliberately NOT unrolled: the unrolled pass (1785 SASS instructions) did
-            // not fit the instruction cache and the kernel was fetch-bound (profiles/r01_lane_v1.md).
-            load_row10<WS>(wp, 0, sh, rowA);
-            load_row10<WS>(wp, 1, sh, rowB);
-            sample_row(0, Sa);
-#pragma unroll
-            for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
-            load_row10<WS>(wp, 2, sh, rowB);
-            sample_row(1, Sb);
-#pragma unroll
-            for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
+            // not fit the instruction cache and the kernel was fetch-bound (profiles/README.md).
+            load_row10_packed<WS>(wp, 0, sh, rowA);
+            load_row10_packed<WS>(wp, 1, sh, rowB);
+            sample_row_packed(OMX, XX, wyp[0], wyp[WS], rowA, rowB, args.one, Sa);
+            rowA = rowB;
+            load_row10_packed<WS>(wp, 2, sh, rowB);
+            sample_row_packed(OMX, XX, wyp[2 * WS], wyp[3 * WS], rowA, rowB, args.one, Sb);
+            rowA = rowB;
 #pragma unroll 1
             for (int r = 2; r < G; ++r) {
-                load_row10<WS>(wp, r + 1, sh, rowB);
-                sample_row(r, Sc);
-#pragma unroll
-                for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
+                load_row10_packed<WS>(wp, r + 1, sh, rowB);
+                sample_row_packed(OMX, XX, wyp[(2 * r) * WS], wyp[(2 * r + 1) * WS], rowA, rowB, args.one, Sc);
+                rowA = rowB;
                 const float *i1row = i1p + ((r - 2) * P) * WS;  // patch row y = r-2; centre samples = grid row r-1 = Sb
-                if (!any_masked) {
+                const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
 #pragma unroll
-                    for (int x = 0; x < P; ++x) {
-                        const int g = x + 1;
-                        const double e = (double)__fadd_rn(i1row[x * WS], -Sb[g]);  // :65-66
-                        const double gx = (double)__fadd_rn(Sb[g + 1], -Sb[g - 1]);  // :70-71
-                        const double gy = (double)__fadd_rn(Sc[g], -Sa[g]);          // :72-73
-                        sb0 = fma(e, gx, sb0);
-                        sb1 = fma(e, gy, sb1);
-                        sc = fma(e, e, sc);
-                        s00 = fma(gx, gx, s00);
-                        s01 = fma(gx, gy, s01);
-                        s11 = fma(gy, gy, s11);
-                    }
-                } else {  // some thread of the warp is on a multi-family level: pixels outside the sub-pass add 0
-                    const bool row_on = (pmy >> (r - 2)) & 1u;
-#pragma unroll
-                    for (int x = 0; x < P; ++x) {
-                        const int g = x + 1;
-                        const bool on = row_on && ((pmx >> x) & 1u);
-                        const double e = (double)(on ? __fadd_rn(i1row[x * WS], -Sb[g]) : 0.f);
-                        const double gx = (double)(on ? __fadd_rn(Sb[g + 1], -Sb[g - 1]) : 0.f);
-                        const double gy = (double)(on ? __fadd_rn(Sc[g], -Sa[g]) : 0.f);
-                        sb0 = fma(e, gx, sb0);
-                        sb1 = fma(e, gy, sb1);
-                        sc = fma(e, e, sc);
-                        s00 = fma(gx, gx, s00);
-                        s01 = fma(gx, gy, s01);
-                        s11 = fma(gy, gy, s11);
-                    }
+                for (int x = 0; x < P; ++x) {
+                    const int g = x + 1;
+                    // any_masked (warp-uniform, FAMILIES instance only): pixels outside the sub-pass add 0
+                    const bool on = !any_masked || (row_on && ((pmx >> x) & 1u));
+                    const double e = (double)(on ? __fadd_rn(i1row[x * WS], -pick(Sb, g)) : 0.f);          // :65-66
+                    const double gx = (double)(on ? __fadd_rn(pick(Sb, g + 1), -pick(Sb, g - 1)) : 0.f);  // :70-71
+                    const double gy = (double)(on ? __fadd_rn(pick(Sc, g), -pick(Sa, g)) : 0.f);          // :72-73
+                    sb0 = fma(e, gx, sb0);
+                    sb1 = fma(e, gy, sb1);
+                    sc = fma(e, e, sc);
+                    s00 = fma(gx, gx, s00);
+                    s01 = fma(gx, gy, s01);
+                    s11 = fma(gy, gy, s11);
                 }
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    Sa[g] = Sb[g];
-                    Sb[g] = Sc[g];
+                for (int j = 0; j < 5; ++j) {
+                    Sa[j] = Sb[j];
+                    Sb[j] = Sc[j];
                 }
             }
 

@@ -258,6 +258,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.inverse = params->inverse;
     a.has_initial = params->has_initial;
     a.eps = params->eps;
+    a.one = 1.0f;
     {
         const char *dbg = getenv("LEGO_KLT_DEBUG");
         a.debug_flags = dbg ? atoi(dbg) : 0;
