@@ -345,13 +345,17 @@ def run_ours(args):
         "roofline": {"kernel": "klt_lane_kernel + klt_warp_kernel on deferred features (fused 4-level GN solver)"
                      if args.kernel in (0, 3) else "klt_warp_kernel (fused 4-level GN solver)", "bound": "fp32-issue (non-tensor)",
                      "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved_tflops / fp32_peak_tflops, "traffic": None,
+                     "frac": achieved_tflops / fp32_peak_tflops,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of klt_lane_kernel, one `ncu --set full` capture at this
+                     # exact configuration (profiles/r01_ncu_final_all_kernels.csv); null for any other configuration
+                     "traffic": 655_785_728 if (B, n, args.kernel, args.subpixel) == (256, 2000, 0, False) else None,
                      "peak_source": f"computed: {sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz un-fused fp32 "
                                     "(not in MEASURED_PEAKS.json, which has only HBM and bf16 tensor peaks)",
                      "algorithmic_flop_per_launch": algo_flop, "gn_iters_per_level": iters,
                      "ms_per_launch": ms_sol, "share_of_step": ms_sol / (ms_sol + ms_pyr)},
         "roofline_pyramid": {"kernel": "pyramid_fused_kernel", "bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": pyr_gbs / hbm_peak, "traffic": None,
+                             "unit": "GB/s", "frac": pyr_gbs / hbm_peak,
+                             "traffic": 330_073_344 if (B, args.kernel) == (256, 0) else None,  # pyramid_fused_kernel, same capture
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": ms_pyr},
         "cpu_baseline": cpu,
