@@ -123,6 +123,15 @@ int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int 
                            int *level_cols, int *level_rows);
 
 /*
+ * Test hook: after lego_klt_build_pyramid, copies the DEVICE rows of `level` (0 = the uploaded image) as they
+ * lie in HBM -- `rows` rows of `*pitch` bytes, pixel (r, 0) at byte r * *pitch + *apron_left -- so that the
+ * row aprons the solver's border semantics rely on (algorithm.h:42-55 clamps and flat addressing) can be
+ * checked directly.  Not needed by the reference's call sites.
+ */
+int lego_klt_debug_read_level(lego_klt_ctx *ctx, int level, uint8_t *out, size_t out_capacity,
+                              int *pitch, int *apron_left);
+
+/*
  * Sequence mode: the reference rebuilds both pyramids inside every LKOpticalFlow4Layer
  * call (src/algorithm.cpp:140-154), so in Frontend::Track the same left image is pyramided up to three
  * times (img2 of the temporal track, img1 of the stereo match, img1 of the next temporal track).  An image

@@ -108,6 +108,15 @@ class Tracker:
             off += nb
         return res
 
+    def debug_read_level(self, level: int, rows: int):
+        """Device rows of `level` after build_pyramid, aprons included: (array rows x pitch, apron_left)."""
+        cap = rows * 8192
+        out = np.zeros(cap, np.uint8)
+        pitch, left = C.c_int(0), C.c_int(0)
+        _lib.check(self._lib.lego_klt_debug_read_level(self._h, level, out.ctypes.data, cap, C.byref(pitch),
+                                                       C.byref(left)), "lego_klt_debug_read_level")
+        return out[:rows * pitch.value].reshape(rows, pitch.value).copy(), left.value
+
     def batch(self, batch: int, rows: int, cols: int, n_per_pair: int, levels: int = 4, step: int | None = None):
         return Batch(self, batch, rows, cols, n_per_pair, levels, step)
 

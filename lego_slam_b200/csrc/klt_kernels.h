@@ -13,7 +13,9 @@ struct ResizeTables {
     short2 *xcoef;  // [cols_l]  {a0, a1}, 2^11 scale
     int *yofs;      // [rows_l]  top tap
     short2 *ycoef;  // [rows_l]
+    int *gofs;      // [ceil(cols_l/4)]  first tap of a regular 4-pixel group (taps sx0 + 2j), else -1
     int x_exact2;   // xofs[c] == 2c and a0 == a1 == 1024 for every c
+    int y_exact2;   // same for the rows
 };
 
 struct PyramidPlan {
@@ -32,14 +34,15 @@ struct PyramidPlan {
 bool pyramid_level_sizes(int cols, int rows, int levels, int *lcols, int *lrows);
 cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan);
 void pyramid_plan_destroy(PyramidPlan *plan);
-// Builds levels 1..L-1 of images [img0, img0 + nimg) of both image sets from level 0, one fused launch.
+// Builds levels 1..L-1 of images [img0, img0 + nimg) of both image sets from level 0 AND writes the row aprons
+// (see LevelView) of every level, one fused launch.
 cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
                            int n_sets = 2);
 // Re-pitches tight level-0 rows (`step` bytes per row, all images of the set back to back starting at the
 // 4-byte aligned `tight`, buffer padded by >= 8 bytes) of images [img0, img0+n_images) into the device layout.
 cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int img0, int n_images,
                           cudaStream_t stream);
-// Writes the row aprons (see LevelView) of every level of both image sets; run after launch_pyramid.
+// Row aprons alone (single-level configurations; launch_pyramid calls it when there is no level to build).
 cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream, int n_sets = 2);
 
 // ---- solver kernels ---------------------------------------------------------------------------

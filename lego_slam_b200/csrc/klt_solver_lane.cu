@@ -80,6 +80,12 @@ constexpr int kTplStride = 52;                                // floats per (fea
 #ifndef LANE_BATCH
 #define LANE_BATCH 1
 #endif
+#ifndef LANE_UNROLL3
+#define LANE_UNROLL3 0   // measured on B200: 189 instead of 212 instructions per row step, yet 3 % SLOWER (code size)
+#endif
+#ifndef LANE_PREFETCH_Q
+#define LANE_PREFETCH_Q 1
+#endif
 #ifndef LANE_T
 #define LANE_T 128
 #endif
@@ -609,6 +615,31 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         a2 = args.kp2_init[gid];
                     }
                     const unsigned km = __ballot_sync(FULL, keep);
+#if LANE_PREFETCH_Q
+                    if (keep) {
+                        // A queued feature is started a few trips from now: pull what its first set-up will load
+                        // (its templates, streamed exactly once, and the rows of its top-level window) into L2 now,
+                        // with all lanes active, instead of stalling the whole warp on DRAM then.
+                        const char *tp = reinterpret_cast<const char *>(args.templates + (size_t)gid * L * kTplStride);
+                        const int tbytes = L * kTplStride * (int)sizeof(float);
+                        for (int o = 0; o < tbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + tbytes - 1));
+                        const LevelView &tl = pyr.lv[L - 1];
+                        const float px = (float)(a2.x * scale_top), py = (float)(a2.y * scale_top);
+                        if (fabsf(px) < 1.0e6f && fabsf(py) < 1.0e6f) {
+                            const int pwx = (((int)floorf(px) + LO - 1 - kWinSlackL) & ~(kWinAlign - 1));
+                            const int pwy = (int)floorf(py) + LO - 1 - kWinSlackT;
+                            if (window_in_apron(tl, pwx)) {
+                                const uint8_t *pimg = tl.base[1] + (size_t)(gid / args.n_per_pair) * tl.slot;
+#pragma unroll
+                                for (int i = 0; i < kWin2Rows; ++i) {
+                                    const int ry = min(max(pwy + i, 0), tl.rows - 1);
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pimg + (ptrdiff_t)ry * tl.pitch + pwx));
+                                }
+                            }
+                        }
+                    }
+#endif
                     if (keep) {
                         const int pos = (q_tail + __popc(km & ((1u << lane) - 1u))) & (kQueue - 1);
                         sm.q_k1[warp][pos] = a1;
@@ -692,7 +723,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     float4 t[kTplStride / 4];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
-                    if (level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
+                    if (!LANE_PREFETCH_Q && level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
                         const char *nxt = reinterpret_cast<const char *>(tp) - kTplStride * sizeof(float);
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
@@ -806,22 +837,24 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             rowA = rowB;
             load_row10_packed<WS>(wp, 2, sh, rowB);
             sample_row_packed(OMX, XX, wyp[2 * WS], wyp[3 * WS], rowA, rowB, args.one, Sb);
+#if !LANE_UNROLL3
             rowA = rowB;
-#pragma unroll 1
-            for (int r = 2; r < G; ++r) {
-                load_row10_packed<WS>(wp, r + 1, sh, rowB);
-                sample_row_packed(OMX, XX, wyp[(2 * r) * WS], wyp[(2 * r + 1) * WS], rowA, rowB, args.one, Sc);
-                rowA = rowB;
-                const float *i1row = i1p + ((r - 2) * P) * WS;  // patch row y = r-2; centre samples = grid row r-1 = Sb
+#endif
+            // One patch row per step: sample row r from pixel rows r, r+1 (PB is loaded here), then the 7 pixels of
+            // patch row y = r-2 with centre samples SB = grid row r-1, SA / SC the rows above / below.
+            auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[5], const float2 (&SB)[5], float2 (&SC)[5]) {
+                load_row10_packed<WS>(wp, r + 1, sh, PB);
+                sample_row_packed(OMX, XX, wyp[(2 * r) * WS], wyp[(2 * r + 1) * WS], PA, PB, args.one, SC);
+                const float *i1row = i1p + ((r - 2) * P) * WS;
                 const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
 #pragma unroll
                 for (int x = 0; x < P; ++x) {
                     const int g = x + 1;
                     // any_masked (warp-uniform, FAMILIES instance only): pixels outside the sub-pass add 0
                     const bool on = !any_masked || (row_on && ((pmx >> x) & 1u));
-                    const double e = (double)(on ? __fadd_rn(i1row[x * WS], -pick(Sb, g)) : 0.f);          // :65-66
-                    const double gx = (double)(on ? __fadd_rn(pick(Sb, g + 1), -pick(Sb, g - 1)) : 0.f);  // :70-71
-                    const double gy = (double)(on ? __fadd_rn(pick(Sc, g), -pick(Sa, g)) : 0.f);          // :72-73
+                    const double e = (double)(on ? __fadd_rn(i1row[x * WS], -pick(SB, g)) : 0.f);          // :65-66
+                    const double gx = (double)(on ? __fadd_rn(pick(SB, g + 1), -pick(SB, g - 1)) : 0.f);  // :70-71
+                    const double gy = (double)(on ? __fadd_rn(pick(SC, g), -pick(SA, g)) : 0.f);          // :72-73
                     sb0 = fma(e, gx, sb0);
                     sb1 = fma(e, gy, sb1);
                     sc = fma(e, e, sc);
@@ -829,12 +862,31 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     s01 = fma(gx, gy, s01);
                     s11 = fma(gy, gy, s11);
                 }
+            };
+#if LANE_UNROLL3
+            // Three steps per trip with the roles of the three sample rows (and of three pixel-row buffers) rotating
+            // by NAME: no register moves (the rolled loop spent 31 of its 212 instructions on them).  7 steps =
+            // r 2,3,4 / 5,6,7 / 8; the body (~550 instructions) still fits the instruction caches.
+            Row2 rowC;
+#pragma unroll 1
+            for (int r = 2; r < G; r += 3) {
+                step(r, rowB, rowC, Sa, Sb, Sc);      // pixel rows: rowB = r, rowC = r+1
+                if (r + 1 >= G) break;
+                step(r + 1, rowC, rowA, Sb, Sc, Sa);
+                step(r + 2, rowA, rowB, Sc, Sa, Sb);
+            }
+#else
+#pragma unroll 1
+            for (int r = 2; r < G; ++r) {
+                step(r, rowA, rowB, Sa, Sb, Sc);
+                rowA = rowB;
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
                     Sa[j] = Sb[j];
                     Sb[j] = Sc[j];
                 }
             }
+#endif
 
             if (FAMILIES && (fam & 0x7f7fu)) {
                 // multi-family level: this trip covered one (x family, y family) combination; partial sums
@@ -898,14 +950,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                                 for (int i = 0; i < kWin2Rows; ++i) {
                                     const int ry = min(max(pwy + i, 0), nl.rows - 1);
                                     const uint8_t *pa = nimg + (ptrdiff_t)ry * nl.pitch + pwx;
-                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
-                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + kWin2Words * 4 - 1));
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
                                 }
                             }
                         }
-                        const char *nt = reinterpret_cast<const char *>(args.templates + ((size_t)feat * L + level) * kTplStride);
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nt));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nt + 128));
                     }
 #endif
                 } else {

@@ -239,8 +239,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
     if (ring) CU_TRY(cudaEventRecord(ring[0], st));
     if (!view_override) {
-        CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
-        CU_TRY(launch_aprons(b->view, img0, nimg, st));
+        CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));  // (row aprons included)
     }
     if (ring) CU_TRY(cudaEventRecord(ring[1], st));
     SolverArgs a;
@@ -772,7 +771,6 @@ int lego_klt_image_upload(lego_klt_image *im, const uint8_t *data) {
     CU_TRY(cudaMemcpyAsync(im->d_tight, ctx->pinned, img_bytes, cudaMemcpyHostToDevice, st));
     CU_TRY(launch_ingest(im->d_tight, im->view.lv[0], 0, 0, 1, st));
     CU_TRY(launch_pyramid(im->plan, im->view, 0, 1, st, 1));
-    CU_TRY(launch_aprons(im->view, 0, 1, st, 1));
     im->valid = true;
     return LEGO_KLT_OK;
 }
@@ -837,7 +835,6 @@ int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int 
     CU_TRY(ingest_set(b, 0, 0, 1, st));
     CU_TRY(ingest_set(b, 1, 0, 1, st));
     CU_TRY(launch_pyramid(b->plan, b->view, 0, 1, st));
-    CU_TRY(launch_aprons(b->view, 0, 1, st));
     size_t off = 0;
     for (int l = 0; l < levels; ++l) {
         const LevelView &lv = b->view.lv[l];
@@ -852,6 +849,22 @@ int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int 
     }
     CU_TRY(cudaStreamSynchronize(st));
     b->uploaded = false;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_debug_read_level(lego_klt_ctx *ctx, int level, uint8_t *out, size_t out_capacity, int *pitch,
+                              int *apron_left) {
+    if (!ctx || !ctx->single) return fail(LEGO_KLT_ERR_STATE, "lego_klt_debug_read_level before lego_klt_build_pyramid");
+    lego_klt_batch *b = ctx->single;
+    if (level < 0 || level >= b->levels) return fail(LEGO_KLT_ERR_BAD_ARG, "level out of range");
+    const LevelView &lv = b->view.lv[level];
+    const size_t nbytes = (size_t)lv.rows * lv.pitch;
+    if (!out || nbytes > out_capacity) return fail(LEGO_KLT_ERR_BAD_ARG, "output buffer too small");
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMemcpyAsync(out, lv.base[0] - kApronL, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (pitch) *pitch = lv.pitch;
+    if (apron_left) *apron_left = kApronL;
     return LEGO_KLT_OK;
 }
 

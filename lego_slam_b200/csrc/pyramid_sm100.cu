@@ -65,20 +65,126 @@ inline int clip_row(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
 
 struct PyrKernelParams {
     ResizeTables tab[kMaxLevels];
-    int smem_off[kMaxLevels];
+    int smem_off[kMaxLevels];  // byte offset of level l's band (pixel 0 of its first row) in dynamic smem
     int top_rows;
     int img0, nimg;  // image range of this launch (chunked batches)
 };
 
 __device__ __forceinline__ int d_clip(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
 
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// (a0 * byte0 + a1 * byte1) of the low / high byte pair of `bytes`, a = {a0, a1} as two 16-bit fields.
+__device__ __forceinline__ int dot2_lo(uint32_t a, uint32_t bytes) {
+    int d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(bytes), "r"(0));
+    return d;
+}
+__device__ __forceinline__ int dot2_hi(uint32_t a, uint32_t bytes) {
+    int d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(bytes), "r"(0));
+    return d;
+}
+
+// Vertical pass + rounding of cv::resize (see the file header) for one pixel.
+template <bool Y2>
+__device__ __forceinline__ uint32_t vertical(int h0, int h1, int b0, int b1) {
+    if (Y2) return (uint32_t)(((h0 >> 10) + (h1 >> 10) + 2) >> 2);  // b0 = b1 = 1024: (1024*(h>>4))>>16 == h>>10
+    return (uint32_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// One destination row of level k: the lanes of the calling warp part stride over the 4-pixel groups.
+//   X2 (horizontal scale exactly 2, weights 1024/1024) and Y2 (same vertically) are per-level properties.
+//   X2 && Y2: (p00+p01+p10+p11+2)>>2 with two pixels per 32-bit word (SWAR on 16-bit lanes).
+//   otherwise: a regular group (taps of pixel j start at sx0 + 2j: everywhere except where the tap offset steps
+//   by one, and in the partial group at the row end) takes its 8 source bytes with two funnel shifts and does the
+//   horizontal pass with dp2a; irregular groups take the per-pixel path.
+template <bool X2, bool Y2>
+__device__ __forceinline__ void resize_row(const uint8_t *__restrict__ s0, const uint8_t *__restrict__ s1,
+                                           uint32_t *__restrict__ drow, const ResizeTables &tb, int b0, int b1,
+                                           int dcols, int src_last, int g0, int gstep) {
+    const int ng = (dcols + 3) >> 2;
+    for (int g = g0; g < ng; g += gstep) {
+        const int c0 = 4 * g;
+        uint32_t packed = 0;
+        int info = X2 ? ((c0 + 3 < dcols) ? 2 * c0 : -1) : __ldg(tb.gofs + g);
+        if (info >= 0) {
+            uint32_t d00, d01, d10, d11;  // source bytes sx0..sx0+7 of the two source rows
+            if (X2) {
+                const uint2 t0 = *reinterpret_cast<const uint2 *>(s0 + info);
+                const uint2 t1 = *reinterpret_cast<const uint2 *>(s1 + info);
+                d00 = t0.x, d01 = t0.y, d10 = t1.x, d11 = t1.y;
+            } else {
+                const int base = info & ~3, sh = (info & 3) * 8;
+                const uint32_t *q0 = reinterpret_cast<const uint32_t *>(s0 + base);
+                const uint32_t *q1 = reinterpret_cast<const uint32_t *>(s1 + base);
+                const uint32_t a0 = q0[0], a1 = q0[1], a2 = q0[2], c0w = q1[0], c1w = q1[1], c2w = q1[2];
+                d00 = __funnelshift_r(a0, a1, sh), d01 = __funnelshift_r(a1, a2, sh);
+                d10 = __funnelshift_r(c0w, c1w, sh), d11 = __funnelshift_r(c1w, c2w, sh);
+            }
+            if (X2 && Y2) {
+                // even + odd bytes per 16-bit lane, both rows, +2, >>2: two output pixels per word
+                const uint32_t sA = __byte_perm(d00, 0u, 0x4240) + __byte_perm(d00, 0u, 0x4341) +
+                                    __byte_perm(d10, 0u, 0x4240) + __byte_perm(d10, 0u, 0x4341) + 0x00020002u;
+                const uint32_t sB = __byte_perm(d01, 0u, 0x4240) + __byte_perm(d01, 0u, 0x4341) +
+                                    __byte_perm(d11, 0u, 0x4240) + __byte_perm(d11, 0u, 0x4341) + 0x00020002u;
+                packed = __byte_perm(sA >> 2, sB >> 2, 0x6420);
+            } else {
+                uint4 cf;
+                if (X2) cf = make_uint4(0x04000400u, 0x04000400u, 0x04000400u, 0x04000400u);
+                else cf = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
+                const uint32_t v0 = vertical<Y2>(dot2_lo(cf.x, d00), dot2_lo(cf.x, d10), b0, b1);
+                const uint32_t v1 = vertical<Y2>(dot2_hi(cf.y, d00), dot2_hi(cf.y, d10), b0, b1);
+                const uint32_t v2 = vertical<Y2>(dot2_lo(cf.z, d01), dot2_lo(cf.z, d11), b0, b1);
+                const uint32_t v3 = vertical<Y2>(dot2_hi(cf.w, d01), dot2_hi(cf.w, d11), b0, b1);
+                packed = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+            }
+        } else {
+            const int4 xo = __ldg(reinterpret_cast<const int4 *>(tb.xofs) + g);
+            const uint4 xc = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
+            const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
+            const uint32_t cs[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c0 + j < dcols) {
+                    const int sx = xs[j];
+                    const int sx1 = min(sx + 1, src_last);
+                    const int a0 = (int)(short)(cs[j] & 0xffffu), a1 = (int)(short)(cs[j] >> 16);
+                    const int h0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1;
+                    const int h1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
+                    packed |= vertical<false>(h0, h1, b0, b1) << (8 * j);
+                }
+            }
+        }
+        drow[g] = packed;
+    }
+}
+
+// Aprons of one row held in shared memory (LevelView: 32 bytes left of column 0 replicate it, columns > cols
+// replicate column cols-1); the wrap byte at column `cols` is written by the caller once the row below exists.
+__device__ __forceinline__ void smem_row_aprons(uint8_t *row, int cols, int pitch, int lane) {
+    const uint32_t first = row[0], last = row[cols - 1];
+    if (lane < kApronL / 4) reinterpret_cast<uint32_t *>(row - kApronL)[lane] = first * 0x01010101u;
+    for (int c = cols + 1 + lane; c < pitch - kApronL; c += 32) row[c] = (uint8_t)last;
+}
+
+// Fused pyramid + aprons.  One CTA owns a band of top-level rows of one image:
+//   1. the level-0 rows it needs arrive in shared memory by ONE bulk copy (cp.async.bulk, mbarrier completion):
+//      a band is contiguous in the pitched layout, so staging costs no instructions;
+//   2. level k is derived from level k-1 in shared memory, including its row aprons;
+//   3. each level's band leaves by bulk stores (shared -> global), again contiguous.
+// Bands of neighbouring CTAs may overlap by a row at the finer levels (both write identical bytes).  The only
+// byte a band cannot know is the wrap byte of its LAST row (first pixel of the row below): it is excluded from
+// the band's stores and written by the CTA whose band starts with that row.
 __global__ void __launch_bounds__(256)
-pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ PyrKernelParams kp) {
-    extern __shared__ __align__(16) uint8_t smem[];
+pyramid_band_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ PyrKernelParams kp) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
     const int L = pyr.levels;
     const int set = blockIdx.y / kp.nimg;
     const int img = kp.img0 + (blockIdx.y - set * kp.nimg);
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarps = 8;
 
     // Row bands [lo, hi) at every level for this CTA's top-level rows.  A band must contain the rows
     // the next-coarser band reads (needed range) AND reach the first row of the next CTA's band, so
@@ -103,17 +209,51 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
         }
     }
 
-    // Stage the level-0 band: contiguous bytes, 16-byte aligned (pitch % 16 == 0).
-    {
-        const LevelView &l0 = pyr.lv[0];
-        const uint4 *src = reinterpret_cast<const uint4 *>(l0.base[set] + (size_t)img * l0.slot +
-                                                           (size_t)lo[0] * l0.pitch);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem + kp.smem_off[0]);
-        const int nvec = (hi[0] - lo[0]) * (l0.pitch >> 4);
-        for (int i = tid; i < nvec; i += nthreads) dst[i] = __ldg(src + i);
+    // ---- 1. level-0 band: bulk copy global -> shared
+    const LevelView &l0 = pyr.lv[0];
+    uint8_t *g0 = l0.base[set] + (size_t)img * l0.slot + (size_t)lo[0] * l0.pitch;
+    uint8_t *S0 = smem + kp.smem_off[0];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t total = (uint32_t)(hi[0] - lo[0]) * (uint32_t)l0.pitch;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(total) : "memory");
+        for (uint32_t off = 0; off < total; off += 16384u) {
+            const uint32_t n = min(16384u, total - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(S0 + off)),
+                         "l"(g0 + off), "r"(n), "r"(smem_addr(bar))
+                         : "memory");
+        }
     }
-    __syncthreads();
+    __syncthreads();  // barrier initialised before anybody polls it
+    {
+        uint32_t ok = 0, spins = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(ok)
+                : "r"(smem_addr(bar)), "r"(0)
+                : "memory");
+            if (!ok && ++spins > (1u << 24)) __trap();  // a copy that never lands must not hang the GPU
+        }
+    }
 
+    // ---- level-0 aprons: straight to global (level 0 itself is input; only the apron bytes are written)
+    for (int r = warp; r < hi[0] - lo[0]; r += kWarps) {
+        const int R = lo[0] + r;
+        const uint8_t *srow = S0 + (size_t)r * l0.pitch;
+        uint8_t *grow = g0 + (size_t)r * l0.pitch;
+        const uint32_t first = srow[0], last = srow[l0.cols - 1];
+        uint32_t wrap;  // data[R*step + cols] of the reference's flat addressing (algorithm.h:48,53)
+        if (l0.step != l0.cols) wrap = srow[l0.cols];  // inside the caller's row padding, uploaded with the row
+        else if (R + 1 >= l0.rows) wrap = 0u;
+        else wrap = (r + 1 < hi[0] - lo[0]) ? srow[l0.pitch] : __ldg(grow + l0.pitch);
+        if (lane < kApronL / 4) reinterpret_cast<uint32_t *>(grow - kApronL)[lane] = first * 0x01010101u;
+        for (int c = l0.cols + lane; c < l0.pitch - kApronL; c += 32) grow[c] = (uint8_t)(c == l0.cols ? wrap : last);
+    }
+
+    // ---- 2./3. coarser levels
 #pragma unroll 1
     for (int k = 1; k < L; ++k) {
         const LevelView &ld = pyr.lv[k];
@@ -122,65 +262,60 @@ pyramid_fused_kernel(const __grid_constant__ PyramidView pyr, const __grid_const
         uint8_t *D = smem + kp.smem_off[k];
         const ResizeTables &tb = kp.tab[k];
         const int nr = hi[k] - lo[k];
-        const int ng = (ld.cols + 3) >> 2;  // 4-pixel groups per row
-        const int src_last = ls.cols - 1;
-        const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-        // a warp owns whole rows (row tables read once per row), its lanes stride over the 4-pixel groups
-        for (int r = warp; r < nr; r += nwarps) {
+        // few rows (coarse levels): several warps share a row
+        int split = 1;
+        while (split * 2 * nr <= kWarps) split *= 2;
+        const int part = warp % split;
+        for (int r = warp / split; r < nr; r += kWarps / split) {
             const int R = lo[k] + r;
             const int yo = __ldg(tb.yofs + R);
             const short2 b = __ldg(tb.ycoef + R);
-            const int b0 = b.x, b1 = b.y;
             const uint8_t *s0 = S + (d_clip(yo, ls.rows) - lo[k - 1]) * ls.pitch;
             const uint8_t *s1 = S + (d_clip(yo + 1, ls.rows) - lo[k - 1]) * ls.pitch;
             uint32_t *drow = reinterpret_cast<uint32_t *>(D + r * ld.pitch);
-            for (int g = lane; g < ng; g += 32) {
-                const int c0 = 4 * g;
-                uint32_t packed = 0;
-                if (tb.x_exact2 && c0 + 3 < ld.cols) {
-                    // exact halving in x: taps 2c, 2c+1 with weights 1024/1024 -> 8 consecutive source bytes
-                    const uint2 t0 = *reinterpret_cast<const uint2 *>(s0 + 2 * c0);
-                    const uint2 t1 = *reinterpret_cast<const uint2 *>(s1 + 2 * c0);
-                    const uint32_t w0[2] = {t0.x, t0.y}, w1[2] = {t1.x, t1.y};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t p0 = w0[j >> 1] >> (16 * (j & 1)), p1 = w1[j >> 1] >> (16 * (j & 1));
-                        const int h0 = (int)((p0 & 0xffu) + ((p0 >> 8) & 0xffu)) << 10;
-                        const int h1 = (int)((p1 & 0xffu) + ((p1 >> 8) & 0xffu)) << 10;
-                        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                        packed |= (uint32_t)v << (8 * j);
-                    }
-                } else {
-                    const int4 xo = __ldg(reinterpret_cast<const int4 *>(tb.xofs) + g);
-                    const uint4 xc = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
-                    const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
-                    const uint32_t cs[4] = {xc.x, xc.y, xc.z, xc.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (c0 + j < ld.cols) {
-                            const int sx = xs[j];
-                            const int sx1 = min(sx + 1, src_last);
-                            const int a0 = (int)(short)(cs[j] & 0xffffu), a1 = (int)(short)(cs[j] >> 16);
-                            const int h0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1;
-                            const int h1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
-                            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                            packed |= (uint32_t)v << (8 * j);
-                        }
-                    }
-                }
-                drow[g] = packed;
+            const int gfirst = part * 32 + lane, gstep = 32 * split;
+            if (tb.x_exact2) {
+                if (tb.y_exact2) resize_row<true, true>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
+                else resize_row<true, false>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
+            } else {
+                if (tb.y_exact2) resize_row<false, true>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
+                else resize_row<false, false>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
             }
         }
         __syncthreads();
-        // Write this level's band back: contiguous, 16-byte vectors.
-        {
-            uint4 *dst = reinterpret_cast<uint4 *>(ld.base[set] + (size_t)img * ld.slot +
-                                                   (size_t)lo[k] * ld.pitch);
-            const uint4 *src = reinterpret_cast<const uint4 *>(D);
-            const int nvec = nr * (ld.pitch >> 4);
-            for (int i = tid; i < nvec; i += nthreads) dst[i] = src[i];
+        for (int r = warp; r < nr; r += kWarps) smem_row_aprons(D + r * ld.pitch, ld.cols, ld.pitch, lane);
+        // wrap bytes (levels >= 1 are continuous, step == cols): first pixel of the row below, 0 after the last row
+        uint8_t *gD = ld.base[set] + (size_t)img * ld.slot + (size_t)lo[k] * ld.pitch;
+        if (tid < nr) {
+            const int R = lo[k] + tid;
+            if (R + 1 >= ld.rows) D[tid * ld.pitch + ld.cols] = 0;
+            else if (tid + 1 < nr) D[tid * ld.pitch + ld.cols] = D[(tid + 1) * ld.pitch];
+        } else if (tid == 32 * (kWarps - 1) && lo[k] > 0) {
+            gD[ld.cols - ld.pitch] = D[0];  // wrap byte of the row above this band
+        }
+        __syncthreads();
+        // band out: [left apron of the first row, column c16 of the last row) in one piece, the rest of the last
+        // row by plain stores that skip the wrap byte unless it is known (last row of the image)
+        const int c16 = ld.cols & ~15;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t total = (uint32_t)((nr - 1) * ld.pitch + c16 + kApronL);
+            for (uint32_t off = 0; off < total; off += 16384u) {
+                const uint32_t n = min(16384u, total - off);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gD - kApronL + off),
+                             "r"(smem_addr(D - kApronL + off)), "r"(n)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (warp == 1) {
+            const bool own_wrap = (hi[k] >= ld.rows);
+            const uint8_t *srow = D + (nr - 1) * ld.pitch;
+            uint8_t *grow = gD + (size_t)(nr - 1) * ld.pitch;
+            for (int c = c16 + lane; c < ld.pitch - kApronL; c += 32)
+                if (c != ld.cols || own_wrap) grow[c] = srow[c];
         }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem is read until here
 }
 
 // Row aprons: one WARP per row; grid = (row blocks of all levels, image * set) so that no thread divides by a run-time
@@ -273,7 +408,7 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
     for (int l = 1; l < levels; ++l) {
         hx[l] = build_axis(plan->cols[l - 1], plan->cols[l], true);
         hy[l] = build_axis(plan->rows[l - 1], plan->rows[l], false);
-        blob += pad4(plan->cols[l]) * 8 + pad4(plan->rows[l]) * 8;
+        blob += pad4(plan->cols[l]) * 8 + pad4(plan->rows[l]) * 8 + pad4((plan->cols[l] + 3) / 4) * 4;
     }
     std::vector<uint8_t> host(blob, 0);
     cudaError_t err = cudaMalloc(&plan->table_blob, blob);
@@ -298,6 +433,22 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
         t.x_exact2 = 1;
         for (int c = 0; c < nc; ++c)
             if (hx[l].ofs[c] != 2 * c || hx[l].coef[c].x != 1024 || hx[l].coef[c].y != 1024) t.x_exact2 = 0;
+        t.y_exact2 = 1;
+        for (int r = 0; r < nr; ++r)
+            if (hy[l].ofs[r] != 2 * r || hy[l].coef[r].x != 1024 || hy[l].coef[r].y != 1024) t.y_exact2 = 0;
+        // per 4-pixel group: first tap of the group if its pixels tap sx0, sx0+2, sx0+4, sx0+6 (the kernel's
+        // regular path), else -1 (tap offset steps inside the group, or partial group at the row end)
+        const int ng = (nc + 3) / 4;
+        std::vector<int> gofs(pad4(ng), -1);
+        for (int g = 0; g < ng; ++g) {
+            const int c0 = 4 * g;
+            bool regular = c0 + 3 < nc && hx[l].ofs[c0] >= 0;
+            for (int j = 1; regular && j < 4; ++j) regular = hx[l].ofs[c0 + j] == hx[l].ofs[c0] + 2 * j;
+            if (regular) gofs[g] = hx[l].ofs[c0];
+        }
+        t.gofs = reinterpret_cast<int *>(dbase + off);
+        memcpy(&host[off], gofs.data(), 4 * (size_t)ng);
+        off += pad4(ng) * 4;
     }
     err = cudaMemcpy(plan->table_blob, host.data(), blob, cudaMemcpyHostToDevice);
     if (err != cudaSuccess) return err;
@@ -319,8 +470,9 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
                 maxr[k - 1] = std::max(maxr[k - 1], hi - lo);
             }
         }
-        size_t bytes = 0;
+        size_t bytes = 128;  // mbarrier
         for (int l = 0; l < levels; ++l) {
+            bytes = ((bytes + 15) & ~(size_t)15) + kApronL;  // the first row's left apron precedes the band
             plan->smem_off[l] = (int)bytes;
             plan->max_rows[l] = maxr[l];
             bytes += (size_t)maxr[l] * plan->pitch[l];
@@ -340,7 +492,8 @@ void pyramid_plan_destroy(PyramidPlan *plan) {
 
 cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
                            int n_sets) {
-    if (plan.levels <= 1 || nimg <= 0) return cudaSuccess;
+    if (nimg <= 0) return cudaSuccess;
+    if (plan.levels <= 1) return launch_aprons(pyr, img0, nimg, stream, n_sets);  // no levels to build: aprons only
     PyrKernelParams kp;
     for (int l = 0; l < kMaxLevels; ++l) {
         kp.tab[l] = plan.tab[l];
@@ -351,7 +504,7 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int 
     kp.nimg = nimg;
     static thread_local size_t configured = 0;
     if (plan.smem_bytes > 48 * 1024 && plan.smem_bytes > configured) {
-        cudaError_t err = cudaFuncSetAttribute(pyramid_fused_kernel,
+        cudaError_t err = cudaFuncSetAttribute(pyramid_band_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)plan.smem_bytes);
         if (err != cudaSuccess) return err;
@@ -359,7 +512,7 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int 
     }
     const int top = plan.levels - 1;
     dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, n_sets * nimg);
-    pyramid_fused_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
+    pyramid_band_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
     return cudaGetLastError();
 }
 

@@ -45,6 +45,36 @@ def test_pyramid_with_row_step(tracker, oracle):
         assert np.array_equal(got[l], ref[l])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,levels,pad", [(376, 1241, 4, 0), (270, 481, 5, 0), (120, 333, 3, 67), (97, 203, 1, 0),
+                                                  (1080, 1920, 5, 0)])
+def test_row_aprons_of_every_level(tracker, oracle, rows, cols, levels, pad):
+    """The device layout the solver's border path relies on (LevelView): 32 bytes left of column 0 replicate it,
+    column `cols` holds the reference's flat-address neighbour data[r*step + cols] (algorithm.h:48,53: first pixel
+    of the next row, 0 after the last row; inside the row padding when step > cols), the rest replicates the last
+    pixel.  Written by the fused pyramid kernel (bands of neighbouring CTAs hand the wrap byte over)."""
+    big = np.random.default_rng(rows + cols).integers(0, 256, size=(rows, cols + pad), dtype=np.uint8)
+    img = big[:, :cols]
+    tracker.build_pyramid(img, levels)
+    ref = oracle.build_pyramid(np.ascontiguousarray(img), levels)
+    for l in range(levels):
+        raw, left = tracker.debug_read_level(l, ref[l].shape[0])
+        r, c = ref[l].shape
+        pitch = raw.shape[1]
+        assert np.array_equal(raw[:, left:left + c], ref[l]), f"level {l} pixels"
+        assert np.array_equal(raw[:, :left], np.repeat(ref[l][:, :1], left, axis=1)), f"level {l} left apron"
+        if l == 0 and pad:
+            wrap = big[:, cols].copy()
+            wrap[-1] = 0       # the ABI defines everything after the last pixel of the image as 0 (oracle: zero padding)
+        else:
+            wrap = np.concatenate([ref[l][1:, 0], [0]]).astype(np.uint8)
+        assert np.array_equal(raw[:, left + c], wrap), f"level {l} wrap byte"
+        n_right = pitch - left - c - 1 - left          # the last `left` bytes of a row are the next row's left apron
+        assert n_right >= 15
+        assert np.array_equal(raw[:, left + c + 1:left + c + 1 + n_right],
+                              np.repeat(ref[l][:, -1:], n_right, axis=1)), f"level {l} right apron"
+
+
 # ------------------------------------------------------------------ golden vectors through the C ABI
 def test_exact_kernel_reproduces_golden_vectors_bitwise(tracker, golden):
     meta, vec = golden
