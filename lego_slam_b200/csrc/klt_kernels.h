@@ -14,6 +14,11 @@ struct ResizeTables {
     int *yofs;      // [rows_l]  top tap
     short2 *ycoef;  // [rows_l]
     int *gofs;      // [ceil(cols_l/4)]  first tap of a regular 4-pixel group (taps sx0 + 2j), else -1
+    int *cofs;      // [ceil(cols_l/8)]  same for the 8-pixel chunks of the level 0 -> 1 streaming kernel
+    int *girr;      // the groups with gofs < 0, and their number
+    int n_girr;
+    int *irr;       // the chunks with cofs < 0, and their number
+    int n_irr;
     int x_exact2;   // xofs[c] == 2c and a0 == a1 == 1024 for every c
     int y_exact2;   // same for the rows
 };
@@ -27,12 +32,18 @@ struct PyramidPlan {
     int max_rows[kMaxLevels] = {0};     // max staged rows of level l over all CTAs
     size_t smem_bytes = 0;
     void *table_blob = nullptr;         // single device allocation behind all tables
+    void *band_tab = nullptr;           // device int2 [n_bands][kMaxLevels]: {first row, rows} of every level's band
+    int n_bands = 0;
+    // Level 0 -> 1 runs as a streaming kernel; levels 2.. are built by the band kernel from level 1, described by
+    // a plan of their own (the same pyramid seen from level 1).  Null in such a sub-plan and when levels == 1.
+    PyramidPlan *sub = nullptr;
 };
 
 // Level sizes of the reference's pyramid: cv::Size(cols*0.5, rows*0.5) repeatedly (truncation).
 // Returns false if a level would be empty.
 bool pyramid_level_sizes(int cols, int rows, int levels, int *lcols, int *lrows);
-cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan);
+cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan,
+                                bool band_kernel_only = false);
 void pyramid_plan_destroy(PyramidPlan *plan);
 // Builds levels 1..L-1 of images [img0, img0 + nimg) of both image sets from level 0 AND writes the row aprons
 // (see LevelView) of every level, one fused launch.

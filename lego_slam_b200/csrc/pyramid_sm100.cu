@@ -9,10 +9,16 @@
 //     h(x)  = S[sx]*a0 + S[sx+1]*a1                                        (int32, per source row)
 //     dst   = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2
 //
-// B200 design: HBM-bound (level 0 is read once, levels 1..L-1 written once; 619,601 B per 1241x376
-// image at L=4).  One CTA owns a band of top-level rows of one image: it stages the level-0 rows it
-// needs in shared memory with coalesced 16-byte loads, derives every coarser level from shared
-// memory, and writes each level's rows back with 16-byte stores -- no level is re-read from HBM.
+// B200 design: HBM-bound on paper (level 0 read once, levels 1..L-1 written once: 619,601 B per 1241x376
+// image at L=4), instruction-bound in practice, so the work is split where the bytes are:
+//   pyramid_l01_kernel   level 0 -> 1 (three quarters of the bytes): streaming, a warp per output row, 16-byte
+//                        loads, dp2a horizontal pass, no shared memory, no barrier; writes the level-0 aprons.
+//   pyramid_band_kernel  levels 2.. from level 1 (L2-resident by then): a CTA owns a band of top-level rows,
+//                        stages the level-1 rows it needs by ONE bulk copy (cp.async.bulk + mbarrier), derives
+//                        every coarser level in shared memory and writes each band back by bulk stores; writes
+//                        the aprons of levels 1...
+// (The first version fused all levels in the band kernel: 1475 instructions per warp of which 370 were resize
+// arithmetic -- per-level set-up, barriers and tiny phases dominated; profiles/README.md.)
 // The coefficient tables are built once per shape on the host and live in global memory (L1/L2 hits).
 #include <algorithm>
 #include <cmath>
@@ -66,8 +72,8 @@ inline int clip_row(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
 struct PyrKernelParams {
     ResizeTables tab[kMaxLevels];
     int smem_off[kMaxLevels];  // byte offset of level l's band (pixel 0 of its first row) in dynamic smem
-    int top_rows;
-    int img0, nimg;  // image range of this launch (chunked batches)
+    const int2 *bands;         // [n_bands][kMaxLevels] {first row, row count} of every level's band (host-built)
+    int img0, nimg;            // image range of this launch (chunked batches)
 };
 
 __device__ __forceinline__ int d_clip(int v, int n) { return v < 0 ? 0 : (v < n ? v : n - 1); }
@@ -106,7 +112,7 @@ __device__ __forceinline__ void resize_row(const uint8_t *__restrict__ s0, const
     const int ng = (dcols + 3) >> 2;
     for (int g = g0; g < ng; g += gstep) {
         const int c0 = 4 * g;
-        uint32_t packed = 0;
+        uint32_t packed;
         int info = X2 ? ((c0 + 3 < dcols) ? 2 * c0 : -1) : __ldg(tb.gofs + g);
         if (info >= 0) {
             uint32_t d00, d01, d10, d11;  // source bytes sx0..sx0+7 of the two source rows
@@ -139,24 +145,21 @@ __device__ __forceinline__ void resize_row(const uint8_t *__restrict__ s0, const
                 const uint32_t v3 = vertical<Y2>(dot2_hi(cf.w, d01), dot2_hi(cf.w, d11), b0, b1);
                 packed = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
             }
-        } else {
-            const int4 xo = __ldg(reinterpret_cast<const int4 *>(tb.xofs) + g);
-            const uint4 xc = __ldg(reinterpret_cast<const uint4 *>(tb.xcoef) + g);
-            const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
-            const uint32_t cs[4] = {xc.x, xc.y, xc.z, xc.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (c0 + j < dcols) {
-                    const int sx = xs[j];
-                    const int sx1 = min(sx + 1, src_last);
-                    const int a0 = (int)(short)(cs[j] & 0xffffu), a1 = (int)(short)(cs[j] >> 16);
-                    const int h0 = (int)s0[sx] * a0 + (int)s0[sx1] * a1;
-                    const int h1 = (int)s1[sx] * a0 + (int)s1[sx1] * a1;
-                    packed |= vertical<false>(h0, h1, b0, b1) << (8 * j);
-                }
-            }
+            drow[g] = packed;
         }
-        drow[g] = packed;
+    }
+    // irregular groups (tap offset steps inside the group; partial group at the row end): one pixel per lane
+    uint8_t *dbytes = reinterpret_cast<uint8_t *>(drow);
+    for (int q = g0; q < 4 * tb.n_girr; q += gstep) {
+        const int col = 4 * __ldg(tb.girr + (q >> 2)) + (q & 3);
+        if (col < dcols) {
+            const int sx = __ldg(tb.xofs + col);
+            const int sx1 = min(sx + 1, src_last);
+            const short2 cf = __ldg(tb.xcoef + col);
+            const int h0 = (int)s0[sx] * cf.x + (int)s0[sx1] * cf.y;
+            const int h1 = (int)s1[sx] * cf.x + (int)s1[sx1] * cf.y;
+            dbytes[col] = (uint8_t)vertical<false>(h0, h1, b0, b1);
+        }
     }
 }
 
@@ -181,42 +184,25 @@ pyramid_band_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     extern __shared__ __align__(128) uint8_t smem[];
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem);
     const int L = pyr.levels;
-    const int set = blockIdx.y / kp.nimg;
-    const int img = kp.img0 + (blockIdx.y - set * kp.nimg);
+    const int set = blockIdx.y >= kp.nimg ? 1 : 0;
+    const int img = kp.img0 + blockIdx.y - set * kp.nimg;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kWarps = 8;
-
-    // Row bands [lo, hi) at every level for this CTA's top-level rows.  A band must contain the rows
-    // the next-coarser band reads (needed range) AND reach the first row of the next CTA's band, so
-    // that the bands of one level tile it completely: with truncated level sizes (135 -> 67) or a
-    // vertical scale above 2 the coarser level does not read every finer row.
-    int lo[kMaxLevels], hi[kMaxLevels];
-    {
-        const bool last_band = (blockIdx.x + 1 == gridDim.x);
-        int next_lo = (blockIdx.x + 1) * kp.top_rows;  // first row of the next band at level k
-        lo[L - 1] = blockIdx.x * kp.top_rows;
-        hi[L - 1] = min(lo[L - 1] + kp.top_rows, pyr.lv[L - 1].rows);
-#pragma unroll
-        for (int k = kMaxLevels - 1; k >= 1; --k) {
-            if (k <= L - 1) {
-                const int *yofs = kp.tab[k].yofs;
-                const int rows_src = pyr.lv[k - 1].rows;
-                lo[k - 1] = d_clip(__ldg(yofs + lo[k]), rows_src);
-                const int needed_hi = d_clip(__ldg(yofs + hi[k] - 1) + 1, rows_src) + 1;
-                next_lo = last_band ? rows_src : d_clip(__ldg(yofs + next_lo), rows_src);
-                hi[k - 1] = max(needed_hi, next_lo);
-            }
-        }
-    }
+    // Row band {first row, row count} of every level for this CTA (built on the host: a band contains the rows the
+    // next-coarser band reads AND reaches the first row of the next CTA's band, so that the bands of one level
+    // tile it completely -- with truncated level sizes (135 -> 67) the coarser level does not read every finer row).
+    const int2 *band = kp.bands + (size_t)blockIdx.x * kMaxLevels;
+    const int2 band0 = __ldg(band);
+    const int lo0 = band0.x, nr0 = band0.y;
 
     // ---- 1. level-0 band: bulk copy global -> shared
     const LevelView &l0 = pyr.lv[0];
-    uint8_t *g0 = l0.base[set] + (size_t)img * l0.slot + (size_t)lo[0] * l0.pitch;
+    uint8_t *g0 = l0.base[set] + (size_t)img * l0.slot + (size_t)lo0 * l0.pitch;
     uint8_t *S0 = smem + kp.smem_off[0];
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t total = (uint32_t)(hi[0] - lo[0]) * (uint32_t)l0.pitch;
+        const uint32_t total = (uint32_t)nr0 * (uint32_t)l0.pitch;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(total) : "memory");
         for (uint32_t off = 0; off < total; off += 16384u) {
             const uint32_t n = min(16384u, total - off);
@@ -240,20 +226,21 @@ pyramid_band_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     }
 
     // ---- level-0 aprons: straight to global (level 0 itself is input; only the apron bytes are written)
-    for (int r = warp; r < hi[0] - lo[0]; r += kWarps) {
-        const int R = lo[0] + r;
+    for (int r = warp; r < nr0; r += kWarps) {
+        const int R = lo0 + r;
         const uint8_t *srow = S0 + (size_t)r * l0.pitch;
         uint8_t *grow = g0 + (size_t)r * l0.pitch;
         const uint32_t first = srow[0], last = srow[l0.cols - 1];
         uint32_t wrap;  // data[R*step + cols] of the reference's flat addressing (algorithm.h:48,53)
         if (l0.step != l0.cols) wrap = srow[l0.cols];  // inside the caller's row padding, uploaded with the row
         else if (R + 1 >= l0.rows) wrap = 0u;
-        else wrap = (r + 1 < hi[0] - lo[0]) ? srow[l0.pitch] : __ldg(grow + l0.pitch);
+        else wrap = (r + 1 < nr0) ? srow[l0.pitch] : __ldg(grow + l0.pitch);
         if (lane < kApronL / 4) reinterpret_cast<uint32_t *>(grow - kApronL)[lane] = first * 0x01010101u;
         for (int c = l0.cols + lane; c < l0.pitch - kApronL; c += 32) grow[c] = (uint8_t)(c == l0.cols ? wrap : last);
     }
 
     // ---- 2./3. coarser levels
+    int lo_src = lo0;
 #pragma unroll 1
     for (int k = 1; k < L; ++k) {
         const LevelView &ld = pyr.lv[k];
@@ -261,45 +248,43 @@ pyramid_band_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         const uint8_t *S = smem + kp.smem_off[k - 1];
         uint8_t *D = smem + kp.smem_off[k];
         const ResizeTables &tb = kp.tab[k];
-        const int nr = hi[k] - lo[k];
-        // few rows (coarse levels): several warps share a row
-        int split = 1;
-        while (split * 2 * nr <= kWarps) split *= 2;
-        const int part = warp % split;
-        for (int r = warp / split; r < nr; r += kWarps / split) {
-            const int R = lo[k] + r;
+        const int2 bk = __ldg(band + k);
+        const int lo = bk.x, nr = bk.y;
+        const int dpitch = ld.pitch, dcols = ld.cols, drows = ld.rows, spitch = ls.pitch, srows = ls.rows;
+        // few rows (coarse levels): 2^lg warps share a row
+        int lg = 0;
+        while ((2 << lg) * nr <= kWarps) ++lg;
+        const int gfirst = (warp & ((1 << lg) - 1)) * 32 + lane, gstep = 32 << lg;
+        const int mode = (tb.x_exact2 ? 2 : 0) | (tb.y_exact2 ? 1 : 0);
+        for (int r = warp >> lg; r < nr; r += kWarps >> lg) {
+            const int R = lo + r;
             const int yo = __ldg(tb.yofs + R);
             const short2 b = __ldg(tb.ycoef + R);
-            const uint8_t *s0 = S + (d_clip(yo, ls.rows) - lo[k - 1]) * ls.pitch;
-            const uint8_t *s1 = S + (d_clip(yo + 1, ls.rows) - lo[k - 1]) * ls.pitch;
-            uint32_t *drow = reinterpret_cast<uint32_t *>(D + r * ld.pitch);
-            const int gfirst = part * 32 + lane, gstep = 32 * split;
-            if (tb.x_exact2) {
-                if (tb.y_exact2) resize_row<true, true>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
-                else resize_row<true, false>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
-            } else {
-                if (tb.y_exact2) resize_row<false, true>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
-                else resize_row<false, false>(s0, s1, drow, tb, b.x, b.y, ld.cols, ls.cols - 1, gfirst, gstep);
-            }
+            const uint8_t *s0 = S + (d_clip(yo, srows) - lo_src) * spitch;
+            const uint8_t *s1 = S + (d_clip(yo + 1, srows) - lo_src) * spitch;
+            uint32_t *drow = reinterpret_cast<uint32_t *>(D + r * dpitch);
+            if (mode == 3) resize_row<true, true>(s0, s1, drow, tb, b.x, b.y, dcols, ls.cols - 1, gfirst, gstep);
+            else if (mode == 1) resize_row<false, true>(s0, s1, drow, tb, b.x, b.y, dcols, ls.cols - 1, gfirst, gstep);
+            else if (mode == 2) resize_row<true, false>(s0, s1, drow, tb, b.x, b.y, dcols, ls.cols - 1, gfirst, gstep);
+            else resize_row<false, false>(s0, s1, drow, tb, b.x, b.y, dcols, ls.cols - 1, gfirst, gstep);
         }
         __syncthreads();
-        for (int r = warp; r < nr; r += kWarps) smem_row_aprons(D + r * ld.pitch, ld.cols, ld.pitch, lane);
+        for (int r = warp; r < nr; r += kWarps) smem_row_aprons(D + r * dpitch, dcols, dpitch, lane);
         // wrap bytes (levels >= 1 are continuous, step == cols): first pixel of the row below, 0 after the last row
-        uint8_t *gD = ld.base[set] + (size_t)img * ld.slot + (size_t)lo[k] * ld.pitch;
+        uint8_t *gD = ld.base[set] + (size_t)img * ld.slot + (size_t)lo * dpitch;
         if (tid < nr) {
-            const int R = lo[k] + tid;
-            if (R + 1 >= ld.rows) D[tid * ld.pitch + ld.cols] = 0;
-            else if (tid + 1 < nr) D[tid * ld.pitch + ld.cols] = D[(tid + 1) * ld.pitch];
-        } else if (tid == 32 * (kWarps - 1) && lo[k] > 0) {
-            gD[ld.cols - ld.pitch] = D[0];  // wrap byte of the row above this band
+            if (lo + tid + 1 >= drows) D[tid * dpitch + dcols] = 0;
+            else if (tid + 1 < nr) D[tid * dpitch + dcols] = D[(tid + 1) * dpitch];
+        } else if (tid == 32 * (kWarps - 1) && lo > 0) {
+            gD[dcols - dpitch] = D[0];  // wrap byte of the row above this band
         }
         __syncthreads();
         // band out: [left apron of the first row, column c16 of the last row) in one piece, the rest of the last
         // row by plain stores that skip the wrap byte unless it is known (last row of the image)
-        const int c16 = ld.cols & ~15;
+        const int c16 = dcols & ~15;
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t total = (uint32_t)((nr - 1) * ld.pitch + c16 + kApronL);
+            const uint32_t total = (uint32_t)((nr - 1) * dpitch + c16 + kApronL);
             for (uint32_t off = 0; off < total; off += 16384u) {
                 const uint32_t n = min(16384u, total - off);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gD - kApronL + off),
@@ -308,14 +293,149 @@ pyramid_band_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         } else if (warp == 1) {
-            const bool own_wrap = (hi[k] >= ld.rows);
-            const uint8_t *srow = D + (nr - 1) * ld.pitch;
-            uint8_t *grow = gD + (size_t)(nr - 1) * ld.pitch;
-            for (int c = c16 + lane; c < ld.pitch - kApronL; c += 32)
-                if (c != ld.cols || own_wrap) grow[c] = srow[c];
+            const bool own_wrap = (lo + nr >= drows);
+            const uint8_t *srow = D + (nr - 1) * dpitch;
+            uint8_t *grow = gD + (size_t)(nr - 1) * dpitch;
+            for (int c = c16 + lane; c < dpitch - kApronL; c += 32)
+                if (c != dcols || own_wrap) grow[c] = srow[c];
         }
+        lo_src = lo;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem is read until here
+}
+
+// ------------------------------------------------------------------------------------------------
+// Level 0 -> level 1 (three quarters of all pyramid bytes) as a pure streaming kernel: no shared memory, no
+// block barrier.  A warp owns one level-1 row; a lane takes 8 output pixels = 16 source bytes of each of the two
+// source rows with one aligned 16-byte load per row.  A 0.5x level has taps sx = 2c + delta(c), delta in {0, 1}
+// (dn = floor(sn/2), so the scale is 2 or 2 + 1/dn): where delta = 1 the 16 bytes start one byte later, and the
+// missing byte comes from the next lane's load by shuffle.  The chunk in which delta steps (one per row when sn
+// is odd) and the partial chunk at the row end take the per-pixel path.  The CTA also writes the level-0 row
+// aprons of the 16 source rows under it (level-1 aprons are written by the band kernel that builds levels 2..).
+// ------------------------------------------------------------------------------------------------
+struct L01Params {
+    const int *yofs;       // [rows1]
+    const short2 *ycoef;   // [rows1]
+    const int *cofs;       // [ceil(cols1/8)] first tap of a regular 8-pixel chunk (taps sx0 + 2j), else -1
+    const int *irr;        // the irregular chunks (same for every row)
+    int n_irr;
+    const int *xofs;       // [cols1] (padded to 8)
+    const short2 *xcoef;   // [cols1] (padded to 8)
+    int img0, nimg;
+};
+
+template <bool X2Y2, bool Y2>
+__global__ void __launch_bounds__(256)
+pyramid_l01_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ L01Params p) {
+    const LevelView &l0 = pyr.lv[0];
+    const LevelView &l1 = pyr.lv[1];
+    const int set = blockIdx.y >= p.nimg ? 1 : 0;
+    const int img = p.img0 + blockIdx.y - set * p.nimg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint8_t *src = l0.base[set] + (size_t)img * l0.slot;
+    uint8_t *dst = l1.base[set] + (size_t)img * l1.slot;
+    const int spitch = l0.pitch, scols = l0.cols, srows = l0.rows;
+
+    const int R = 8 * blockIdx.x + warp;
+    if (R < l1.rows) {
+    const int yo = __ldg(p.yofs + R);
+    const short2 b = __ldg(p.ycoef + R);
+    const uint8_t *s0 = src + (size_t)d_clip(yo, srows) * spitch;
+    const uint8_t *s1 = src + (size_t)d_clip(yo + 1, srows) * spitch;
+    uint8_t *drow = dst + (size_t)R * l1.pitch;
+    const int dcols = l1.cols, nchunks = (dcols + 7) >> 3, src_last = scols - 1;
+
+    // chunk i = 16 source bytes per row + the word after them (for delta = 1); the loads of the next trip are
+    // issued before this trip's arithmetic (the kernel is latency-bound otherwise: profiles/)
+    uint4 a_n = make_uint4(0, 0, 0, 0), c_n = a_n;
+    uint32_t na_n = 0, nc_n = 0;
+    int info_n = -1;
+    auto fetch = [&](int i) {
+        if (i < nchunks) {
+            a_n = __ldg(reinterpret_cast<const uint4 *>(s0) + i);
+            c_n = __ldg(reinterpret_cast<const uint4 *>(s1) + i);
+            na_n = __ldg(reinterpret_cast<const uint32_t *>(s0) + 4 * i + 4);  // (the row's allocation extends 48 bytes
+            nc_n = __ldg(reinterpret_cast<const uint32_t *>(s1) + 4 * i + 4);  //  past the last pixel)
+            info_n = __ldg(p.cofs + i);
+        }
+    };
+    fetch(lane);
+    for (int i = lane; i < nchunks; i += 32) {
+        const uint4 a = a_n, c = c_n;
+        const uint32_t na = na_n, nc = nc_n;
+        const int info = info_n;
+        fetch(i + 32);
+        if (info >= 0) {
+            uint2 out;
+            const int sh = (info - 16 * i) * 8;  // 0 or 8 (host-checked)
+            const uint32_t w0[4] = {__funnelshift_r(a.x, a.y, sh), __funnelshift_r(a.y, a.z, sh), __funnelshift_r(a.z, a.w, sh),
+                                    __funnelshift_r(a.w, na, sh)};
+            const uint32_t w1[4] = {__funnelshift_r(c.x, c.y, sh), __funnelshift_r(c.y, c.z, sh), __funnelshift_r(c.z, c.w, sh),
+                                    __funnelshift_r(c.w, nc, sh)};
+            if (X2Y2) {
+                uint32_t t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    t[q] = (__byte_perm(w0[q], 0u, 0x4240) + __byte_perm(w0[q], 0u, 0x4341) + __byte_perm(w1[q], 0u, 0x4240) +
+                            __byte_perm(w1[q], 0u, 0x4341) + 0x00020002u) >> 2;
+                out.x = __byte_perm(t[0], t[1], 0x6420);
+                out.y = __byte_perm(t[2], t[3], 0x6420);
+            } else {
+                const uint4 cf0 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i);
+                const uint4 cf1 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i + 1);
+                const uint32_t cf[8] = {cf0.x, cf0.y, cf0.z, cf0.w, cf1.x, cf1.y, cf1.z, cf1.w};
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int h0 = (j & 1) ? dot2_hi(cf[j], w0[j >> 1]) : dot2_lo(cf[j], w0[j >> 1]);
+                    const int h1 = (j & 1) ? dot2_hi(cf[j], w1[j >> 1]) : dot2_lo(cf[j], w1[j >> 1]);
+                    v[j] = vertical<Y2>(h0, h1, b.x, b.y);
+                }
+                out.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                out.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+            }
+            reinterpret_cast<uint2 *>(drow)[i] = out;
+        }
+    }
+    // The irregular chunks (where the tap offset steps, and the partial chunk at the row end): one pixel per lane.
+    for (int q = lane; q < 8 * p.n_irr; q += 32) {
+        const int col = 8 * __ldg(p.irr + (q >> 3)) + (q & 7);
+        if (col < dcols) {
+            const int sx = __ldg(p.xofs + col);
+            const int sx1 = min(sx + 1, src_last);
+            const short2 cf = __ldg(p.xcoef + col);
+            const int h0 = (int)s0[sx] * cf.x + (int)s0[sx1] * cf.y;
+            const int h1 = (int)s1[sx] * cf.x + (int)s1[sx1] * cf.y;
+            drow[col] = (uint8_t)vertical<false>(h0, h1, b.x, b.y);
+        }
+    }
+    }
+
+    // ---- level-0 aprons of the 16 source rows under this CTA: ONE warp, a lane per row (every warp doing two
+    // rows cost a quarter of the kernel's instructions, mostly 64-bit address arithmetic: profiles/)
+    if (warp == 7) {
+        const int Rr = 16 * blockIdx.x + (lane & 15);
+        if (Rr < srows) {
+            uint8_t *grow = const_cast<uint8_t *>(src) + (size_t)Rr * spitch;
+            const uint32_t first = grow[0], last = grow[scols - 1];
+            uint32_t wrap;  // data[R*step + cols] of the reference's flat addressing (algorithm.h:48,53)
+            if (l0.step != scols) wrap = grow[scols];  // inside the caller's row padding, uploaded with the row
+            else wrap = (Rr + 1 < srows) ? grow[spitch] : 0u;
+            if (lane < 16) {  // left apron: 32 bytes, 16-byte aligned
+                const uint32_t f4 = first * 0x01010101u;
+                reinterpret_cast<uint4 *>(grow - kApronL)[0] = make_uint4(f4, f4, f4, f4);
+                reinterpret_cast<uint4 *>(grow - kApronL)[1] = make_uint4(f4, f4, f4, f4);
+            } else {          // right apron: wrap byte, then the last pixel replicated up to the next row's left apron
+                const int end = spitch - kApronL;
+                int c = scols;
+                grow[c++] = (uint8_t)wrap;
+                for (; (c & 3) && c < end; ++c) grow[c] = (uint8_t)last;
+                const uint32_t l4 = last * 0x01010101u;
+                for (; c + 4 <= end; c += 4) *reinterpret_cast<uint32_t *>(grow + c) = l4;
+                for (; c < end; ++c) grow[c] = (uint8_t)last;
+            }
+        }
+    }
 }
 
 // Row aprons: one WARP per row; grid = (row blocks of all levels, image * set) so that no thread divides by a run-time
@@ -394,7 +514,8 @@ cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan) {
+cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch, PyramidPlan *plan,
+                                bool band_kernel_only) {
     *plan = PyramidPlan();
     plan->levels = levels;
     if (!pyramid_level_sizes(cols, rows, levels, plan->cols, plan->rows)) return cudaErrorInvalidValue;
@@ -405,10 +526,12 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
     std::vector<HostAxis> hx(levels), hy(levels);
     size_t blob = 0;
     auto pad4 = [](int n) { return (size_t)((n + 3) & ~3); };
+    auto pad8 = [](int n) { return (size_t)((n + 7) & ~7); };  // x tables: the streaming kernel reads 8 entries at a time
     for (int l = 1; l < levels; ++l) {
         hx[l] = build_axis(plan->cols[l - 1], plan->cols[l], true);
         hy[l] = build_axis(plan->rows[l - 1], plan->rows[l], false);
-        blob += pad4(plan->cols[l]) * 8 + pad4(plan->rows[l]) * 8 + pad4((plan->cols[l] + 3) / 4) * 4;
+        blob += pad8(plan->cols[l]) * 8 + pad4(plan->rows[l]) * 8 + 2 * pad4((plan->cols[l] + 3) / 4) * 4 +
+                2 * pad4((plan->cols[l] + 7) / 8) * 4;
     }
     std::vector<uint8_t> host(blob, 0);
     cudaError_t err = cudaMalloc(&plan->table_blob, blob);
@@ -420,10 +543,10 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
         const int nc = plan->cols[l], nr = plan->rows[l];
         t.xofs = reinterpret_cast<int *>(dbase + off);
         memcpy(&host[off], hx[l].ofs.data(), 4 * (size_t)nc);
-        off += pad4(nc) * 4;
+        off += pad8(nc) * 4;
         t.xcoef = reinterpret_cast<short2 *>(dbase + off);
         memcpy(&host[off], hx[l].coef.data(), 4 * (size_t)nc);
-        off += pad4(nc) * 4;
+        off += pad8(nc) * 4;
         t.yofs = reinterpret_cast<int *>(dbase + off);
         memcpy(&host[off], hy[l].ofs.data(), 4 * (size_t)nr);
         off += pad4(nr) * 4;
@@ -449,17 +572,57 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
         t.gofs = reinterpret_cast<int *>(dbase + off);
         memcpy(&host[off], gofs.data(), 4 * (size_t)ng);
         off += pad4(ng) * 4;
+        // per 8-pixel chunk (level 0 -> 1 streaming kernel): first tap if the chunk is complete, its pixels tap
+        // sx0 + 2j and sx0 is 0..1 bytes past the chunk's aligned 16 source bytes
+        const int nch = (nc + 7) / 8;
+        std::vector<int> cofs(pad4(nch), -1);
+        for (int i = 0; i < nch; ++i) {
+            const int c0 = 8 * i;
+            bool regular = c0 + 7 < nc && hx[l].ofs[c0] >= 16 * i && hx[l].ofs[c0] <= 16 * i + 1;
+            for (int j = 1; regular && j < 8; ++j) regular = hx[l].ofs[c0 + j] == hx[l].ofs[c0] + 2 * j;
+            if (regular) cofs[i] = hx[l].ofs[c0];
+        }
+        t.cofs = reinterpret_cast<int *>(dbase + off);
+        memcpy(&host[off], cofs.data(), 4 * (size_t)nch);
+        off += pad4(nch) * 4;
+        // the irregular groups / chunks as lists (the kernels give them one pixel per lane after the regular ones)
+        std::vector<int> girr, irr;
+        for (int g = 0; g < ng; ++g)
+            if (gofs[g] < 0) girr.push_back(g);
+        for (int i = 0; i < nch; ++i)
+            if (cofs[i] < 0) irr.push_back(i);
+        t.girr = reinterpret_cast<int *>(dbase + off);
+        t.n_girr = (int)girr.size();
+        memcpy(&host[off], girr.data(), 4 * girr.size());
+        off += pad4(ng) * 4;
+        t.irr = reinterpret_cast<int *>(dbase + off);
+        t.n_irr = (int)irr.size();
+        memcpy(&host[off], irr.data(), 4 * irr.size());
+        off += pad4(nch) * 4;
     }
     err = cudaMemcpy(plan->table_blob, host.data(), blob, cudaMemcpyHostToDevice);
     if (err != cudaSuccess) return err;
 
-    // ---- band sizes: pick the largest top-row band whose staging fits comfortably in smem ----
+    if (!band_kernel_only) {
+        // level 0 -> 1: streaming kernel (tables of level 1 above); levels 2..: band kernel on the pyramid seen from level 1
+        plan->sub = new PyramidPlan();
+        return pyramid_plan_create(plan->cols[1], plan->rows[1], levels - 1, pitch + 1, plan->sub, true);
+    }
+
+    // ---- bands: the largest top-row band whose staging fits the shared-memory budget; every band's row range
+    // at every level goes into a device table (the kernel used to derive it with a chain of dependent loads) ----
     const int top = levels - 1;
-    for (int tr = 4; tr >= 1; tr >>= 1) {
+    size_t budget = 48 * 1024;  // measured on B200 (1241x376, L=4): 40-48 KB bands best, 64-100 KB 5 % slower
+    if (const char *e = getenv("LEGO_KLT_PYR_SMEM_KB")) budget = (size_t)atoi(e) * 1024;  // tuning aid
+    std::vector<int2> bands;
+    for (int tr = 32; tr >= 1; tr >>= 1) {
         int maxr[kMaxLevels] = {0};
+        bands.clear();
         for (int t0 = 0; t0 < plan->rows[top]; t0 += tr) {
             const bool last_band = t0 + tr >= plan->rows[top];
             int lo = t0, hi = std::min(t0 + tr, plan->rows[top]), next_lo = t0 + tr;
+            int2 rec[kMaxLevels] = {};
+            rec[top] = make_int2(lo, hi - lo);
             maxr[top] = std::max(maxr[top], hi - lo);
             for (int k = top; k >= 1; --k) {
                 int nlo = clip_row(hy[k].ofs[lo], plan->rows[k - 1]);
@@ -467,8 +630,10 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
                 next_lo = last_band ? plan->rows[k - 1] : clip_row(hy[k].ofs[next_lo], plan->rows[k - 1]);
                 lo = nlo;
                 hi = std::max(needed_hi, next_lo);
+                rec[k - 1] = make_int2(lo, hi - lo);
                 maxr[k - 1] = std::max(maxr[k - 1], hi - lo);
             }
+            bands.insert(bands.end(), rec, rec + kMaxLevels);
         }
         size_t bytes = 128;  // mbarrier
         for (int l = 0; l < levels; ++l) {
@@ -479,41 +644,84 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
         }
         plan->smem_bytes = bytes;
         plan->top_rows_per_cta = tr;
-        if (bytes <= 56 * 1024 || tr == 1) break;
+        if (bytes <= budget || tr == 1) break;
     }
+    plan->n_bands = (int)(bands.size() / kMaxLevels);
+    err = cudaMalloc(&plan->band_tab, bands.size() * sizeof(int2));
+    if (err != cudaSuccess) return err;
+    err = cudaMemcpy(plan->band_tab, bands.data(), bands.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return err;
     if (plan->smem_bytes > 220 * 1024) return cudaErrorInvalidValue;
     return cudaSuccess;
 }
 
 void pyramid_plan_destroy(PyramidPlan *plan) {
+    if (plan->sub) {
+        pyramid_plan_destroy(plan->sub);
+        delete plan->sub;
+    }
     if (plan->table_blob) cudaFree(plan->table_blob);
+    if (plan->band_tab) cudaFree(plan->band_tab);
     *plan = PyramidPlan();
 }
 
-cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
-                           int n_sets) {
-    if (nimg <= 0) return cudaSuccess;
+namespace {
+
+cudaError_t launch_band_kernel(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
+                               int n_sets) {
     if (plan.levels <= 1) return launch_aprons(pyr, img0, nimg, stream, n_sets);  // no levels to build: aprons only
     PyrKernelParams kp;
     for (int l = 0; l < kMaxLevels; ++l) {
         kp.tab[l] = plan.tab[l];
         kp.smem_off[l] = plan.smem_off[l];
     }
-    kp.top_rows = plan.top_rows_per_cta;
+    kp.bands = static_cast<const int2 *>(plan.band_tab);
     kp.img0 = img0;
     kp.nimg = nimg;
     static thread_local size_t configured = 0;
     if (plan.smem_bytes > 48 * 1024 && plan.smem_bytes > configured) {
-        cudaError_t err = cudaFuncSetAttribute(pyramid_band_kernel,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(pyramid_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)plan.smem_bytes);
         if (err != cudaSuccess) return err;
         configured = plan.smem_bytes;
     }
-    const int top = plan.levels - 1;
-    dim3 grid((plan.rows[top] + plan.top_rows_per_cta - 1) / plan.top_rows_per_cta, n_sets * nimg);
+    dim3 grid(plan.n_bands, n_sets * nimg);
     pyramid_band_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int img0, int nimg, cudaStream_t stream,
+                           int n_sets) {
+    if (nimg <= 0) return cudaSuccess;
+    if (!plan.sub) return launch_band_kernel(plan, pyr, img0, nimg, stream, n_sets);
+    // level 0 -> 1 (+ level-0 aprons)
+    L01Params p;
+    const ResizeTables &t = plan.tab[1];
+    p.yofs = t.yofs;
+    p.ycoef = t.ycoef;
+    p.cofs = t.cofs;
+    p.xofs = t.xofs;
+    p.xcoef = t.xcoef;
+    p.irr = t.irr;
+    p.n_irr = t.n_irr;
+    p.img0 = img0;
+    p.nimg = nimg;
+    // 8 level-1 rows and the 16 level-0 rows under them per CTA; one more CTA if an odd last level-0 row is left over
+    const int ctas = std::max((plan.rows[1] + 7) / 8, (plan.rows[0] + 15) / 16);
+    dim3 grid(ctas, n_sets * nimg);
+    if (t.x_exact2 && t.y_exact2) pyramid_l01_kernel<true, true><<<grid, 256, 0, stream>>>(pyr, p);
+    else if (t.y_exact2) pyramid_l01_kernel<false, true><<<grid, 256, 0, stream>>>(pyr, p);
+    else pyramid_l01_kernel<false, false><<<grid, 256, 0, stream>>>(pyr, p);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    // levels 2..: the same pyramid seen from level 1 (the band kernel also writes the aprons of its level 0)
+    PyramidView up;
+    up.levels = pyr.levels - 1;
+    up.n_images = pyr.n_images;
+    for (int l = 0; l < up.levels; ++l) up.lv[l] = pyr.lv[l + 1];
+    return launch_band_kernel(*plan.sub, up, img0, nimg, stream, n_sets);
 }
 
 }  // namespace legoklt
