@@ -85,7 +85,8 @@ struct SolverArgs {
     const int *list_count;
     // LANE kernel work distribution / deferral (device scalars, zeroed before each run).
     double *scratch;          // LANE kernel: 6 doubles per resident thread (multi-family partial sums)
-    float *templates;         // [n_total][levels][52]: I1 patches + regularity flag (template kernel)
+    float *templates;         // [levels][tpl_features][52]: I1 patches + regularity flag (template kernel), level-major
+    unsigned long long tpl_features;  // features per level in `templates` (the batch's capacity)
     int *feat_flag;           // [n_total]: 4*epoch+2 -> warp kernel owns the feature, 4*epoch+1 -> lane<FAMILIES>
     int epoch;                // run counter (>= 1): flags from earlier runs are stale, no memset needed
     int *work_counter;

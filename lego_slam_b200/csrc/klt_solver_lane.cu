@@ -84,7 +84,7 @@ constexpr int kTplStride = 52;                                // floats per (fea
 #define LANE_UNROLL3 0   // measured on B200: 189 instead of 212 instructions per row step, yet 3 % SLOWER (code size)
 #endif
 #ifndef LANE_PREFETCH_Q
-#define LANE_PREFETCH_Q 1
+#define LANE_PREFETCH_Q 0   // measured on B200: no gain (the set-up stalls are not DRAM latency)
 #endif
 #ifndef LANE_T
 #define LANE_T 128
@@ -442,23 +442,31 @@ __device__ __forceinline__ void row10_from_regs(const uint4 &q0, const uint4 &q1
 template <int T>
 __global__ void __launch_bounds__(T)
 klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ SolverArgs args) {
-    const int tid = threadIdx.x;
+    // Output staging: a warp's 32 records (consecutive features of one level: 32 x 208 contiguous bytes in the
+    // level-major layout) are transposed through shared memory and leave as 13 fully coalesced 512-byte stores.
+    // Per-thread 16-byte stores at a 208-byte stride cost as much as all of the kernel's arithmetic (measured:
+    // 316 us -> 154 us without the stores; without the LOADS still 313 us).  Record stride = 13 float4 (odd):
+    // conflict-free both ways.
+    __shared__ float4 stage[T / 32][32 * (kTplStride / 4)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = pyr.levels;
+    // item space padded so that every level starts at a multiple of 32: a warp never straddles two levels
+    const int n_pad = (args.n_total + 31) & ~31;
     const long long item = (long long)blockIdx.x * T + tid;
-    if (item >= (long long)args.n_total * L) return;
-    const int level = L - 1 - (int)(item / args.n_total);
-    const int f = args.f0 + (int)(item % args.n_total);
+    const int level = L - 1 - (int)(item / n_pad);   // (coarse levels first)
+    const int idx = (int)(item % n_pad);
+    const bool valid = level >= 0 && idx < args.n_total;
+    const int f = args.f0 + (valid ? idx : 0);
     const int img = f / args.n_per_pair;
-    const LevelView &lv = pyr.lv[level];
+    const LevelView &lv = pyr.lv[valid ? level : 0];
     const float2 k0 = args.kp1[f];
     const float kx = level_coord(k0.x, L, level), ky = level_coord(k0.y, L, level);
-    float4 *out = reinterpret_cast<float4 *>(args.templates + ((size_t)f * L + level) * kTplStride);
 
     float xx[G], omx[G], yy[G], omy[G];
     int ixn = 0, iyn = 0;
     unsigned mBx, mBy;
     double ex, ey;
-    bool regular = axis_families(kx, mBx, ex) && axis_families(ky, mBy, ey);
+    bool regular = valid && axis_families(kx, mBx, ex) && axis_families(ky, mBy, ey);
     if (regular) {
         // float(kx + c) == (double)kx + c + e_c exactly: the template grid is the d = 0 grid of each family
         regular = (grid_axis<false>((double)kx, 0.0, lv.cols, ixn, xx, omx) |
@@ -494,7 +502,8 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     //   4*epoch + 2 -> exact warp kernel (irregular on some level), 4*epoch + 1 -> lane<FAMILIES> (two
     //   coordinate families on some level), smaller -> the common lane kernel.  A feature is appended to a
     //   list by the thread that raises its flag to that list's value; lane<FAMILIES> re-checks the flag.
-    if (!regular) {
+    if (!valid) {
+    } else if (!regular) {
         const int tag = 4 * args.epoch + 2;
         if (atomicMax(&args.feat_flag[f], tag) < tag) {
             args.defer_list[atomicAdd(args.defer_count, 1)] = f;
@@ -533,8 +542,21 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         }
         buf[kI1Count] = 1.f;  // regularity flag
     }
+    float4 *mine = &stage[warp][lane * (kTplStride / 4)];
 #pragma unroll
-    for (int i = 0; i < kTplStride / 4; ++i) out[i] = make_float4(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]);
+    for (int i = 0; i < kTplStride / 4; ++i) mine[i] = make_float4(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]);
+    __syncwarp();
+    // the warp's first item is feature args.f0 + (idx - lane) of this level; n_warp of its items are valid
+    const int idx0 = idx - lane;
+    const int n_warp = (level >= 0) ? min(32, args.n_total - idx0) : 0;
+    if (n_warp > 0) {
+        float4 *out = reinterpret_cast<float4 *>(args.templates + ((size_t)level * args.tpl_features + (size_t)(args.f0 + idx0)) * kTplStride);
+#pragma unroll
+        for (int k = 0; k < kTplStride / 4; ++k) {
+            const int e = k * 32 + lane;
+            if (e < n_warp * (kTplStride / 4)) out[e] = stage[warp][e];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -620,8 +642,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         // A queued feature is started a few trips from now: pull what its first set-up will load
                         // (its templates, streamed exactly once, and the rows of its top-level window) into L2 now,
                         // with all lanes active, instead of stalling the whole warp on DRAM then.
-                        const char *tp = reinterpret_cast<const char *>(args.templates + (size_t)gid * L * kTplStride);
-                        const int tbytes = L * kTplStride * (int)sizeof(float);
+                        const char *tp = reinterpret_cast<const char *>(args.templates + ((size_t)(L - 1) * args.tpl_features + (size_t)gid) * kTplStride);
+                        const int tbytes = kTplStride * (int)sizeof(float);  // (the top level's record)
                         for (int o = 0; o < tbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + tbytes - 1));
                         const LevelView &tl = pyr.lv[L - 1];
@@ -719,12 +741,12 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 constexpr int kHalf = kWin2Rows / 2;
                 const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
                 if (new_level) {
-                    const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)feat * L + level) * kTplStride);
+                    const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride);
                     float4 t[kTplStride / 4];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
                     if (!LANE_PREFETCH_Q && level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
-                        const char *nxt = reinterpret_cast<const char *>(tp) - kTplStride * sizeof(float);
+                        const char *nxt = reinterpret_cast<const char *>(tp) - args.tpl_features * (kTplStride * sizeof(float));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
                     }
@@ -991,7 +1013,7 @@ size_t lane_scratch_bytes(int sm_count) { return (size_t)sm_count * kLaneMinCtas
 cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
     auto kernel = klt_template_kernel<kTplThreads>;
-    const long long items = (long long)args.n_total * pyr.levels;
+    const long long items = (long long)((args.n_total + 31) & ~31) * pyr.levels;
     const int grid = (int)((items + kTplThreads - 1) / kTplThreads);
     kernel<<<grid, kTplThreads, 0, stream>>>(pyr, args);
     return cudaGetLastError();

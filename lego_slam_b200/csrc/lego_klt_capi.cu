@@ -40,6 +40,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
 constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings)
+constexpr int kMaxSub = 32; // timed sub-ranges of an interleaved run
 constexpr int kMaxChunks = 16;  // chunks of the overlapped end-to-end path (lego_klt_track_batched)
 
 }  // namespace
@@ -69,6 +70,10 @@ struct lego_klt_batch {
     unsigned long long *h_stats = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ring[kRing][3] = {};  // run r: [0] before pyramid, [1] after pyramid, [2] after solver
+    // interleaved runs (pyramid and template launches alternate per sub-range): [2i], [2i+1] bracket the i-th
+    // pyramid launch; created on first use
+    cudaEvent_t ring_sub[kRing][2 * kMaxSub] = {};
+    int ring_nsub[kRing] = {};
     long long runs = 0;
     int *d_work = nullptr;         // per chunk: [0] lane work counter, [1] deferred count, [2] family count,
                                    // [3] lane<FAMILIES> work counter
@@ -237,8 +242,21 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     const WarpKernelMaps *maps = maps_override ? maps_override : b->maps;
     int *work = b->d_work + 4 * chunk;
     CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
-    if (ring) CU_TRY(cudaEventRecord(ring[0], st));
-    if (!view_override) {
+    const int ring_slot = ring ? (int)((ring - &b->ring[0][0]) / 3) : 0;
+    if (ring) {
+        b->ring_nsub[ring_slot] = 0;
+        CU_TRY(cudaEventRecord(ring[0], st));
+    }
+    // LANE path on a large range: pyramids and templates go sub-range by sub-range, so that the template kernel
+    // reads img1 pyramids that are still in L2 (a pyramid pass over all 512 images first evicts them: the
+    // template kernel was bound by DRAM latency x outstanding-miss capacity, profiles/README.md); the solver
+    // then runs once over the whole range (a persistent kernel, it wants many features per thread).
+    static const int sub_pairs = [] {
+        const char *e = getenv("LEGO_KLT_SUBRANGE");  // tuning aid; 0 = off
+        return e ? atoi(e) : 0;  // measured: 16/32/64-pair sub-ranges are 16 % / 6 % / 1 % SLOWER than one pass (launch tails)
+    }();
+    const bool interleave = !view_override && sub_pairs > 0 && nimg >= 2 * sub_pairs;
+    if (!view_override && !interleave) {
         CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));  // (row aprons included)
     }
     if (ring) CU_TRY(cudaEventRecord(ring[1], st));
@@ -270,6 +288,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.fam_list = b->d_fam_list + a.f0;
     a.fam_count = work + 2;
     a.templates = nullptr;
+    a.tpl_features = 0;
     a.scratch = nullptr;
     a.feat_flag = nullptr;
     a.epoch = 0;
@@ -277,6 +296,8 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     if (kernel == LEGO_KLT_KERNEL_AUTO) kernel = lane_kernel_supports(a) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
         return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the 7x7 forward configuration only");
+    if (interleave && !(kernel == LEGO_KLT_KERNEL_LANE && a.n_total > 0))
+        CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
@@ -285,10 +306,32 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         int rc = ensure_lane_buffers(b);
         if (rc) return rc;
         a.templates = b->d_templates;
+        a.tpl_features = (unsigned long long)b->B * (unsigned long long)(b->n_cap > 0 ? b->n_cap : 1);
         a.feat_flag = b->d_feat_flag;
         a.scratch = b->d_scratch;
         a.epoch = (int)((b->runs % 0x0fffffff) + 1);
-        CU_TRY(launch_klt_template(view, a, st));
+        if (interleave && kernel == LEGO_KLT_KERNEL_LANE) {
+            int isub = 0;
+            for (int s0 = 0; s0 < nimg; s0 += sub_pairs, ++isub) {
+                const int ns = std::min(sub_pairs, nimg - s0);
+                cudaEvent_t *se = nullptr;
+                if (ring && isub < kMaxSub) {
+                    se = &b->ring_sub[ring_slot][2 * isub];
+                    for (int i = 0; i < 2; ++i)
+                        if (!se[i]) CU_TRY(cudaEventCreate(&se[i]));
+                    b->ring_nsub[ring_slot] = isub + 1;
+                    CU_TRY(cudaEventRecord(se[0], st));
+                }
+                CU_TRY(launch_pyramid(b->plan, b->view, img0 + s0, ns, st));
+                if (se) CU_TRY(cudaEventRecord(se[1], st));
+                SolverArgs as = a;  // same lists and counters, a sub-range of the features
+                as.f0 = (img0 + s0) * b->n_active;
+                as.n_total = ns * b->n_active;
+                CU_TRY(launch_klt_template(view, as, st));
+            }
+        } else {
+            CU_TRY(launch_klt_template(view, a, st));
+        }
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
         CU_TRY(cudaEventRecord(b->ev_fork, st));
@@ -326,6 +369,21 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     return LEGO_KLT_OK;
 }
 
+// Kernel times of run slot r: pyramid launches (incl. aprons) and everything else (templates + solver).
+cudaError_t run_times(lego_klt_batch *b, int r, float *ms_pyr, float *ms_solver) {
+    float pyr = 0.f, total = 0.f, ms = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&pyr, b->ring[r][0], b->ring[r][1]);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaEventElapsedTime(&total, b->ring[r][0], b->ring[r][2])) != cudaSuccess) return e;
+    for (int i = 0; i < b->ring_nsub[r]; ++i) {
+        if ((e = cudaEventElapsedTime(&ms, b->ring_sub[r][2 * i], b->ring_sub[r][2 * i + 1])) != cudaSuccess) return e;
+        pyr += ms;
+    }
+    *ms_pyr = pyr;
+    *ms_solver = total - pyr;
+    return cudaSuccess;
+}
+
 void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     memset(s, 0, sizeof(*s));
     s->n_features = (uint64_t)b->B * (uint64_t)b->n_active;
@@ -340,9 +398,11 @@ void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev[EV_START], b->ev[EV_H2D]) == cudaSuccess) s->ms_h2d = ms;
     if (b->runs > 0 && !b->last_chunked) {
-        cudaEvent_t *ring = b->ring[(b->runs - 1) % kRing];
-        if (cudaEventElapsedTime(&ms, ring[0], ring[1]) == cudaSuccess) s->ms_pyramid = ms;
-        if (cudaEventElapsedTime(&ms, ring[1], ring[2]) == cudaSuccess) s->ms_solver = ms;
+        float mp = 0.f, msol = 0.f;
+        if (run_times(b, (int)((b->runs - 1) % kRing), &mp, &msol) == cudaSuccess) {
+            s->ms_pyramid = mp;
+            s->ms_solver = msol;
+        }
     } else if (cudaEventElapsedTime(&ms, b->ev[EV_H2D], b->ev[EV_SOLVE]) == cudaSuccess) {
         s->ms_solver = ms;  // chunked run: copies and kernels overlap, only the total is meaningful
     }
@@ -477,9 +537,12 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     pyramid_plan_destroy(&b->plan);
     for (int i = 0; i < EV_COUNT; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
-    for (int r = 0; r < kRing; ++r)
+    for (int r = 0; r < kRing; ++r) {
         for (int i = 0; i < 3; ++i)
             if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
+        for (int i = 0; i < 2 * kMaxSub; ++i)
+            if (b->ring_sub[r][i]) cudaEventDestroy(b->ring_sub[r][i]);
+    }
     cudaFree(b->d_work);
     cudaFree(b->d_defer_list);
     cudaFree(b->d_fam_list);
@@ -560,11 +623,10 @@ int lego_klt_batch_timings(lego_klt_batch *b, int last_n, float *ms_pyramid_avg,
     CU_TRY(cudaStreamSynchronize(b->ctx->stream));
     double sp = 0, ss = 0;
     for (long long r = b->runs - last_n; r < b->runs; ++r) {
-        float ms = 0.f;
-        CU_TRY(cudaEventElapsedTime(&ms, b->ring[r % kRing][0], b->ring[r % kRing][1]));
-        sp += ms;
-        CU_TRY(cudaEventElapsedTime(&ms, b->ring[r % kRing][1], b->ring[r % kRing][2]));
-        ss += ms;
+        float mp = 0.f, msol = 0.f;
+        CU_TRY(run_times(b, (int)(r % kRing), &mp, &msol));
+        sp += mp;
+        ss += msol;
     }
     if (ms_pyramid_avg) *ms_pyramid_avg = (float)(sp / last_n);
     if (ms_solver_avg) *ms_solver_avg = (float)(ss / last_n);
