@@ -179,6 +179,48 @@ int lego_klt_sync(lego_klt_ctx *ctx);
 void *lego_klt_alloc_pinned(size_t bytes);
 void lego_klt_free_pinned(void *p);
 
+/*
+ * ---- Triangulation of tracked features ---------------------------------------------------
+ * legoslam::triangulation (include/legoslam/algorithm.h:11-34), called per feature right after
+ * FindFeaturesInRight by Frontend::TriangulateNewPoints / BuildInitMap (src/frontend_g2o.cpp:111-155, :310-349)
+ * with poses = {camera_left->pose(), camera_right->pose()}.  One GPU thread per feature; same outputs: the world
+ * point (written whatever the verdict, like the reference's out-parameter) and the bool it returns
+ * (finite && S[3]/S[2] < sing_ratio_thr).  The caller's extra gates (y <= 2 m, depth limits) stay with the caller.
+ */
+#define LEGO_TRI_MAX_VIEWS 8
+
+/* Camera (include/legoslam/camera.h:13-24): intrinsics and pose_.matrix3x4(), row-major. */
+typedef struct lego_camera {
+    double fx, fy, cx, cy;
+    double pose34[12];
+} lego_camera;
+
+/*
+ * Generic form: n features seen in the same n_views (2..LEGO_TRI_MAX_VIEWS) views.
+ *   poses34   : n_views x 12, SE3::matrix3x4() row-major                  (std::vector<SE3> poses)
+ *   points_xy : n x n_views x {x, y}: points[i][0], points[i][1]          (VecVec3 points; [2] is not read)
+ *   pt_world  : n x 3 out;  ok : n bytes out (the reference's return value)
+ */
+int lego_klt_triangulate(lego_klt_ctx *ctx, const double *poses34, int n_views, const double *points_xy, int n,
+                     double sing_ratio_thr, double *pt_world, uint8_t *ok);
+
+/*
+ * Stereo form fused with Camera::pixel2camera (src/camera.cpp:21-25, depth 1): pixel keypoints as
+ * lego_klt_track* leaves them.  valid (may be null) = the tracker's success flags: a feature with valid == 0
+ * has no right feature in the reference (src/frontend_g2o.cpp:114-115) and gets ok = 0, point = 0.
+ */
+int lego_klt_triangulate_stereo(lego_klt_ctx *ctx, const lego_camera *left, const lego_camera *right,
+                            const float *kp_left_xy, const float *kp_right_xy, const uint8_t *valid, int n,
+                            double sing_ratio_thr, double *pt_world, uint8_t *ok);
+
+/*
+ * The same on a batch that has been run (lego_klt_batch_run / lego_klt_track_batched): left keypoints, tracked
+ * right keypoints and success flags are taken where they lie in HBM; only the results cross PCIe.
+ *   pt_world : B*n x 3 out;  ok : B*n bytes out
+ */
+int lego_klt_batch_triangulate(lego_klt_batch *b, const lego_camera *left, const lego_camera *right,
+                               double sing_ratio_thr, double *pt_world, uint8_t *ok);
+
 #ifdef __cplusplus
 }
 #endif

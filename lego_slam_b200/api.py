@@ -23,6 +23,19 @@ def make_params(levels=4, patch_lo=-3, patch_hi=3, max_iters=10, inverse=False, 
     return Params(levels, patch_lo, patch_hi, max_iters, int(inverse), int(has_initial), kernel, 0, eps)
 
 
+class Camera(C.Structure):
+    """Mirror of lego_camera (include/lego_klt.h): Camera intrinsics + pose_.matrix3x4() row-major
+    (/root/reference include/legoslam/camera.h:13-24)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("pose34", C.c_double * 12)]
+
+
+def make_camera(fx, fy, cx, cy, pose34) -> Camera:
+    cam = Camera(fx, fy, cx, cy)
+    cam.pose34[:] = [float(v) for v in np.asarray(pose34, np.float64).reshape(12)]
+    return cam
+
+
 def _img_args(img: np.ndarray):
     if img.dtype != np.uint8 or img.ndim != 2 or img.strides[1] != 1:
         raise ValueError("image must be a 2-D uint8 array with unit column stride")
@@ -107,6 +120,34 @@ class Tracker:
             res.append(out[off:off + nb].reshape(lr[l], lc[l]).copy())
             off += nb
         return res
+
+    def triangulation(self, poses34, points_xy, sing_ratio_thr: float = 1e-3):
+        """legoslam::triangulation (include/legoslam/algorithm.h:11-34) for n features seen in the same views.
+        poses34: (n_views, 3, 4); points_xy: (n, n_views, 2).  Returns (pt_world (n,3) float64, ok (n,) uint8)."""
+        poses = np.ascontiguousarray(poses34, np.float64).reshape(-1, 12)
+        pts = np.ascontiguousarray(points_xy, np.float64).reshape(-1, poses.shape[0], 2)
+        n = pts.shape[0]
+        out = np.zeros((max(n, 1), 3), np.float64)
+        ok = np.zeros(max(n, 1), np.uint8)
+        _lib.check(self._lib.lego_klt_triangulate(self._h, poses.ctypes.data, poses.shape[0], pts.ctypes.data, n,
+                                              sing_ratio_thr, out.ctypes.data, ok.ctypes.data), "lego_klt_triangulate")
+        return out[:n], ok[:n]
+
+    def triangulation_stereo(self, cam_left: Camera, cam_right: Camera, kp_left, kp_right, valid=None,
+                             sing_ratio_thr: float = 1e-3):
+        """pixel2camera + triangulation of tracked stereo keypoints (the body of Frontend::TriangulateNewPoints,
+        src/frontend_g2o.cpp:111-155, without the caller's depth gates)."""
+        kl = np.ascontiguousarray(kp_left, np.float32).reshape(-1, 2)
+        kr = np.ascontiguousarray(kp_right, np.float32).reshape(-1, 2)
+        n = kl.shape[0]
+        v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+        out = np.zeros((max(n, 1), 3), np.float64)
+        ok = np.zeros(max(n, 1), np.uint8)
+        _lib.check(self._lib.lego_klt_triangulate_stereo(self._h, C.byref(cam_left), C.byref(cam_right), kl.ctypes.data,
+                                                     kr.ctypes.data, None if v is None else v.ctypes.data, n,
+                                                     sing_ratio_thr, out.ctypes.data, ok.ctypes.data),
+                   "lego_klt_triangulate_stereo")
+        return out[:n], ok[:n]
 
     def debug_read_level(self, level: int, rows: int):
         """Device rows of `level` after build_pyramid, aprons included: (array rows x pitch, apron_left)."""
@@ -204,6 +245,16 @@ class Batch:
         _lib.check(self._lib.lego_klt_batch_download(self._h, kp2_out.ctypes.data, success.ctypes.data,
                                                      C.byref(st)), "lego_klt_batch_download")
         return kp2_out, success, st
+
+    def triangulate(self, cam_left: Camera, cam_right: Camera, sing_ratio_thr: float = 1e-3, out=None, ok=None):
+        """lego_klt_batch_triangulate: world points of the tracked pairs, keypoints taken where they lie in HBM."""
+        nt = self.B * self.n
+        out = np.zeros((self.B, self.n, 3), np.float64) if out is None else out
+        ok = np.zeros((self.B, self.n), np.uint8) if ok is None else ok
+        _lib.check(self._lib.lego_klt_batch_triangulate(self._h, C.byref(cam_left), C.byref(cam_right),
+                                                           sing_ratio_thr, out.ctypes.data, ok.ctypes.data),
+                   "lego_klt_batch_triangulate")
+        return out, ok
 
     def timings(self, last_n: int):
         """(ms_pyramid, ms_solver) averaged over the last `last_n` runs (CUDA events around each launch)."""

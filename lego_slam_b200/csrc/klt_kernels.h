@@ -74,4 +74,14 @@ size_t lane_scratch_bytes(int sm_count);
 cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
 cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
 
+// ---- triangulation (triangulate_sm100.cu) ------------------------------------------------
+constexpr int kTriMaxViews = 8;
+// poses34: host, n_views x 12 (row-major 3x4); points: device, n x n_views x {x, y}; outputs: device n x 3 / n.
+cudaError_t launch_triangulate(const double *poses34, int n_views, const double *d_points, int n, double thr,
+                               double *d_pt_world, uint8_t *d_ok, cudaStream_t stream);
+// cam_*: host {fx, fy, cx, cy}; poses34: host 2 x 12 (left, right); keypoints: device packed float2 (pixels).
+cudaError_t launch_triangulate_stereo(const double *poses34, const double *cam_left, const double *cam_right,
+                                      const float2 *d_kp_left, const float2 *d_kp_right, const uint8_t *d_valid, int n,
+                                      double thr, double *d_pt_world, uint8_t *d_ok, cudaStream_t stream);
+
 }  // namespace legoklt

@@ -83,6 +83,10 @@ constexpr int kTplStride = 52;                                // floats per (fea
 #ifndef LANE_UNROLL3
 #define LANE_UNROLL3 0   // measured on B200: 189 instead of 212 instructions per row step, yet 3 % SLOWER (code size)
 #endif
+#ifndef LANE_ASYNC_SETUP
+#define LANE_ASYNC_SETUP 0  // level set-up by cp.async straight into shared memory, overlapped with the grid set-up:
+                            // measured on B200, identical time (1.740 ms both) at 10 more registers -> off
+#endif
 #ifndef LANE_PREFETCH_Q
 #define LANE_PREFETCH_Q 0   // measured on B200: no gain (the set-up stalls are not DRAM latency)
 #endif
@@ -740,6 +744,38 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 // holding all 41 loads in flight needs ~250 registers and did not pay (profiles/README.md).
                 constexpr int kHalf = kWin2Rows / 2;
                 const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
+#if LANE_ASYNC_SETUP
+                // All copies of the set-up (49 template floats, 72 window words) go global -> shared memory by
+                // cp.async, 4 bytes each because a thread's words are interleaved with its neighbours'; they are in
+                // flight together and land while the grid coordinates of the pass are computed (waited for just
+                // before the pass).  The register-staged version made three dependent round trips per set-up
+                // (template, two window halves) with the whole warp stalled on each: a third of all stall samples.
+                if (new_level) {
+                    const float *tp = args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride;
+                    if (level > 0) {  // the next level's template will be needed a few trips from now
+                        const char *nxt = reinterpret_cast<const char *>(tp) - args.tpl_features * (kTplStride * sizeof(float));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
+                    }
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.i1[0][tid]);
+#pragma unroll
+                    for (int i = 0; i < kI1Count; ++i)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * WS * 4), "l"(tp + i) : "memory");
+                }
+                if (!no_window) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.win2[0][tid]);
+#pragma unroll
+                    for (int i = 0; i < kWin2Rows; ++i) {
+                        const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+                        const uint8_t *rp = img2 + (ptrdiff_t)ry * lv.pitch + wx0;
+#pragma unroll
+                        for (int w = 0; w < kWin2Words; ++w)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (i * kWin2Words + w) * WS * 4), "l"(rp + 4 * w)
+                                         : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+#else
                 if (new_level) {
                     const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride);
                     float4 t[kTplStride / 4];
@@ -766,6 +802,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     window_load<kHalf>(img2, lv, wx0, wy0 + kHalf, wv);
                     window_store<kHalf, WS>(wv, &sm.win2[kHalf * kWin2Words][tid]);
                 }
+#endif
                 need_win = false;
                 state = ST_RUN;
             }
@@ -820,6 +857,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         }
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
+#if LANE_ASYNC_SETUP
+        asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's set-up copies (each thread reads only its own words)
+#endif
         const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & 0x7f7fu) != 0u);
         if (run) {
             const LevelView &lv = pyr.lv[level];

@@ -53,6 +53,8 @@ struct lego_klt_ctx {
     lego_klt_batch *single = nullptr;  // cached B=1 batch behind lego_klt_track / build_pyramid
     uint8_t *pinned = nullptr;         // staging for the single-pair path
     size_t pinned_bytes = 0;
+    uint8_t *d_tri = nullptr;          // triangulation scratch (grow-only)
+    size_t tri_bytes = 0;
 };
 
 struct lego_klt_batch {
@@ -492,6 +494,7 @@ void lego_klt_destroy(lego_klt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->single) lego_klt_batch_destroy(ctx->single);
+    if (ctx->d_tri) cudaFree(ctx->d_tri);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -928,6 +931,93 @@ int lego_klt_debug_read_level(lego_klt_ctx *ctx, int level, uint8_t *out, size_t
     if (pitch) *pitch = lv.pitch;
     if (apron_left) *apron_left = kApronL;
     return LEGO_KLT_OK;
+}
+
+// ---- triangulation ---------------------------------------------------------------------------------------
+static int ensure_tri(lego_klt_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->tri_bytes) return LEGO_KLT_OK;
+    if (ctx->d_tri) cudaFree(ctx->d_tri);
+    ctx->d_tri = nullptr;
+    ctx->tri_bytes = 0;
+    CU_TRY(cudaMalloc(&ctx->d_tri, bytes));
+    ctx->tri_bytes = bytes;
+    return LEGO_KLT_OK;
+}
+
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int lego_klt_triangulate(lego_klt_ctx *ctx, const double *poses34, int n_views, const double *points_xy, int n,
+                     double sing_ratio_thr, double *pt_world, uint8_t *ok) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    if (!poses34 || n_views < 2 || n_views > kTriMaxViews) return fail(LEGO_KLT_ERR_BAD_ARG, "n_views must be in [2, %d]", kTriMaxViews);
+    if (n < 0 || (n > 0 && (!points_xy || !pt_world || !ok))) return fail(LEGO_KLT_ERR_BAD_ARG, "bad point arguments");
+    if (n == 0) return LEGO_KLT_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t in_b = up256((size_t)n * n_views * 2 * sizeof(double)), out_b = up256((size_t)n * 3 * sizeof(double));
+    int rc = ensure_tri(ctx, in_b + out_b + up256((size_t)n));
+    if (rc) return rc;
+    double *d_in = reinterpret_cast<double *>(ctx->d_tri), *d_out = reinterpret_cast<double *>(ctx->d_tri + in_b);
+    uint8_t *d_ok = ctx->d_tri + in_b + out_b;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemcpyAsync(d_in, points_xy, (size_t)n * n_views * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(launch_triangulate(poses34, n_views, d_in, n, sing_ratio_thr, d_out, d_ok, st));
+    CU_TRY(cudaMemcpyAsync(pt_world, d_out, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(ok, d_ok, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return LEGO_KLT_OK;
+}
+
+static int tri_stereo_device(lego_klt_ctx *ctx, const lego_camera *left, const lego_camera *right, const float2 *d_kl,
+                             const float2 *d_kr, const uint8_t *d_valid, int n, double thr, size_t scratch_off,
+                             double *pt_world, uint8_t *ok) {
+    const size_t out_b = up256((size_t)n * 3 * sizeof(double));
+    double *d_out = reinterpret_cast<double *>(ctx->d_tri + scratch_off);
+    uint8_t *d_ok = ctx->d_tri + scratch_off + out_b;
+    double poses[24];
+    memcpy(poses, left->pose34, sizeof(double) * 12);
+    memcpy(poses + 12, right->pose34, sizeof(double) * 12);
+    const double cl[4] = {left->fx, left->fy, left->cx, left->cy}, cr[4] = {right->fx, right->fy, right->cx, right->cy};
+    cudaStream_t st = ctx->stream;
+    CU_TRY(launch_triangulate_stereo(poses, cl, cr, d_kl, d_kr, d_valid, n, thr, d_out, d_ok, st));
+    CU_TRY(cudaMemcpyAsync(pt_world, d_out, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(ok, d_ok, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_triangulate_stereo(lego_klt_ctx *ctx, const lego_camera *left, const lego_camera *right,
+                            const float *kp_left_xy, const float *kp_right_xy, const uint8_t *valid, int n,
+                            double sing_ratio_thr, double *pt_world, uint8_t *ok) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    if (!left || !right) return fail(LEGO_KLT_ERR_BAD_ARG, "camera is null");
+    if (n < 0 || (n > 0 && (!kp_left_xy || !kp_right_xy || !pt_world || !ok))) return fail(LEGO_KLT_ERR_BAD_ARG, "bad point arguments");
+    if (n == 0) return LEGO_KLT_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t kp_b = up256((size_t)n * sizeof(float2)), v_b = up256((size_t)n);
+    int rc = ensure_tri(ctx, 2 * kp_b + v_b + up256((size_t)n * 3 * sizeof(double)) + up256((size_t)n));
+    if (rc) return rc;
+    float2 *d_kl = reinterpret_cast<float2 *>(ctx->d_tri), *d_kr = reinterpret_cast<float2 *>(ctx->d_tri + kp_b);
+    uint8_t *d_valid = valid ? ctx->d_tri + 2 * kp_b : nullptr;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemcpyAsync(d_kl, kp_left_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_kr, kp_right_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    if (valid) CU_TRY(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, st));
+    return tri_stereo_device(ctx, left, right, d_kl, d_kr, d_valid, n, sing_ratio_thr, 2 * kp_b + v_b, pt_world, ok);
+}
+
+int lego_klt_batch_triangulate(lego_klt_batch *b, const lego_camera *left, const lego_camera *right,
+                               double sing_ratio_thr, double *pt_world, uint8_t *ok) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (!left || !right) return fail(LEGO_KLT_ERR_BAD_ARG, "camera is null");
+    if (!b->ran) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_triangulate before lego_klt_batch_run");
+    const size_t nt = (size_t)b->B * (size_t)b->n_active;
+    if (nt == 0) return LEGO_KLT_OK;
+    if (!pt_world || !ok) return fail(LEGO_KLT_ERR_BAD_ARG, "output pointer is null");
+    lego_klt_ctx *ctx = b->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_tri(ctx, up256(nt * 3 * sizeof(double)) + up256(nt));
+    if (rc) return rc;
+    return tri_stereo_device(ctx, left, right, b->d_kp1, b->d_kp2_out, b->d_success, (int)nt, sing_ratio_thr, 0, pt_world, ok);
 }
 
 }  // extern "C"
