@@ -142,6 +142,21 @@ int lego_klt_image_create(lego_klt_ctx *ctx, int cols, int rows, size_t step, in
 void lego_klt_image_destroy(lego_klt_image *img);
 /* H2D + pyramid + aprons (asynchronous on the context stream; `data` is copied before returning). */
 int lego_klt_image_upload(lego_klt_image *img, const uint8_t *data);
+/*
+ * Image ingest: Dataset::NextFrame halves every frame before the frontend sees it,
+ *     cv::resize(image, resized, cv::Size(), 0.5, 0.5, cv::INTER_NEAREST)          src/dataset.cpp:75-77
+ * (OpenCV, third party: dsize = cvRound(size * 0.5), pixel (x, y) = source (min(2x, cols-1), min(2y, rows-1))).
+ * Uploads the FULL-resolution frame and halves it on the device into the handle's level 0, then builds the
+ * pyramid.  The handle must have been created with cols/rows = lego_klt_half_size() of the frame and step == cols
+ * (cv::resize outputs are continuous).
+ */
+int lego_klt_image_upload_fullres(lego_klt_image *img, const uint8_t *full, int full_cols, int full_rows,
+                                  size_t full_step);
+/* cvRound(v * 0.5): the size cv::resize(..., Size(), 0.5, 0.5) gives an axis of v pixels. */
+int lego_klt_half_size(int v);
+/* The same halving, host to host (out: tightly packed half_rows x half_cols), for callers and tests. */
+int lego_klt_downscale_half(lego_klt_ctx *ctx, const uint8_t *full, int full_cols, int full_rows, size_t full_step,
+                            uint8_t *out, size_t out_capacity);
 int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, const lego_klt_image *img1,
                           const lego_klt_image *img2, const float *kp1_xy, float *kp2_xy, uint8_t *success, int n,
                           lego_klt_stats *stats_or_null);

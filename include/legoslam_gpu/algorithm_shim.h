@@ -3,6 +3,7 @@
 // Same names, same signatures, same argument meaning as
 //   /root/reference include/legoslam/algorithm.h:123-128   legoslam::LKOpticalFlow1Layer
 //   /root/reference include/legoslam/algorithm.h:131-136   legoslam::LKOpticalFlow4Layer
+//   /root/reference include/legoslam/algorithm.h:11-34     legoslam::triangulation   
 // so the two call sites (src/frontend_g2o.cpp:473, :515; identical in src/frontend_lego.cpp:486,528)
 // compile unchanged when this header is included instead of the reference's definitions:
 //
@@ -100,6 +101,37 @@ void LKOpticalFlow4Layer(const MatT &img1, const MatT &img2, const std::vector<K
                          std::vector<KeyPointT> &kp2, std::vector<bool> &success, bool inverse = false,
                          bool has_initial = true) {
     gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 4);  // :135 pyramids = 4
+}
+
+// ---- legoslam::triangulation (include/legoslam/algorithm.h:11-34) ------------------------------------
+// Same name, arguments and return value.  SE3T needs matrix3x4() whose result is indexable as m(r, c)
+// (Sophus::SE3d), Vec3T needs operator[] (Eigen::Vector3d): with the reference's typedefs this IS
+//     bool triangulation(const std::vector<SE3> &poses, const VecVec3 &points, Vec3 &pt_world, double thr = 1e-3)
+// and Frontend::TriangulateNewPoints / BuildInitMap (src/frontend_g2o.cpp:111-155, :310-349) compile unchanged.
+// One feature per call costs a launch and two small copies; a frontend that keeps its keypoints on the GPU
+// calls lego_klt_batch_triangulate / lego_klt_triangulate_stereo once per frame instead.
+template <class SE3T, class Vec3T, class Alloc>
+bool triangulation(const std::vector<SE3T> &poses, const std::vector<Vec3T, Alloc> &points, Vec3T &pt_world,
+                   double singRatioThr = 1e-3) {
+    const size_t nv = poses.size();
+    if (nv < 2 || nv > LEGO_TRI_MAX_VIEWS || points.size() < nv)
+        throw std::runtime_error("triangulation: 2..8 views with one point each are supported");
+    std::vector<double> m(12 * nv), xy(2 * nv);
+    for (size_t i = 0; i < nv; ++i) {
+        const auto mat = poses[i].matrix3x4();
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c) m[12 * i + 4 * r + c] = mat(r, c);
+        xy[2 * i] = points[i][0];
+        xy[2 * i + 1] = points[i][1];
+    }
+    double out[3];
+    uint8_t ok = 0;
+    int rc = lego_klt_triangulate(gpu::thread_context(), m.data(), (int)nv, xy.data(), 1, singRatioThr, out, &ok);
+    if (rc != LEGO_KLT_OK) throw std::runtime_error(std::string("lego_klt_triangulate: ") + lego_klt_last_error());
+    pt_world[0] = out[0];  // written whatever the verdict, like the reference's out-parameter (:24)
+    pt_world[1] = out[1];
+    pt_world[2] = out[2];
+    return ok != 0;
 }
 
 #ifdef OPENCV_CORE_HPP  // OpenCV present: exact reference signatures (include/legoslam/algorithm.h:123-136)

@@ -15,7 +15,8 @@ MAX_LEVELS = 8
 EXPORTS = [
     "lego_klt_abi_version", "lego_klt_last_error", "lego_klt_default_params", "lego_klt_device_count",
     "lego_klt_create", "lego_klt_destroy", "lego_klt_set_stream", "lego_klt_track",
-    "lego_klt_build_pyramid", "lego_klt_debug_read_level", "lego_klt_triangulate", "lego_klt_triangulate_stereo",
+    "lego_klt_build_pyramid", "lego_klt_debug_read_level", "lego_klt_image_upload_fullres", "lego_klt_half_size",
+    "lego_klt_downscale_half", "lego_klt_triangulate", "lego_klt_triangulate_stereo",
     "lego_klt_batch_triangulate", "lego_klt_batch_create", "lego_klt_batch_destroy", "lego_klt_batch_upload",
     "lego_klt_batch_run", "lego_klt_batch_download", "lego_klt_batch_timings", "lego_klt_track_batched",
     "lego_klt_batch_device_ptrs", "lego_klt_sync", "lego_klt_alloc_pinned", "lego_klt_free_pinned",
@@ -77,6 +78,9 @@ def load():
     lib.lego_klt_triangulate.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_double, vp, vp]
     lib.lego_klt_triangulate_stereo.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_double, vp, vp]
     lib.lego_klt_batch_triangulate.argtypes = [vp, vp, vp, C.c_double, vp, vp]
+    lib.lego_klt_image_upload_fullres.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t]
+    lib.lego_klt_half_size.argtypes = [C.c_int]
+    lib.lego_klt_downscale_half.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t]
     lib.lego_klt_debug_read_level.argtypes = [vp, C.c_int, vp, C.c_size_t, ip, ip]
     lib.lego_klt_batch_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
                                           C.POINTER(vp)]

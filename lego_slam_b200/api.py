@@ -149,6 +149,15 @@ class Tracker:
                    "lego_klt_triangulate_stereo")
         return out[:n], ok[:n]
 
+    def downscale_half(self, full: np.ndarray) -> np.ndarray:
+        """cv::resize(full, out, cv::Size(), 0.5, 0.5, cv::INTER_NEAREST) of Dataset::NextFrame (src/dataset.cpp:75-77)."""
+        rows, cols, step = _img_args(full)
+        hr, hc = self._lib.lego_klt_half_size(rows), self._lib.lego_klt_half_size(cols)
+        out = np.zeros((hr, hc), np.uint8)
+        _lib.check(self._lib.lego_klt_downscale_half(self._h, full.ctypes.data, cols, rows, step, out.ctypes.data,
+                                                     out.size), "lego_klt_downscale_half")
+        return out
+
     def debug_read_level(self, level: int, rows: int):
         """Device rows of `level` after build_pyramid, aprons included: (array rows x pitch, apron_left)."""
         cap = rows * 8192
@@ -195,6 +204,13 @@ class Image:
         if _img_args(img) != (self.rows, self.cols, self.step):
             raise ValueError("image shape/step does not match the handle")
         _lib.check(self._lib.lego_klt_image_upload(self._h, img.ctypes.data), "lego_klt_image_upload")
+        return self
+
+    def upload_fullres(self, full: np.ndarray):
+        """Dataset::NextFrame's 0.5x INTER_NEAREST halving (src/dataset.cpp:75-77) on the device, then the pyramid."""
+        rows, cols, step = _img_args(full)
+        _lib.check(self._lib.lego_klt_image_upload_fullres(self._h, full.ctypes.data, cols, rows, step),
+                   "lego_klt_image_upload_fullres")
         return self
 
     def close(self):

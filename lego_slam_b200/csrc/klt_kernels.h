@@ -53,6 +53,10 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int 
 // 4-byte aligned `tight`, buffer padded by >= 8 bytes) of images [img0, img0+n_images) into the device layout.
 cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int img0, int n_images,
                           cudaStream_t stream);
+// 0.5x INTER_NEAREST downscale of a tight full-resolution frame (device) into level 0 of a single device image
+// (Dataset::NextFrame, src/dataset.cpp:75-77).
+cudaError_t launch_half_nearest(const uint8_t *full, int full_cols, int full_rows, size_t full_step, const LevelView &l0,
+                                cudaStream_t stream);
 // Row aprons alone (single-level configurations; launch_pyramid calls it when there is no level to build).
 cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream_t stream, int n_sets = 2);
 

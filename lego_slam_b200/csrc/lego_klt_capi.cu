@@ -3,6 +3,7 @@
 //
 // Reference boundary replaced: legoslam::LKOpticalFlow4Layer / LKOpticalFlow1Layer
 // (include/legoslam/algorithm.h:123-136), called at src/frontend_g2o.cpp:473 and :515.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -102,6 +103,8 @@ struct lego_klt_image {
     WarpKernelMaps *maps = nullptr;  // TMA descriptors for the role "img2"
     uint8_t *d_levels = nullptr;
     uint8_t *d_tight = nullptr;
+    uint8_t *d_full = nullptr;     // landing buffer of lego_klt_image_upload_fullres (grow-only)
+    size_t full_bytes = 0;
     bool valid = false;
 };
 
@@ -817,6 +820,7 @@ void lego_klt_image_destroy(lego_klt_image *im) {
     pyramid_plan_destroy(&im->plan);
     cudaFree(im->d_levels);
     cudaFree(im->d_tight);
+    cudaFree(im->d_full);
     cudaGetLastError();
     delete im;
 }
@@ -838,6 +842,60 @@ int lego_klt_image_upload(lego_klt_image *im, const uint8_t *data) {
     CU_TRY(launch_pyramid(im->plan, im->view, 0, 1, st, 1));
     im->valid = true;
     return LEGO_KLT_OK;
+}
+
+int lego_klt_half_size(int v) { return (int)lrint((double)v * 0.5); }  // cvRound: round half to even
+
+int lego_klt_image_upload_fullres(lego_klt_image *im, const uint8_t *full, int full_cols, int full_rows,
+                                  size_t full_step) {
+    if (!im || !full) return fail(LEGO_KLT_ERR_BAD_ARG, "null image/data");
+    if (full_cols <= 0 || full_rows <= 0 || full_step < (size_t)full_cols) return fail(LEGO_KLT_ERR_BAD_ARG, "bad frame shape");
+    if (im->cols != lego_klt_half_size(full_cols) || im->rows != lego_klt_half_size(full_rows) || im->step != (size_t)im->cols)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "handle is %dx%d step %zu; a %dx%d frame halves to %dx%d (continuous)", im->cols,
+                    im->rows, im->step, full_cols, full_rows, lego_klt_half_size(full_cols), lego_klt_half_size(full_rows));
+    lego_klt_ctx *ctx = im->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)(full_rows - 1) * full_step + (size_t)full_cols;  // what a cv::Mat guarantees
+    int rc = ensure_pinned(ctx, bytes);
+    if (rc) return rc;
+    if (bytes > im->full_bytes) {
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        if (im->d_full) cudaFree(im->d_full);
+        im->d_full = nullptr;
+        im->full_bytes = 0;
+        CU_TRY(cudaMalloc(&im->d_full, bytes));
+        im->full_bytes = bytes;
+    }
+    CU_TRY(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
+    memcpy(ctx->pinned, full, bytes);
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemcpyAsync(im->d_full, ctx->pinned, bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(launch_half_nearest(im->d_full, full_cols, full_rows, full_step, im->view.lv[0], st));
+    CU_TRY(launch_pyramid(im->plan, im->view, 0, 1, st, 1));
+    im->valid = true;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_downscale_half(lego_klt_ctx *ctx, const uint8_t *full, int full_cols, int full_rows, size_t full_step,
+                            uint8_t *out, size_t out_capacity) {
+    if (!ctx || !full || !out) return fail(LEGO_KLT_ERR_BAD_ARG, "null argument");
+    const int hc = lego_klt_half_size(full_cols), hr = lego_klt_half_size(full_rows);
+    if (full_cols <= 0 || full_rows <= 0 || hc <= 0 || hr <= 0 || full_step < (size_t)full_cols)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "bad frame shape");
+    if ((size_t)hc * hr > out_capacity) return fail(LEGO_KLT_ERR_BAD_ARG, "output buffer too small");
+    lego_klt_image *im = nullptr;
+    int rc = lego_klt_image_create(ctx, hc, hr, (size_t)hc, 1, &im);
+    if (rc) return rc;
+    rc = lego_klt_image_upload_fullres(im, full, full_cols, full_rows, full_step);
+    if (rc == LEGO_KLT_OK) {
+        const LevelView &lv = im->view.lv[0];
+        cudaError_t e = cudaMemcpy2DAsync(out, (size_t)hc, lv.base[0], (size_t)lv.pitch, (size_t)hc, (size_t)hr,
+                                          cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(LEGO_KLT_ERR_CUDA, "downscale read-back: %s", cudaGetErrorString(e));
+    }
+    lego_klt_image_destroy(im);
+    return rc;
 }
 
 int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, const lego_klt_image *img1,

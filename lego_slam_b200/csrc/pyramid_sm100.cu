@@ -492,7 +492,37 @@ ingest_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst_base, i
     }
 }
 
+// Dataset::NextFrame's cv::resize(img, out, cv::Size(), 0.5, 0.5, cv::INTER_NEAREST) (src/dataset.cpp:75-77; OpenCV
+// is third party: dsize = cvRound(size * 0.5), source index = min(floor(d * 2), size - 1); pinned against
+// Python cv2 by tests): full-resolution tight rows -> the pitched level 0 of a device image.  One thread per 4
+// output pixels.
+__global__ void __launch_bounds__(256)
+half_nearest_kernel(const uint8_t *__restrict__ src, int scols, int srows, size_t sstep, uint8_t *__restrict__ dst,
+                    int dcols, int drows, int dpitch) {
+    const int groups = (dcols + 3) >> 2;
+    const long long total = (long long)groups * drows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / groups), g = (int)(i - (long long)y * groups);
+        const uint8_t *srow = src + (size_t)min(2 * y, srows - 1) * sstep;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = 4 * g + j;
+            if (x < dcols) packed |= (uint32_t)__ldg(srow + min(2 * x, scols - 1)) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(dst + (size_t)y * dpitch + 4 * g) = packed;  // (spill-over lands in the row's apron)
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_half_nearest(const uint8_t *full, int full_cols, int full_rows, size_t full_step, const LevelView &l0,
+                                cudaStream_t stream) {
+    const long long total = (long long)((l0.cols + 3) / 4) * l0.rows;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    half_nearest_kernel<<<grid, 256, 0, stream>>>(full, full_cols, full_rows, full_step, l0.base[0], l0.cols, l0.rows, l0.pitch);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, int img0, int n_images,
                           cudaStream_t stream) {  // (single-image handles pass set = 0)

@@ -19,7 +19,52 @@ struct KeyPoint {
 struct Mat { unsigned char *data; int cols, rows; size_t step; };
 }  // namespace fakecv
 
+// look-alikes of Sophus::SE3d / Eigen::Vector3d, as far as legoslam::triangulation touches them
+namespace fakeeigen {
+struct Mat34 {
+    double v[3][4];
+    double operator()(int r, int c) const { return v[r][c]; }
+};
+struct SE3 {
+    Mat34 m;
+    Mat34 matrix3x4() const { return m; }
+};
+struct Vec3 {
+    double v[3];
+    double &operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+};
+}  // namespace fakeeigen
+
+// /root/reference test/legoslam_test_triangulation.cpp:5-23 through the shim's legoslam::triangulation
+static int triangulation_kat() {
+    using namespace fakeeigen;
+    const double pw[3] = {30, 20, 10};
+    const double ty[3] = {0, -10, 10};
+    std::vector<SE3> poses(3);
+    std::vector<Vec3> points(3);
+    for (int i = 0; i < 3; ++i) {
+        // Eigen::Quaterniond(0, 0, 0, 1): w = 0, z = 1 -> rotation by pi about z = diag(-1, -1, 1)
+        const double R[3][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, 1}}, t[3] = {0, ty[i], 0};
+        double pc[3];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) poses[i].m.v[r][c] = R[r][c];
+            poses[i].m.v[r][3] = t[r];
+            pc[r] = R[r][0] * pw[0] + R[r][1] * pw[1] + R[r][2] * pw[2] + t[r];
+        }
+        points[i] = Vec3{{pc[0] / pc[2], pc[1] / pc[2], 1.0}};
+    }
+    Vec3 est{{0, 0, 0}};
+    const bool ok = legoslam::triangulation(poses, points, est);
+    std::printf("shim: triangulation -> %d (%.6f %.6f %.6f)\n", (int)ok, est[0], est[1], est[2]);
+    if (!ok) return 5;                                                     // EXPECT_TRUE
+    for (int k = 0; k < 3; ++k)
+        if (std::fabs(est[k] - pw[k]) > 0.01) return 6;                    // EXPECT_NEAR(..., 0.01)
+    return 0;
+}
+
 int main() {
+    if (int rc = triangulation_kat()) return rc;
     const int cols = 620, rows = 188;
     std::vector<unsigned char> left((size_t)cols * rows), right((size_t)cols * rows);
     // smooth pseudo-random texture; right = left shifted by 6 px

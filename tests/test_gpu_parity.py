@@ -321,3 +321,36 @@ def test_bad_arguments_are_rejected(tracker):
         tracker.track(img, img, kp, kp, klt.make_params(levels=7))  # level would be empty
     with pytest.raises(_lib.KltError):
         tracker.track(img, img, kp, kp, klt.make_params(levels=1, patch_lo=-8, patch_hi=8))
+
+
+# ------------------------------------------------------------------ image ingest
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,cols,pad", [(376, 1241, 0), (375, 1242, 0), (751, 2483, 13), (3, 5, 0), (1080, 1920, 0)])
+def test_ingest_half_nearest_equals_cv2(tracker, rows, cols, pad):
+    """Dataset::NextFrame: cv::resize(img, out, cv::Size(), 0.5, 0.5, cv::INTER_NEAREST) (src/dataset.cpp:75-77).
+    OpenCV is third party; the pin is Python cv2 in this image (same call)."""
+    cv2 = pytest.importorskip("cv2")
+    big = np.random.default_rng(rows * 7 + cols).integers(0, 256, size=(rows, cols + pad), dtype=np.uint8)
+    full = big[:, :cols]
+    ref = cv2.resize(np.ascontiguousarray(full), None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
+    got = tracker.downscale_half(full)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_fullres_upload_tracks_like_the_halved_images(tracker, oracle):
+    """Frame ingest + sequence mode: handles fed with full-resolution frames give the same bytes as tracking the
+    host-halved images (and hence the oracle)."""
+    cv2 = pytest.importorskip("cv2")
+    L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, 300, seed=77)
+    halve = lambda a: cv2.resize(a, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
+    l2, r2 = halve(L), halve(R)
+    k1 = (kp1 * 0.5).astype(np.float32)
+    k1 = k1[(k1[:, 0] > 8) & (k1[:, 0] < l2.shape[1] - 8) & (k1[:, 1] > 8) & (k1[:, 1] < l2.shape[0] - 8)]
+    a = tracker.image(l2.shape[0], l2.shape[1]).upload_fullres(L)
+    b = tracker.image(l2.shape[0], l2.shape[1]).upload_fullres(R)
+    out, succ, st = tracker.track_images(a, b, k1, k1)
+    ref, rs, _ = oracle.track(l2, r2, k1, k1)
+    assert_parity(out, succ, ref, rs, l2.shape[1], l2.shape[0], "fullres ingest")
+    out2, succ2, _ = tracker.track(l2, r2, k1, k1)
+    assert np.array_equal(out.view(np.uint32), out2.view(np.uint32)) and np.array_equal(succ, succ2)
