@@ -184,6 +184,58 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(cuda_index: int):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are
+    allocated (first touch puts them on that node).  With 8 ranks the end-to-end path is bound by host memory /
+    PCIe root complexes; remote pinned buffers halve it.  Returns a short description (or the reason it did not)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:       # "00000000:1b:00.0" -> sysfs uses a 4-digit domain
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no local cpus in the affinity mask"
+        os.sched_setaffinity(0, cpus)
+        node = open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip()
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({e!r})"
+
+
+_TRAFFIC = None
+
+
+def traffic(kernel: str, args):
+    """DRAM bytes per launch of `kernel` (ncu dram__bytes_read.sum + dram__bytes_write.sum) at the default
+    configuration, from profiles/r01_traffic.json; None for any other configuration or if never captured."""
+    global _TRAFFIC
+    if (args.pairs, args.features, args.kernel, bool(args.subpixel)) != (256, 2000, 0, False):
+        return None
+    if _TRAFFIC is None:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                _TRAFFIC = json.load(f)
+        except Exception:
+            _TRAFFIC = {}
+    v = _TRAFFIC.get(kernel)
+    return int(v) if v else None
+
+
 def workload_config(args):
     return {"workload": f"C3: {args.pairs} independent stereo pairs {COLS}x{ROWS} u8 per GPU x {args.features} "
                         f"features, {LEVELS}-level pyramid, 7x7 patch (reference half_patch_size=3), forward, kp2=kp1",
@@ -216,6 +268,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     B, n = args.pairs, args.features
     base = make_workload(B, n, args.distinct, 1000 + rank * B)
     imgs1, imgs2, kp1, kp2 = fill_batch(base, B, n, klt.pinned_empty)
@@ -276,18 +329,42 @@ def run_ours(args):
     defer_reason = [int(v) for v in st.defer_reason]
 
     # ---------------- end to end: host buffers -> lego_klt_track_batched -> host buffers ----------------
+    # kp2 is in/out (initial guess in, tracked position out): every timed step gets its own pre-filled pinned
+    # buffer, so that no host-side refill of the guess sits inside the timed region.
+    n_ring = args.steps if args.steps <= 32 else 1
+    kp2_ring = [kp2_io] + [klt.pinned_empty((B, n, 2), np.float32) for _ in range(n_ring - 1)]
     for _ in range(min(args.warmup, 3)):
         np.copyto(kp2_io, kp2)
         batch.track(imgs1, imgs2, kp1, kp2_io, succ, params)
+    for buf in kp2_ring:
+        np.copyto(buf, kp2)
     barrier()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        np.copyto(kp2_io, kp2)
-        batch.track(imgs1, imgs2, kp1, kp2_io, succ, params)
+    e0.record(stream)
+    for i in range(args.steps):
+        if n_ring == 1:
+            np.copyto(kp2_io, kp2)
+        batch.track(imgs1, imgs2, kp1, kp2_ring[i % n_ring], succ, params)   # synchronous: returns after the D2H
+    e1.record(stream)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_wall_s = time.perf_counter() - t0
+    e2e_s = e0.elapsed_time(e1) * 1e-3     # device clock on the library's stream; the call blocks, so wall == device
     barrier()
+
+    # ---------------- next step of the frontend on the tracked batch: triangulation ----------------
+    left34 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    right34 = np.hstack([np.eye(3), np.array([[-0.537], [0.0], [0.0]])])
+    cam_l = klt.make_camera(718.856, 718.856, 607.1928, 185.2157, left34)
+    cam_r = klt.make_camera(718.856, 718.856, 607.1928, 185.2157, right34)
+    tri_pt = klt.pinned_empty((B, n, 3), np.float64)
+    tri_ok = klt.pinned_empty((B, n), np.uint8)
+    batch.triangulate(cam_l, cam_r, 1e-3, tri_pt, tri_ok)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        batch.triangulate(cam_l, cam_r, 1e-3, tri_pt, tri_ok)
+    tri_ms = (time.perf_counter() - t0) / 3 * 1e3
 
     # max over ranks of the timed regions
     t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
@@ -341,23 +418,32 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(imgs1.nbytes + imgs2.nbytes + kp1.nbytes + kp2.nbytes),
                 "d2h_bytes_per_step": int(kp2_io.nbytes + succ.nbytes + 12 * 8),
                 "ms_per_step": e2e_ms / args.steps, "api": "lego_klt_track_batched (pinned host buffers)"},
-        "gpu_launches": (3 if args.kernel in (0, 3) else 2) * args.steps,
-        "roofline": {"kernel": "klt_lane_kernel + klt_warp_kernel on deferred features (fused 4-level GN solver)"
+        # kernels of this library launched inside the device-resident timed region, per step: pyramid_l01_kernel,
+        # pyramid_band_kernel, then klt_template_kernel + klt_warp_kernel (deferred features) + klt_lane_kernel x2
+        # (LANE path) or one solver kernel
+        "gpu_launches": (6 if args.kernel in (0, 3) else 3) * args.steps,
+        "roofline": {"kernel": "klt_template_kernel + klt_lane_kernel (+ klt_warp_kernel on deferred features): fused 4-level GN solver"
                      if args.kernel in (0, 3) else "klt_warp_kernel (fused 4-level GN solver)", "bound": "fp32-issue (non-tensor)",
                      "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved_tflops / fp32_peak_tflops,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of klt_lane_kernel, one `ncu --set full` capture at this
-                     # exact configuration (profiles/r01_ncu_final_all_kernels.csv); null for any other configuration
-                     "traffic": 655_785_728 if (B, n, args.kernel, args.subpixel) == (256, 2000, 0, False) else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture at this
+                     # exact configuration (profiles/r01_traffic.json, written by tools/summarise_ncu.py); null otherwise
+                     "traffic": traffic("klt_lane_kernel", args),
+                     "traffic_template_kernel": traffic("klt_template_kernel", args),
                      "peak_source": f"computed: {sm_count} SMs x 128 lanes x {sm_max_mhz:.0f} MHz un-fused fp32 "
                                     "(not in MEASURED_PEAKS.json, which has only HBM and bf16 tensor peaks)",
                      "algorithmic_flop_per_launch": algo_flop, "gn_iters_per_level": iters,
                      "ms_per_launch": ms_sol, "share_of_step": ms_sol / (ms_sol + ms_pyr)},
-        "roofline_pyramid": {"kernel": "pyramid_fused_kernel", "bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": pyr_gbs / hbm_peak,
-                             "traffic": 330_073_344 if (B, args.kernel) == (256, 0) else None,  # pyramid_fused_kernel, same capture
+        "roofline_pyramid": {"kernel": "pyramid_l01_kernel + pyramid_band_kernel (all levels + row aprons)", "bound": "hbm",
+                             "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak,
+                             "traffic": (traffic("pyramid_l01_kernel", args) or 0) + (traffic("pyramid_band_kernel", args) or 0) or None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_launch": pyr_bytes, "ms_per_launch": ms_pyr},
+        "triangulation": {"what": "lego_klt_batch_triangulate on the tracked batch (keypoints in HBM, world points to "
+                                  "pinned host memory): legoslam::triangulation, SURVEY.md 8f N3",
+                          "points_per_s": world * n_tracks / (tri_ms * 1e-3), "ms_per_call": tri_ms,
+                          "d2h_bytes_per_call": int(tri_pt.nbytes + tri_ok.nbytes), "n_accepted": int(tri_ok.sum())},
+        "host": {"numa_binding": numa, "e2e_wall_ms_per_step": e2e_wall_s * 1e3 / args.steps},
         "cpu_baseline": cpu,
         "clocks": clocks,
         "solver": {"n_success": n_success, "n_slow_path_passes": slow, "n_deferred_features": deferred, "defer_reason[inexact,margin,nominal,range]": defer_reason,

@@ -35,5 +35,29 @@ def main(rep, out):
             w.writerow([r[hdr.index("Kernel Name")][:60]] + [r[i] for i in cols])
 
 
+def traffic_json(rep, out):
+    """DRAM bytes per launch (read + write) of every kernel in the report, keyed by the bare kernel name: the
+    numbers bench.py quotes as roofline.traffic (first launch of each kernel)."""
+    import json
+    import re
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {}
+    for r in rows[2:]:
+        m = re.search(r"(\w+_kernel)", r[ik])
+        name = m.group(1) if m else r[ik]
+        total = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        if name not in res or total > res[name]:      # (klt_lane_kernel<.., true> is the empty FAMILIES instance)
+            res[name] = total
+    with open(out, "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    if sys.argv[1] == "--traffic":
+        traffic_json(sys.argv[2], sys.argv[3])
+    else:
+        main(sys.argv[1], sys.argv[2])
