@@ -278,12 +278,13 @@ pyramid_band_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         } else if (tid == 32 * (kWarps - 1) && lo > 0) {
             gD[dcols - dpitch] = D[0];  // wrap byte of the row above this band
         }
+        // every thread's shared-memory writes must be visible to the async proxy that reads them for the bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         // band out: [left apron of the first row, column c16 of the last row) in one piece, the rest of the last
         // row by plain stores that skip the wrap byte unless it is known (last row of the image)
         const int c16 = dcols & ~15;
         if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const uint32_t total = (uint32_t)((nr - 1) * dpitch + c16 + kApronL);
             for (uint32_t off = 0; off < total; off += 16384u) {
                 const uint32_t n = min(16384u, total - off);
