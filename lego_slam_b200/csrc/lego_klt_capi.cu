@@ -90,6 +90,8 @@ struct lego_klt_batch {
     cudaStream_t copy = nullptr;   // chunked end-to-end path: H2D of chunk c+1 overlaps compute of chunk c
     cudaEvent_t ev_chunk[kMaxChunks] = {};
     cudaEvent_t ev_compute_done = nullptr;
+    cudaStream_t d2h = nullptr;    // chunked end-to-end path: results of chunk c leave while chunk c+1 computes
+    cudaEvent_t ev_done[kMaxChunks] = {};
     bool uploaded = false, ran = false, pyramids_valid = false, last_chunked = false;
     lego_klt_params last_params;
 };
@@ -562,6 +564,9 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     for (int i = 0; i < kMaxChunks; ++i)
         if (b->ev_chunk[i]) cudaEventDestroy(b->ev_chunk[i]);
     if (b->ev_compute_done) cudaEventDestroy(b->ev_compute_done);
+    if (b->d2h) cudaStreamDestroy(b->d2h);
+    for (int i = 0; i < kMaxChunks; ++i)
+        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     cudaFree(b->d_images);
     cudaFree(b->d_tight);
     cudaFree(b->d_kp1);
@@ -648,7 +653,17 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     // (10 chunks with a fine tail measured 6 % slower than 8 equal ones).
     int bounds[kMaxChunks + 1];
     const int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
-    for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
+    // the work after the LAST upload is not hidden by any copy: an optionally smaller last chunk shortens it
+    static const int tail_pairs = [] {
+        const char *e = getenv("LEGO_KLT_E2E_TAIL");  // tuning aid; 0 = equal chunks
+        return e ? atoi(e) : 0;
+    }();
+    if (tail_pairs > 0 && n_chunks > 1 && tail_pairs < b->B / n_chunks) {
+        for (int c = 0; c < n_chunks; ++c) bounds[c] = (int)((long long)(b->B - tail_pairs) * c / (n_chunks - 1));
+        bounds[n_chunks] = b->B;
+    } else {
+        for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
+    }
     if (n_chunks == 1) {
         int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
         if (rc) return rc;
@@ -668,31 +683,44 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     cudaStream_t st = ctx->stream;
     if (!b->copy) {
         CU_TRY(cudaStreamCreateWithFlags(&b->copy, cudaStreamNonBlocking));
-        for (int i = 0; i < kMaxChunks; ++i) CU_TRY(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
+        CU_TRY(cudaStreamCreateWithFlags(&b->d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) {
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
+        }
         CU_TRY(cudaEventCreateWithFlags(&b->ev_compute_done, cudaEventDisableTiming));
     }
     CU_TRY(cudaEventRecord(b->ev[EV_START], st));
     CU_TRY(cudaStreamWaitEvent(b->copy, b->ev[EV_START], 0));  // the copy stream starts after earlier work
+    CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev[EV_START], 0));
     CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
     CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
     const int n = b->n_active;
+    // All keypoints first, as two copies (per-chunk keypoint copies are 256 KB each: latency-bound gaps on the link),
+    // and before any result comes back: kp2_xy is both the initial guess and the output buffer.
+    if (nt) {
+        CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
+        CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
+    }
     for (int c = 0; c < n_chunks; ++c) {
         const int img0 = bounds[c], img1 = bounds[c + 1];
         const int nimg = img1 - img0;
         if (nimg <= 0) continue;
         CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));
         CU_TRY(upload_set(b, 1, imgs2, img0, nimg, b->copy));
-        if (n) {
-            const size_t off = (size_t)img0 * n, cnt = (size_t)nimg * n;
-            CU_TRY(cudaMemcpyAsync(b->d_kp1 + off, kp1_xy + 2 * off, cnt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
-            CU_TRY(cudaMemcpyAsync(b->d_kp2_init + off, kp2_xy + 2 * off, cnt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
-        }
         CU_TRY(cudaEventRecord(b->ev_chunk[c], b->copy));
         CU_TRY(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
         CU_TRY(ingest_set(b, 0, img0, nimg, st));
         CU_TRY(ingest_set(b, 1, img0, nimg, st));
         rc = run_range(b, params, img0, nimg, c, nullptr);
         if (rc) return rc;
+        if (n) {  // this chunk's results go home while the next chunk computes
+            const size_t off = (size_t)img0 * n, cnt = (size_t)nimg * n;
+            CU_TRY(cudaEventRecord(b->ev_done[c], st));
+            CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_done[c], 0));
+            CU_TRY(cudaMemcpyAsync(kp2_xy + 2 * off, b->d_kp2_out + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, b->d2h));
+            CU_TRY(cudaMemcpyAsync(success + off, b->d_success + off, cnt, cudaMemcpyDeviceToHost, b->d2h));
+        }
     }
     CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
     b->uploaded = true;
@@ -701,7 +729,12 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     b->last_chunked = true;
     b->last_params = *params;
     ++b->runs;
-    return lego_klt_batch_download(b, kp2_xy, success, stats);
+    CU_TRY(cudaMemcpyAsync(b->h_stats, b->d_stats, kStatCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(b->ev[EV_D2H], st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaStreamSynchronize(b->d2h));
+    if (stats) fill_stats(b, stats);
+    return LEGO_KLT_OK;
 }
 
 int lego_klt_batch_device_ptrs(lego_klt_batch *b, void **imgs1, void **imgs2, void **kp1_xy, void **kp2_xy_init,
