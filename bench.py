@@ -464,7 +464,9 @@ def main():
     ap.add_argument("--features", type=int, default=2000)
     ap.add_argument("--distinct", type=int, default=64, help="distinct generated pairs (tiled to --pairs)")
     ap.add_argument("--kernel", type=int, default=0, help="LEGO_KLT_KERNEL_* (0 = auto)")
-    ap.add_argument("--streams", type=int, default=1, help="device-resident batches in flight (value only)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="device-resident batches in flight (value only; 2 = double buffering: the pyramid / template "
+                         "kernels of one batch fill the tail of the other batch's persistent solver kernel)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--subpixel", action="store_true",
