@@ -236,6 +236,67 @@ def traffic(kernel: str, args):
     return int(v) if v else None
 
 
+def sequence_mode(trk, n_feat, args):
+    """BASELINE config C2 beside the headline: ONE camera, frame after frame -- per frame the temporal track
+    (last left -> current left) and the stereo match (current left -> current right), 2000 features each, the way
+    Frontend::Track calls them (src/frontend_g2o.cpp:453-535).  Latency-bound (two synchronous calls per frame), so
+    tracks/s is far below the batched figure; timed by wall clock around the calls a user makes (host buffers in,
+    host buffers out).  `handles`: image handles with cached pyramids (each frame uploads 2 images, builds 2 pyramids);
+    `pairwise`: lego_klt_track as the reference's signature implies (4 uploads, 4 pyramids per frame)."""
+    from lego_slam_b200 import synth
+    import lego_slam_b200 as klt
+    frames = []
+    L, R, kps, _, _ = synth.stereo_case(ROWS, COLS, n_feat, seed=2)
+    for f in (1, 2, 3):
+        P, Cur, kt, _, _ = synth.temporal_case(ROWS, COLS, n_feat, seed=2, frame=f)
+        frames.append((P, Cur, kt))
+    params = klt.make_params(levels=LEVELS, patch_lo=PATCH_LO, patch_hi=PATCH_HI)
+    prev_h, cur_h, right_h = (trk.image(ROWS, COLS, LEVELS) for _ in range(3))
+    n_frames = 60
+
+    def run_handles(count):
+        nonlocal prev_h, cur_h
+        for i in range(count):
+            P, Cur, kt = frames[i % len(frames)]
+            if i == 0:
+                prev_h.upload(P)
+            cur_h.upload(Cur)
+            right_h.upload(R)
+            trk.track_images(prev_h, cur_h, kt, kt, params)       # Frontend::TrackLastFrame...4LayerSelf
+            trk.track_images(cur_h, right_h, kps, kps, params)    # Frontend::FindFeaturesInRight...4LayerSelf
+            prev_h, cur_h = cur_h, prev_h
+
+    def run_pairwise(count):
+        for i in range(count):
+            P, Cur, kt = frames[i % len(frames)]
+            trk.track(P, Cur, kt, kt, params)
+            trk.track(L, R, kps, kps, params)
+
+    res = {"workload": f"C2: sequence, per frame temporal + stereo track of {n_feat} features, {COLS}x{ROWS}, {LEVELS} levels"}
+    for name, fn in (("handles", run_handles), ("pairwise", run_pairwise)):
+        fn(5)
+        trk.sync()
+        t0 = time.perf_counter()
+        fn(n_frames)
+        trk.sync()
+        dt = time.perf_counter() - t0
+        res[name] = {"ms_per_frame": dt / n_frames * 1e3, "frames_per_s": n_frames / dt,
+                     "tracks_per_s": 2 * n_feat * n_frames / dt}
+    if not args.no_cpu_baseline:
+        from oracle import binding as ob   # the checker, timed as the CPU baseline of this configuration
+        threads = os.cpu_count() or 1
+        P, Cur, kt = frames[0]
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ob.track(P, Cur, kt, kt, threads=threads)
+            ob.track(L, R, kps, kps, threads=threads)
+        dt = (time.perf_counter() - t0) / reps
+        res["cpu_baseline"] = {"ms_per_frame": dt * 1e3, "tracks_per_s": 2 * n_feat / dt, "cores": threads, "kind": "port",
+                               "sample": f"{reps} frames, features split over {threads} threads like cv::parallel_for_"}
+    return res
+
+
 def workload_config(args):
     return {"workload": f"C3: {args.pairs} independent stereo pairs {COLS}x{ROWS} u8 per GPU x {args.features} "
                         f"features, {LEVELS}-level pyramid, 7x7 patch (reference half_patch_size=3), forward, kp2=kp1",
@@ -408,6 +469,8 @@ def run_ours(args):
                "sample": f"{n_pairs} pairs x {n} features of the same workload ({dt:.1f} s wall), full pyramids + "
                          f"{LEVELS} levels, oracle built -std=c++11 -O3 (reference flags), one pair per thread"}
 
+    seq = sequence_mode(trk, n, args) if world == 1 and not args.no_sequence else None
+
     value = world * n_tracks * args.steps / (ms_total * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": world, "steps": args.steps,
@@ -443,6 +506,7 @@ def run_ours(args):
                                   "pinned host memory): legoslam::triangulation, SURVEY.md 8f N3",
                           "points_per_s": world * n_tracks / (tri_ms * 1e-3), "ms_per_call": tri_ms,
                           "d2h_bytes_per_call": int(tri_pt.nbytes + tri_ok.nbytes), "n_accepted": int(tri_ok.sum())},
+        "sequence_mode": seq,
         "host": {"numa_binding": numa, "e2e_wall_ms_per_step": e2e_wall_s * 1e3 / args.steps},
         "cpu_baseline": cpu,
         "clocks": clocks,
@@ -468,6 +532,7 @@ def main():
                     help="device-resident batches in flight (value only; 2 = double buffering: the pyramid / template "
                          "kernels of one batch fill the tail of the other batch's persistent solver kernel)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
+    ap.add_argument("--no-sequence", action="store_true", help="skip the C2 sequence-mode side measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--subpixel", action="store_true",
                     help="jitter the source keypoints by +-0.5 px (tracked points as fed back by TrackLastFrame)")

@@ -43,7 +43,8 @@ enum {
 
 /* ---- solver kernel selection ---- */
 enum {
-    LEGO_KLT_KERNEL_AUTO = 0,   /* LANE where it applies (7x7 forward), else WARP                  */
+    LEGO_KLT_KERNEL_AUTO = 0,   /* LANE where it applies (7x7 forward) and the call has more than 4096
+                                   features, else WARP (lower latency on small calls)               */
     LEGO_KLT_KERNEL_EXACT = 1,  /* one thread per feature, reference operation order, flat global
                                    addressing: bit-identical to the CPU oracle; the on-GPU checker  */
     LEGO_KLT_KERNEL_WARP = 2,   /* one warp per feature, windows staged in shared memory, fp64

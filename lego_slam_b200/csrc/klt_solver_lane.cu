@@ -87,6 +87,10 @@ constexpr int kTplStride = 52;                                // floats per (fea
 #define LANE_ASYNC_SETUP 0  // level set-up by cp.async straight into shared memory, overlapped with the grid set-up:
                             // measured on B200, identical time (1.740 ms both) at 10 more registers -> off
 #endif
+#ifndef LANE_SWPIPE
+#define LANE_SWPIPE 0       // shared-memory loads of row step r+1 issued during row step r (rolled loop, manual pipelining):
+                            // measured on B200: 4 % SLOWER (1.782 vs 1.715 ms, 160 vs 150 registers) -> off
+#endif
 #ifndef LANE_PREFETCH_Q
 #define LANE_PREFETCH_Q 0   // measured on B200: no gain (the set-up stalls are not DRAM latency)
 #endif
@@ -314,6 +318,22 @@ __device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, int ka, uint32_t 
     p.x = __uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7440u + ka));
     p.y = __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7440u + kb));
     return add2_rn(p, make_float2(-8388608.0f, -8388608.0f));
+}
+
+// (raw window words of row i / their conversion: separate, so that the loads can be issued one row step ahead)
+template <int WS>
+__device__ __forceinline__ void load_row_words(const uint32_t *wp, int i, uint32_t (&w)[4]) {
+    const uint32_t *p = wp + i * kWin2Words * WS;
+    w[0] = p[0], w[1] = p[WS], w[2] = p[2 * WS], w[3] = p[3 * WS];
+}
+
+__device__ __forceinline__ void convert_row10_packed(const uint32_t (&w)[4], int sh, Row2 &row) {
+    const uint32_t b[3] = {__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh)};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        row.e[j] = bytes_to_float2(b[(2 * j) >> 2], (2 * j) & 3, b[(2 * j + 1) >> 2], (2 * j + 1) & 3);
+        row.o[j] = bytes_to_float2(b[(2 * j + 1) >> 2], (2 * j + 1) & 3, b[(2 * j + 2) >> 2], (2 * j + 2) & 3);
+    }
 }
 
 template <int WS>
@@ -936,6 +956,51 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 if (r + 1 >= G) break;
                 step(r + 1, rowC, rowA, Sb, Sc, Sa);
                 step(r + 2, rowA, rowB, Sc, Sa, Sb);
+            }
+#elif LANE_SWPIPE
+            // Rolled loop, software-pipelined by hand: the 13 shared-memory words of the NEXT row step (window row,
+            // row weights, template row) are loaded while this step computes, so no step starts by waiting for them.
+            uint32_t nw[4];
+            float nomy, nyy, ni1[P];
+            auto prefetch = [&](int r) {
+                load_row_words<WS>(wp, r + 1, nw);
+                nomy = wyp[(2 * r) * WS];
+                nyy = wyp[(2 * r + 1) * WS];
+                const float *i1row = i1p + ((r - 2) * P) * WS;
+#pragma unroll
+                for (int x = 0; x < P; ++x) ni1[x] = i1row[x * WS];
+            };
+            prefetch(2);
+#pragma unroll 1
+            for (int r = 2; r < G; ++r) {
+                convert_row10_packed(nw, sh, rowB);
+                const float omy_r = nomy, yy_r = nyy;
+                float ci1[P];
+#pragma unroll
+                for (int x = 0; x < P; ++x) ci1[x] = ni1[x];
+                if (r + 1 < G) prefetch(r + 1);
+                sample_row_packed(OMX, XX, omy_r, yy_r, rowA, rowB, args.one, Sc);
+                const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
+#pragma unroll
+                for (int x = 0; x < P; ++x) {
+                    const int g = x + 1;
+                    const bool on = !any_masked || (row_on && ((pmx >> x) & 1u));
+                    const double e = (double)(on ? __fadd_rn(ci1[x], -pick(Sb, g)) : 0.f);               // :65-66
+                    const double gx = (double)(on ? __fadd_rn(pick(Sb, g + 1), -pick(Sb, g - 1)) : 0.f);  // :70-71
+                    const double gy = (double)(on ? __fadd_rn(pick(Sc, g), -pick(Sa, g)) : 0.f);          // :72-73
+                    sb0 = fma(e, gx, sb0);
+                    sb1 = fma(e, gy, sb1);
+                    sc = fma(e, e, sc);
+                    s00 = fma(gx, gx, s00);
+                    s01 = fma(gx, gy, s01);
+                    s11 = fma(gy, gy, s11);
+                }
+                rowA = rowB;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    Sa[j] = Sb[j];
+                    Sb[j] = Sc[j];
+                }
             }
 #else
 #pragma unroll 1

@@ -42,6 +42,10 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
 constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings)
 constexpr int kMaxSub = 32; // timed sub-ranges of an interleaved run
+constexpr size_t kIoStatsBytes = 256;                       // device counters (kStatCount x 8 bytes, padded)
+constexpr size_t kIoHeadBytes = kIoStatsBytes + 256;        // + work counters (4 x kMaxChunks ints)
+static_assert(kStatCount * sizeof(unsigned long long) <= kIoStatsBytes && 4 * 16 * sizeof(int) <= 256, "io head layout");
+constexpr int kAutoLaneMinFeatures = 4096;  // LEGO_KLT_KERNEL_AUTO: LANE above, WARP up to this many features per call
 constexpr int kMaxChunks = 16;  // chunks of the overlapped end-to-end path (lego_klt_track_batched)
 
 }  // namespace
@@ -56,6 +60,17 @@ struct lego_klt_ctx {
     size_t pinned_bytes = 0;
     uint8_t *d_tri = nullptr;          // triangulation scratch (grow-only)
     size_t tri_bytes = 0;
+    // image-upload staging: a ring of pinned slots, each guarded by an event, so that an upload does not have to
+    // drain the stream before it may overwrite the staging memory (lego_klt_image_upload*)
+    struct Stage {
+        uint8_t *p = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t done = nullptr;
+        bool busy = false;
+    } stage[3];
+    int stage_next = 0;
+    uint8_t *pin_io = nullptr;         // keypoint / result staging of the single-pair paths
+    size_t pin_io_bytes = 0;
 };
 
 struct lego_klt_batch {
@@ -67,6 +82,10 @@ struct lego_klt_batch {
     WarpKernelMaps *maps = nullptr;
     uint8_t *d_images = nullptr;  // all levels, both sets
     uint8_t *d_tight = nullptr;   // H2D landing buffer: 2 sets of B tight images
+    // keypoints, flags and counters live in ONE allocation: [kp1 | kp2_init] and [stats | work | kp2_out | success],
+    // so that the single-pair paths move each group with one copy (lego_klt_track / lego_klt_track_images)
+    uint8_t *d_io = nullptr;
+    size_t io_out_off = 0;         // byte offset of the output group in d_io
     float2 *d_kp1 = nullptr, *d_kp2_init = nullptr, *d_kp2_out = nullptr;
     uint8_t *d_success = nullptr;
     unsigned long long *d_stats = nullptr;
@@ -182,13 +201,17 @@ int batch_alloc(lego_klt_ctx *ctx, int B, int cols, int rows, size_t step, int n
     if (e != cudaSuccess) return cleanup(fail(LEGO_KLT_ERR_CUDA, "cudaMalloc landing buffer: %s", cudaGetErrorString(e)));
 
     const size_t nt = (size_t)B * (size_t)(n > 0 ? n : 1);
-    if ((e = cudaMalloc(&b->d_kp1, nt * sizeof(float2))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_kp2_init, nt * sizeof(float2))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_kp2_out, nt * sizeof(float2))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_success, nt)) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_work, 4 * kMaxChunks * sizeof(int))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_defer_list, nt * sizeof(int))) != cudaSuccess ||
+    b->io_out_off = align_up(2 * nt * sizeof(float2), 256);
+    const size_t io_bytes = b->io_out_off + kIoHeadBytes + nt * sizeof(float2) + align_up(nt, 256);
+    if ((e = cudaMalloc(&b->d_io, io_bytes)) != cudaSuccess)
+        return cleanup(fail(LEGO_KLT_ERR_CUDA, "allocating keypoint buffers: %s", cudaGetErrorString(e)));
+    b->d_kp1 = reinterpret_cast<float2 *>(b->d_io);
+    b->d_kp2_init = b->d_kp1 + nt;
+    b->d_stats = reinterpret_cast<unsigned long long *>(b->d_io + b->io_out_off);
+    b->d_work = reinterpret_cast<int *>(b->d_io + b->io_out_off + kIoStatsBytes);
+    b->d_kp2_out = reinterpret_cast<float2 *>(b->d_io + b->io_out_off + kIoHeadBytes);
+    b->d_success = reinterpret_cast<uint8_t *>(b->d_kp2_out + nt);
+    if ((e = cudaMalloc(&b->d_defer_list, nt * sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc(&b->d_fam_list, nt * sizeof(int))) != cudaSuccess ||
         (e = cudaMallocHost(&b->h_stats, kStatCount * sizeof(unsigned long long))) != cudaSuccess)
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "allocating keypoint buffers: %s", cudaGetErrorString(e)));
@@ -300,7 +323,11 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.feat_flag = nullptr;
     a.epoch = 0;
     int kernel = params->kernel;
-    if (kernel == LEGO_KLT_KERNEL_AUTO) kernel = lane_kernel_supports(a) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
+    // AUTO: the thread-per-feature LANE kernel needs tens of thousands of features to fill the machine (57k resident
+    // threads); below ~4k features of one call the warp-per-feature kernel has the lower latency (measured, 1241x376:
+    // n = 2000: 0.24 vs 0.31 ms per call, n = 5000: equal, n = 20000: 0.70 vs 0.42 ms).  Same fidelity contract.
+    if (kernel == LEGO_KLT_KERNEL_AUTO)
+        kernel = (lane_kernel_supports(a) && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
         return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the 7x7 forward configuration only");
     if (interleave && !(kernel == LEGO_KLT_KERNEL_LANE && a.n_total > 0))
@@ -427,6 +454,75 @@ int ensure_pinned(lego_klt_ctx *ctx, size_t bytes) {
     return LEGO_KLT_OK;
 }
 
+// Next slot of the upload staging ring, at least `bytes` large and no longer read by an earlier copy.
+int acquire_stage(lego_klt_ctx *ctx, size_t bytes, lego_klt_ctx::Stage **out) {
+    lego_klt_ctx::Stage &sl = ctx->stage[ctx->stage_next];
+    ctx->stage_next = (ctx->stage_next + 1) % 3;
+    if (!sl.done) CU_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    if (sl.busy) {
+        CU_TRY(cudaEventSynchronize(sl.done));
+        sl.busy = false;
+    }
+    if (sl.bytes < bytes) {
+        if (sl.p) cudaFreeHost(sl.p);
+        sl.p = nullptr;
+        sl.bytes = 0;
+        CU_TRY(cudaMallocHost(&sl.p, bytes));
+        sl.bytes = bytes;
+    }
+    *out = &sl;
+    return LEGO_KLT_OK;
+}
+
+int release_stage(lego_klt_ctx *ctx, lego_klt_ctx::Stage *sl) {  // call after the copy that reads it was enqueued
+    CU_TRY(cudaEventRecord(sl->done, ctx->stream));
+    sl->busy = true;
+    return LEGO_KLT_OK;
+}
+
+// Single-pair paths: both keypoint arrays go up in ONE copy and counters + positions + flags come back in ONE
+// copy, through pinned staging (caller memory is usually pageable: a cudaMemcpyAsync from / to it would make the
+// driver stage and, for device-to-host, block the stream once per copy).  The cached batch's pointers are
+// re-based for the call's n (groups packed, not at capacity stride).
+int single_upload_keypoints(lego_klt_ctx *ctx, lego_klt_batch *b, const float *kp1_xy, const float *kp2_xy, int n) {
+    const size_t kp_bytes = (size_t)n * sizeof(float2);
+    const size_t need = 2 * kp_bytes + kIoHeadBytes + kp_bytes + (size_t)n + 64;
+    if (ctx->pin_io_bytes < need) {
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->pin_io) cudaFreeHost(ctx->pin_io);
+        ctx->pin_io = nullptr;
+        ctx->pin_io_bytes = 0;
+        CU_TRY(cudaMallocHost(&ctx->pin_io, need + need / 2));
+        ctx->pin_io_bytes = need + need / 2;
+    }
+    b->n_active = n;
+    b->d_kp2_init = b->d_kp1 + n;
+    b->d_success = reinterpret_cast<uint8_t *>(b->d_kp2_out + n);
+    if (n) {
+        memcpy(ctx->pin_io, kp1_xy, kp_bytes);
+        memcpy(ctx->pin_io + kp_bytes, kp2_xy, kp_bytes);
+        CU_TRY(cudaMemcpyAsync(b->d_kp1, ctx->pin_io, 2 * kp_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return LEGO_KLT_OK;
+}
+
+int single_download(lego_klt_ctx *ctx, lego_klt_batch *b, float *kp2_xy, uint8_t *success, int n, lego_klt_stats *stats) {
+    const size_t kp_bytes = (size_t)n * sizeof(float2);
+    uint8_t *h = ctx->pin_io + 2 * kp_bytes;  // (after the input group)
+    h = reinterpret_cast<uint8_t *>(align_up((size_t)(uintptr_t)h, 16));
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaMemcpyAsync(h, b->d_io + b->io_out_off, kIoHeadBytes + kp_bytes + (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (stats) CU_TRY(cudaEventRecord(b->ev[EV_D2H], st));
+    CU_TRY(cudaStreamSynchronize(st));
+    memcpy(b->h_stats, h, kStatCount * sizeof(unsigned long long));
+    if (n) {
+        memcpy(kp2_xy, h + kIoHeadBytes, kp_bytes);
+        memcpy(success, h + kIoHeadBytes + kp_bytes, (size_t)n);
+    }
+    if (stats) fill_stats(b, stats);
+    return LEGO_KLT_OK;
+}
+
 // (Re)creates the cached single-pair batch when the shape changes or more features are needed.
 int ensure_single(lego_klt_ctx *ctx, int cols, int rows, size_t step, int n, int levels) {
     lego_klt_batch *s = ctx->single;
@@ -500,6 +596,11 @@ void lego_klt_destroy(lego_klt_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->single) lego_klt_batch_destroy(ctx->single);
     if (ctx->d_tri) cudaFree(ctx->d_tri);
+    for (auto &sl : ctx->stage) {
+        if (sl.p) cudaFreeHost(sl.p);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (ctx->pin_io) cudaFreeHost(ctx->pin_io);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -551,7 +652,6 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
         for (int i = 0; i < 2 * kMaxSub; ++i)
             if (b->ring_sub[r][i]) cudaEventDestroy(b->ring_sub[r][i]);
     }
-    cudaFree(b->d_work);
     cudaFree(b->d_defer_list);
     cudaFree(b->d_fam_list);
     cudaFree(b->d_templates);
@@ -569,11 +669,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
     cudaFree(b->d_images);
     cudaFree(b->d_tight);
-    cudaFree(b->d_kp1);
-    cudaFree(b->d_kp2_init);
-    cudaFree(b->d_kp2_out);
-    cudaFree(b->d_success);
-    cudaFree(b->d_stats);
+    cudaFree(b->d_io);
     if (b->h_stats) cudaFreeHost(b->h_stats);
     cudaGetLastError();
     delete b;
@@ -761,36 +857,34 @@ int lego_klt_track(lego_klt_ctx *ctx, const lego_klt_params *params, const uint8
     int rc = ensure_single(ctx, cols, rows, step, n, params->levels);
     if (rc) return rc;
     lego_klt_batch *b = ctx->single;
-    b->n_active = n;
     // Stage through pinned memory: a cv::Mat guarantees only (rows-1)*step + cols readable bytes.
-    const size_t img_bytes = (size_t)rows * step, kp_bytes = (size_t)n * sizeof(float2);
-    rc = ensure_pinned(ctx, 2 * img_bytes + 3 * kp_bytes + (size_t)n + 64);
+    const size_t img_bytes = (size_t)rows * step;
+    CU_TRY(cudaSetDevice(ctx->device));
+    lego_klt_ctx::Stage *sl = nullptr;
+    rc = acquire_stage(ctx, 2 * img_bytes, &sl);
     if (rc) return rc;
-    uint8_t *h1 = ctx->pinned, *h2 = h1 + img_bytes;
-    float *hk1 = reinterpret_cast<float *>(h2 + img_bytes);
-    float *hk2 = hk1 + 2 * (size_t)n;
-    float *hout = hk2 + 2 * (size_t)n;
-    uint8_t *hs = reinterpret_cast<uint8_t *>(hout + 2 * (size_t)n);
+    uint8_t *h1 = sl->p, *h2 = h1 + img_bytes;
     const size_t valid = (size_t)(rows - 1) * step + (size_t)cols;
     memcpy(h1, img1, valid);
     memset(h1 + valid, 0, img_bytes - valid);
     memcpy(h2, img2, valid);
     memset(h2 + valid, 0, img_bytes - valid);
-    if (n) {
-        memcpy(hk1, kp1_xy, kp_bytes);
-        memcpy(hk2, kp2_xy, kp_bytes);
-    }
-    rc = lego_klt_batch_upload(b, h1, h2, hk1, hk2);
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaEventRecord(b->ev[EV_START], st));
+    CU_TRY(upload_set(b, 0, h1, 0, 1, st));
+    CU_TRY(upload_set(b, 1, h2, 0, 1, st));
+    rc = release_stage(ctx, sl);
     if (rc) return rc;
+    CU_TRY(ingest_set(b, 0, 0, 1, st));
+    CU_TRY(ingest_set(b, 1, 0, 1, st));
+    rc = single_upload_keypoints(ctx, b, kp1_xy, kp2_xy, n);
+    if (rc) return rc;
+    b->uploaded = true;
+    b->pyramids_valid = false;
+    b->last_chunked = false;
     rc = batch_run(b, params);
     if (rc) return rc;
-    rc = lego_klt_batch_download(b, hout, hs, stats);
-    if (rc) return rc;
-    if (n) {
-        memcpy(kp2_xy, hout, kp_bytes);
-        memcpy(success, hs, (size_t)n);
-    }
-    return LEGO_KLT_OK;
+    return single_download(ctx, b, kp2_xy, success, n, stats);
 }
 
 int lego_klt_image_create(lego_klt_ctx *ctx, int cols, int rows, size_t step, int levels, lego_klt_image **out) {
@@ -863,14 +957,16 @@ int lego_klt_image_upload(lego_klt_image *im, const uint8_t *data) {
     lego_klt_ctx *ctx = im->ctx;
     CU_TRY(cudaSetDevice(ctx->device));
     const size_t img_bytes = (size_t)im->rows * im->step;
-    int rc = ensure_pinned(ctx, 2 * img_bytes);
+    lego_klt_ctx::Stage *sl = nullptr;
+    int rc = acquire_stage(ctx, img_bytes, &sl);  // (a ring of pinned slots: no need to drain the stream first)
     if (rc) return rc;
-    CU_TRY(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
     const size_t valid = (size_t)(im->rows - 1) * im->step + (size_t)im->cols;  // what a cv::Mat guarantees
-    memcpy(ctx->pinned, data, valid);
-    memset(ctx->pinned + valid, 0, img_bytes - valid);
+    memcpy(sl->p, data, valid);
+    memset(sl->p + valid, 0, img_bytes - valid);
     cudaStream_t st = ctx->stream;
-    CU_TRY(cudaMemcpyAsync(im->d_tight, ctx->pinned, img_bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(im->d_tight, sl->p, img_bytes, cudaMemcpyHostToDevice, st));
+    rc = release_stage(ctx, sl);
+    if (rc) return rc;
     CU_TRY(launch_ingest(im->d_tight, im->view.lv[0], 0, 0, 1, st));
     CU_TRY(launch_pyramid(im->plan, im->view, 0, 1, st, 1));
     im->valid = true;
@@ -889,7 +985,8 @@ int lego_klt_image_upload_fullres(lego_klt_image *im, const uint8_t *full, int f
     lego_klt_ctx *ctx = im->ctx;
     CU_TRY(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)(full_rows - 1) * full_step + (size_t)full_cols;  // what a cv::Mat guarantees
-    int rc = ensure_pinned(ctx, bytes);
+    lego_klt_ctx::Stage *sl = nullptr;
+    int rc = acquire_stage(ctx, bytes, &sl);
     if (rc) return rc;
     if (bytes > im->full_bytes) {
         CU_TRY(cudaStreamSynchronize(ctx->stream));
@@ -899,10 +996,11 @@ int lego_klt_image_upload_fullres(lego_klt_image *im, const uint8_t *full, int f
         CU_TRY(cudaMalloc(&im->d_full, bytes));
         im->full_bytes = bytes;
     }
-    CU_TRY(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
-    memcpy(ctx->pinned, full, bytes);
+    memcpy(sl->p, full, bytes);
     cudaStream_t st = ctx->stream;
-    CU_TRY(cudaMemcpyAsync(im->d_full, ctx->pinned, bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(im->d_full, sl->p, bytes, cudaMemcpyHostToDevice, st));
+    rc = release_stage(ctx, sl);
+    if (rc) return rc;
     CU_TRY(launch_half_nearest(im->d_full, full_cols, full_rows, full_step, im->view.lv[0], st));
     CU_TRY(launch_pyramid(im->plan, im->view, 0, 1, st, 1));
     im->valid = true;
@@ -947,14 +1045,10 @@ int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, cons
     lego_klt_batch *b = ctx->single;
     rc = validate_params(params, b->levels);
     if (rc) return rc;
-    b->n_active = n;
-    const size_t kp_bytes = (size_t)n * sizeof(float2);
     cudaStream_t st = ctx->stream;
     CU_TRY(cudaSetDevice(ctx->device));
-    if (n) {
-        CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, kp_bytes, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, kp_bytes, cudaMemcpyHostToDevice, st));
-    }
+    rc = single_upload_keypoints(ctx, b, kp1_xy, kp2_xy, n);
+    if (rc) return rc;
     PyramidView view = img1->view;
     for (int l = 0; l < view.levels; ++l) view.lv[l].base[1] = img2->view.lv[l].base[0];
     CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
@@ -967,7 +1061,7 @@ int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, cons
     ++b->runs;
     b->ran = true;
     b->last_chunked = false;
-    return lego_klt_batch_download(b, kp2_xy, success, stats);
+    return single_download(ctx, b, kp2_xy, success, n, stats);
 }
 
 int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step, int levels,

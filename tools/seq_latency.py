@@ -1,0 +1,22 @@
+"""Latency of one track call (image handles, solver only) by kernel and feature count."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lego_slam_b200 as klt
+from lego_slam_b200 import synth
+
+trk = klt.Tracker(0)
+for n in (150, 500, 2000, 5000, 20000):
+    L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, n, seed=2, min_dist=3 if n > 5000 else None)
+    a = trk.image(376, 1241).upload(L)
+    b = trk.image(376, 1241).upload(R)
+    row = [f"n={kp1.shape[0]:6d}"]
+    for name, k in (("lane", klt.KERNEL_LANE), ("warp", klt.KERNEL_WARP)):
+        p = klt.make_params(kernel=k)
+        for _ in range(5):
+            trk.track_images(a, b, kp1, kp2, p)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            trk.track_images(a, b, kp1, kp2, p)
+        row.append(f"{name} {(time.perf_counter() - t0) / 50 * 1e3:.3f} ms")
+    print("  ".join(row))
