@@ -326,15 +326,20 @@ def test_bad_arguments_are_rejected(tracker):
 # ------------------------------------------------------------------ image ingest
 @pytest.mark.gpu
 @pytest.mark.parametrize("rows,cols,pad", [(376, 1241, 0), (375, 1242, 0), (751, 2483, 13), (3, 5, 0), (1080, 1920, 0)])
-def test_ingest_half_nearest_equals_cv2(tracker, rows, cols, pad):
+def test_ingest_half_nearest_equals_oracle_and_cv2(tracker, rows, cols, pad):
     """Dataset::NextFrame: cv::resize(img, out, cv::Size(), 0.5, 0.5, cv::INTER_NEAREST) (src/dataset.cpp:75-77).
     OpenCV is third party; the pin is Python cv2 in this image (same call)."""
-    cv2 = pytest.importorskip("cv2")
+    from oracle import ingest_np
     big = np.random.default_rng(rows * 7 + cols).integers(0, 256, size=(rows, cols + pad), dtype=np.uint8)
     full = big[:, :cols]
-    ref = cv2.resize(np.ascontiguousarray(full), None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
+    ref = ingest_np.downscale_half_nearest(full)      # (pinned against cv2 by tests/test_oracle_pyramid.py)
     got = tracker.downscale_half(full)
     assert got.shape == ref.shape and np.array_equal(got, ref)
+    try:
+        import cv2
+        assert np.array_equal(got, cv2.resize(np.ascontiguousarray(full), None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST))
+    except ImportError:
+        pass
 
 
 @pytest.mark.gpu

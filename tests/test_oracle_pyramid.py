@@ -49,3 +49,14 @@ def test_empty_level_is_an_error(oracle):
     img = np.zeros((3, 3), np.uint8)
     with pytest.raises(RuntimeError):
         oracle.build_pyramid(img, 4)
+
+
+@pytest.mark.parametrize("rows,cols", [(376, 1241), (375, 1242), (751, 2483), (3, 5), (1080, 1920), (2, 2), (2, 3)])  # (an axis of 1 pixel halves to 0: OpenCV asserts, the C ABI returns BAD_ARG)
+def test_ingest_oracle_equals_cv2_nearest_halving(rows, cols):
+    """Dataset::NextFrame (src/dataset.cpp:75-77): the numpy restatement against the only OpenCV in this image."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ingest_np
+    img = np.random.default_rng(rows * 31 + cols).integers(0, 256, size=(rows, cols), dtype=np.uint8)
+    ref = cv2.resize(img, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
+    got = ingest_np.downscale_half_nearest(img)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
