@@ -38,16 +38,30 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library if it is missing or older than its sources.  Safe under `torchrun` (every rank calls it):
+    an exclusive file lock serialises the ranks, the link goes to a temporary file and is renamed into place."""
     if not force and not needs_build():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    defs = os.environ.get("LEGO_KLT_NVCC_DEFS", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode:
-        raise RuntimeError("nvcc failed building liblego_klt.so")
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another rank built it while we waited
+                return LIB
+            srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+            defs = os.environ.get("LEGO_KLT_NVCC_DEFS", "").split()
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building liblego_klt.so")
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
