@@ -473,7 +473,7 @@ def run_ours(args):
 
     # The metric text of BASELINE.json says "8x8 patch"; the reference computes 7x7 (src/algorithm.cpp:40,63-64,
     # SURVEY.md F1), which is what `value` measures.  The literal 8x8 patch (-4..3) beside it, same batch, device-
-    # resident: it runs on the warp-per-feature kernel (the LANE kernel is specialised for the reference's 7x7).
+    # resident: the LANE solver is compiled for both patches (klt_solver_lane_p8.cu).
     p88 = None
     if world == 1 and not args.no_sequence:
         params88 = klt.make_params(levels=LEVELS, patch_lo=-4, patch_hi=3)
@@ -487,7 +487,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms88 = e0.elapsed_time(e1) / 3
         p88 = {"patch": [-4, 3], "value": n_tracks / (ms88 * 1e-3), "unit": "tracks/s", "ms_per_step": ms88,
-               "kernel": "klt_warp_kernel<2, 8> (warp per feature, TMA-staged windows)"}
+               "kernel": "klt_template_kernel + klt_lane_kernel compiled for offsets -4..3 (96-thread CTAs, 3 per SM)"}
 
     value = world * n_tracks * args.steps / (ms_total * 1e-3)
     line = {

@@ -51,9 +51,25 @@ namespace legoklt {
 
 namespace {
 
-constexpr int LO = -3, HI = 3, P = 7, G = 9;
+// Patch bounds are compile-time: this file is compiled once per supported patch (klt_solver_lane_p8.cu includes it
+// with LANE_PATCH_LO/HI = -4/3 and a symbol suffix).  The code below is written for P <= 8: five sample pairs per
+// grid row (G <= 10), 11 window pixels per row from four words, 8-bit family masks.
+#ifndef LANE_PATCH_LO
+#define LANE_PATCH_LO (-3)
+#define LANE_PATCH_HI 3
+#endif
+#ifndef LANE_SUFFIX
+#define LANE_SUFFIX
+#endif
+#define LANE_CAT2(a, b) a##b
+#define LANE_CAT(a, b) LANE_CAT2(a, b)
+#define LANE_FN(name) LANE_CAT(name, LANE_SUFFIX)
+constexpr int LO = LANE_PATCH_LO, HI = LANE_PATCH_HI, P = HI - LO + 1, G = P + 2;
+static_assert(P >= 3 && P <= 8, "the LANE kernel's row structure (5 pairs, 4 window words) covers patches up to 8x8");
+constexpr unsigned kPMask = (1u << P) - 1u;                    // one bit per patch column / row
+constexpr unsigned kPMask2 = kPMask | (kPMask << 8);           // x mask | y mask << 8 (family bookkeeping)
 #ifndef LANE_WROWS
-#define LANE_WROWS 12
+#define LANE_WROWS (G + 3)
 #endif
 #ifndef LANE_WWORDS
 #define LANE_WWORDS 6
@@ -72,11 +88,13 @@ constexpr int kWinAlign = (LANE_WWORDS == 8) ? 16 : 8;
 constexpr int kWinSlackL = (LANE_WWORDS == 8) ? 2 : 3;         // footprint starts kWinSlackL..kWinSlackL+kWinAlign-1 bytes in
 constexpr int kWinSlackT = (LANE_WROWS - (G + 1)) / 2;         // rows above the footprint
 constexpr int kWin2Total = kWin2Rows * kWin2Words;            // 112 words
-constexpr int kTplRows = 8;                                   // img1 window rows in the template kernel
+constexpr int kTplRows = P + 1;                               // img1 window rows in the template kernel
 constexpr int kI1Count = P * P;                               // 49 floats, index y*P + x
 constexpr int kQueue = LANE_QUEUE;                            // feature ring entries per warp (power of two, >= 32)
 static_assert(kQueue >= 32 && (kQueue & (kQueue - 1)) == 0, "ring size");
-constexpr int kTplStride = 52;                                // floats per (feature, level): 49 + flag + pad
+constexpr int kTplStride = ((P * P + 1 + 3) / 4 * 4) | 4;      // floats per (feature, level): patch + flag + pad; an ODD
+                                                              // number of float4 (conflict-free transposed stores)
+static_assert(kTplStride >= P * P + 1 && (kTplStride / 4) % 2 == 1 && kTplStride % 4 == 0, "template record stride");
 #ifndef LANE_BATCH
 #define LANE_BATCH 1
 #endif
@@ -819,8 +837,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     uint32_t wv[kHalf][kWin2Words];
                     window_load<kHalf>(img2, lv, wx0, wy0, wv);
                     window_store<kHalf, WS>(wv, &sm.win2[0][tid]);
-                    window_load<kHalf>(img2, lv, wx0, wy0 + kHalf, wv);
-                    window_store<kHalf, WS>(wv, &sm.win2[kHalf * kWin2Words][tid]);
+                    uint32_t wv2[kWin2Rows - kHalf][kWin2Words];  // (an odd row count leaves the larger half here)
+                    window_load<kWin2Rows - kHalf>(img2, lv, wx0, wy0 + kHalf, wv2);
+                    window_store<kWin2Rows - kHalf, WS>(wv2, &sm.win2[kHalf * kWin2Words][tid]);
                 }
 #endif
                 need_win = false;
@@ -833,13 +852,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         bool fast = false;
         float xx[G], omx[G];
         int ixn = 0, iyn = 0;
-        unsigned pmx = 0x7fu, pmy = 0x7fu;  // pixels (columns / rows) that belong to this sub-pass
+        unsigned pmx = kPMask, pmy = kPMask;  // pixels (columns / rows) that belong to this sub-pass
         if (run) {
             const LevelView &lv = pyr.lv[level];
             float yy[G], omy[G];
             double kxd = (double)kx, kyd = (double)ky;
-            if (FAMILIES && (fam & 0x7f7fu)) {  // this sub-pass works on one (x family, y family) combination
-                const unsigned mBx = fam & 0x7fu, mBy = (fam >> 8) & 0x7fu, sub = (fam >> 16) & 3u;
+            if (FAMILIES && (fam & kPMask2)) {  // this sub-pass works on one (x family, y family) combination
+                const unsigned mBx = fam & kPMask, mBy = (fam >> 8) & kPMask, sub = (fam >> 16) & 3u;
                 const bool fx = mBx && (sub & 1u), fy = mBy && (mBx ? (sub >> 1) : (sub & 1u));
                 if (fx) {
                     const int c = LO + __ffs(mBx) - 1;
@@ -849,8 +868,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     const int c = LO + __ffs(mBy) - 1;
                     kyd += (double)(ky + (float)c) - (kyd + (double)c);
                 }
-                pmx = fx ? mBx : (~mBx & 0x7fu);
-                pmy = fy ? mBy : (~mBy & 0x7fu);
+                pmx = fx ? mBx : (~mBx & kPMask);
+                pmy = fy ? mBy : (~mBy & kPMask);
             }
             const int whyx = grid_axis<false>(kxd, dx, lv.cols, ixn, xx, omx);
             const int whyy = grid_axis<true>(kyd, dy, lv.rows, iyn, yy, omy);
@@ -880,7 +899,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 #if LANE_ASYNC_SETUP
         asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's set-up copies (each thread reads only its own words)
 #endif
-        const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & 0x7f7fu) != 0u);
+        const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & kPMask2) != 0u);
         if (run) {
             const LevelView &lv = pyr.lv[level];
             const float *i1p = &sm.i1[0][tid];
@@ -896,7 +915,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 s00 = sums[3];
                 s01 = sums[4];
                 s11 = sums[5];
-                fam &= 0x7f7fu;
+                fam &= kPMask2;
             } else {
             const int ox = ixn - wx0;
             const int sh = (ox & 3) * 8;
@@ -1015,13 +1034,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             }
 #endif
 
-            if (FAMILIES && (fam & 0x7f7fu)) {
+            if (FAMILIES && (fam & kPMask2)) {
                 // multi-family level: this trip covered one (x family, y family) combination; partial sums
                 // wait in global scratch until the last combination has been added (rare, so out of line)
                 const unsigned sub = (fam >> 16) & 3u;
-                const unsigned nsub = ((fam & 0x7fu) ? 2u : 1u) * ((fam & 0x7f00u) ? 2u : 1u);
+                const unsigned nsub = ((fam & kPMask) ? 2u : 1u) * ((fam & (kPMask << 8)) ? 2u : 1u);
                 solve_now = multi_family_step(parked, sub, nsub, sb0, sb1, sc, s00, s01, s11);
-                fam = (fam & 0x7f7fu) | (solve_now ? 0u : ((sub + 1u) << 16));
+                fam = (fam & kPMask2) | (solve_now ? 0u : ((sub + 1u) << 16));
             }
             }
             if (solve_now) {
@@ -1107,15 +1126,15 @@ constexpr int kTplThreads = 128;
 
 }  // namespace
 
-bool lane_kernel_supports(const SolverArgs &args) {
+bool LANE_FN(lane_kernel_supports)(const SolverArgs &args) {
     return args.patch_lo == LO && args.patch_hi == HI && !args.inverse && args.max_iters >= 1 && args.max_iters <= 15;
 }
 
-size_t lane_template_bytes(int n_total, int levels) { return (size_t)n_total * levels * kTplStride * sizeof(float); }
+size_t LANE_FN(lane_template_bytes)(int n_total, int levels) { return (size_t)n_total * levels * kTplStride * sizeof(float); }
 
-size_t lane_scratch_bytes(int sm_count) { return (size_t)sm_count * kLaneMinCtas * kLaneThreads * 6 * sizeof(double); }
+size_t LANE_FN(lane_scratch_bytes)(int sm_count) { return (size_t)sm_count * kLaneMinCtas * kLaneThreads * 6 * sizeof(double); }
 
-cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream) {
+cudaError_t LANE_FN(launch_klt_template)(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
     auto kernel = klt_template_kernel<kTplThreads>;
     const long long items = (long long)((args.n_total + 31) & ~31) * pyr.levels;
@@ -1124,7 +1143,7 @@ cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream) {
+cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream) {
     if (args.n_total <= 0) return cudaSuccess;
     const size_t smem = sizeof(LaneSmem<kLaneThreads>);
     int grid = sm_count * kLaneMinCtas;

@@ -252,9 +252,10 @@ cudaError_t ingest_set(lego_klt_batch *b, int set, int img0, int nimg, cudaStrea
 int ensure_lane_buffers(lego_klt_batch *b) {
     if (b->d_templates) return LEGO_KLT_OK;
     const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
-    CU_TRY(cudaMalloc(&b->d_templates, lane_template_bytes((int)cap, b->levels)));
+    // (sized for the larger of the two compiled patch variants)
+    CU_TRY(cudaMalloc(&b->d_templates, std::max(lane_template_bytes((int)cap, b->levels), lane_template_bytes_p8((int)cap, b->levels))));
     CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
-    CU_TRY(cudaMalloc(&b->d_scratch, lane_scratch_bytes(b->ctx->sm_count)));
+    CU_TRY(cudaMalloc(&b->d_scratch, std::max(lane_scratch_bytes(b->ctx->sm_count), lane_scratch_bytes_p8(b->ctx->sm_count))));
     CU_TRY(cudaMemset(b->d_feat_flag, 0, cap * sizeof(int)));
     CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -326,10 +327,11 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     // AUTO: the thread-per-feature LANE kernel needs tens of thousands of features to fill the machine (57k resident
     // threads); below ~4k features of one call the warp-per-feature kernel has the lower latency (measured, 1241x376:
     // n = 2000: 0.24 vs 0.31 ms per call, n = 5000: equal, n = 20000: 0.70 vs 0.42 ms).  Same fidelity contract.
+    const bool lane7 = lane_kernel_supports(a), lane8 = lane_kernel_supports_p8(a);
     if (kernel == LEGO_KLT_KERNEL_AUTO)
-        kernel = (lane_kernel_supports(a) && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
-    if (kernel == LEGO_KLT_KERNEL_LANE && !lane_kernel_supports(a))
-        return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the 7x7 forward configuration only");
+        kernel = ((lane7 || lane8) && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
+    if (kernel == LEGO_KLT_KERNEL_LANE && !(lane7 || lane8))
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the forward 7x7 (-3..3) and 8x8 (-4..3) patches only");
     if (interleave && !(kernel == LEGO_KLT_KERNEL_LANE && a.n_total > 0))
         CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
@@ -361,10 +363,10 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
                 SolverArgs as = a;  // same lists and counters, a sub-range of the features
                 as.f0 = (img0 + s0) * b->n_active;
                 as.n_total = ns * b->n_active;
-                CU_TRY(launch_klt_template(view, as, st));
+                CU_TRY(lane8 ? launch_klt_template_p8(view, as, st) : launch_klt_template(view, as, st));
             }
         } else {
-            CU_TRY(launch_klt_template(view, a, st));
+            CU_TRY(lane8 ? launch_klt_template_p8(view, a, st) : launch_klt_template(view, a, st));
         }
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
@@ -375,7 +377,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         aw.list_count = a.defer_count;
         CU_TRY(launch_klt_warp(view, maps, aw, ctx->sm_count, b->side));
         CU_TRY(cudaEventRecord(b->ev_join, b->side));
-        CU_TRY(launch_klt_lane(view, a, ctx->sm_count, st));
+        CU_TRY(lane8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st) : launch_klt_lane(view, a, ctx->sm_count, st));
         CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
     }
     if (ring) CU_TRY(cudaEventRecord(ring[2], st));

@@ -15,10 +15,11 @@ FAST_KERNELS = [klt.KERNEL_WARP, klt.KERNEL_LANE]
 
 
 def _supported(kernel, kw):
-    """The LANE kernel is specialised for the reference's call-site configuration (7x7, forward)."""
+    """The LANE kernel is compiled for the reference's patch (7x7, -3..3) and for the 8x8 patch of the metric text
+    (-4..3), forward mode."""
     if kernel != klt.KERNEL_LANE:
         return True
-    return (kw.get("patch_lo", -3), kw.get("patch_hi", 3)) == (-3, 3) and not kw.get("inverse", False)
+    return (kw.get("patch_lo", -3), kw.get("patch_hi", 3)) in ((-3, 3), (-4, 3)) and not kw.get("inverse", False)
 
 
 def _iters(st, levels):
@@ -308,7 +309,30 @@ def test_lane_kernel_rejects_unsupported_configurations(tracker):
     with pytest.raises(_lib.KltError):
         tracker.track(img, img, kp, kp, klt.make_params(levels=2, inverse=True, kernel=klt.KERNEL_LANE))
     with pytest.raises(_lib.KltError):
-        tracker.track(img, img, kp, kp, klt.make_params(levels=2, patch_lo=-4, patch_hi=3, kernel=klt.KERNEL_LANE))
+        tracker.track(img, img, kp, kp, klt.make_params(levels=2, patch_lo=-5, patch_hi=5, kernel=klt.KERNEL_LANE))
+
+
+@pytest.mark.gpu
+def test_lane_kernel_8x8_patch_on_a_large_batch_equals_exact_kernel(tracker):
+    """The 8x8 (-4..3) instance of the LANE kernel (the patch BASELINE.json's metric text names) against the
+    bit-exact EXACT kernel on a batch large enough to fill the persistent kernel: flags equal, positions within the
+    contract, identical iteration counts."""
+    B, rows, cols, n = 12, 376, 1241, 2000
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 2000)
+    res = {}
+    for name, k in (("exact", klt.KERNEL_EXACT), ("lane", klt.KERNEL_LANE), ("auto", klt.KERNEL_AUTO)):
+        batch = tracker.batch(B, rows, cols, n, levels=4)
+        batch.upload(imgs1, imgs2, kp1, kp2)
+        batch.run(klt.make_params(patch_lo=-4, patch_hi=3, kernel=k))
+        o, s_, st = batch.download()
+        res[name] = (o.copy(), s_.copy(), _iters(st, 4))
+    eo, es, ei = res["exact"]
+    for name in ("lane", "auto"):
+        o, s_, it = res[name]
+        assert np.array_equal(s_, es), name
+        assert np.abs(o.astype(np.float64) - eo).max() <= 1e-3, name
+        assert it == ei, name
+    assert (res["lane"][0].view(np.uint32) == eo.view(np.uint32)).all(axis=2).mean() >= 0.999
 
 
 def test_bad_arguments_are_rejected(tracker):
