@@ -98,20 +98,6 @@ static_assert(kTplStride >= P * P + 1 && (kTplStride / 4) % 2 == 1 && kTplStride
 #ifndef LANE_BATCH
 #define LANE_BATCH 1
 #endif
-#ifndef LANE_UNROLL3
-#define LANE_UNROLL3 0   // measured on B200: 189 instead of 212 instructions per row step, yet 3 % SLOWER (code size)
-#endif
-#ifndef LANE_ASYNC_SETUP
-#define LANE_ASYNC_SETUP 0  // level set-up by cp.async straight into shared memory, overlapped with the grid set-up:
-                            // measured on B200, identical time (1.740 ms both) at 10 more registers -> off
-#endif
-#ifndef LANE_SWPIPE
-#define LANE_SWPIPE 0       // shared-memory loads of row step r+1 issued during row step r (rolled loop, manual pipelining):
-                            // measured on B200: 4 % SLOWER (1.782 vs 1.715 ms, 160 vs 150 registers) -> off
-#endif
-#ifndef LANE_PREFETCH_Q
-#define LANE_PREFETCH_Q 0   // measured on B200: no gain (the set-up stalls are not DRAM latency)
-#endif
 #ifndef LANE_T
 #define LANE_T 128
 #endif
@@ -269,24 +255,6 @@ __device__ __forceinline__ void window_store(const uint32_t (&v)[ROWS][kWin2Word
         for (int w = 0; w < kWin2Words; ++w) dst[(i * kWin2Words + w) * WS] = v[i][w];
 }
 
-// Ten consecutive window pixels of row i (starting at the footprint's first column) as floats.
-template <int WS>
-__device__ __forceinline__ void load_row10(const uint32_t *wp, int i, int sh, float (&row)[G + 1]) {
-    const uint32_t *p = wp + i * kWin2Words * WS;
-    const uint32_t w0 = p[0], w1 = p[WS], w2 = p[2 * WS], w3 = p[3 * WS];
-    const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = __funnelshift_r(w2, w3, sh);
-    row[0] = byte_to_float(b0, 0);
-    row[1] = byte_to_float(b0, 1);
-    row[2] = byte_to_float(b0, 2);
-    row[3] = byte_to_float(b0, 3);
-    row[4] = byte_to_float(b1, 0);
-    row[5] = byte_to_float(b1, 1);
-    row[6] = byte_to_float(b1, 2);
-    row[7] = byte_to_float(b1, 3);
-    row[8] = byte_to_float(b2, 0);
-    row[9] = byte_to_float(b2, 1);
-}
-
 // ---- packed FP32x2 variant of the row load / sample row (sm_100 FMUL2 / FADD2: two IEEE-rounded fp32 operations
 // per instruction, bit-identical to the scalar ones).  A pixel row is kept as five even pairs (0,1)(2,3)..(8,9)
 // and five odd pairs (1,2)(3,4)..(9,10), so that both taps of two adjacent samples are register pairs.
@@ -336,22 +304,6 @@ __device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, int ka, uint32_t 
     p.x = __uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7440u + ka));
     p.y = __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7440u + kb));
     return add2_rn(p, make_float2(-8388608.0f, -8388608.0f));
-}
-
-// (raw window words of row i / their conversion: separate, so that the loads can be issued one row step ahead)
-template <int WS>
-__device__ __forceinline__ void load_row_words(const uint32_t *wp, int i, uint32_t (&w)[4]) {
-    const uint32_t *p = wp + i * kWin2Words * WS;
-    w[0] = p[0], w[1] = p[WS], w[2] = p[2 * WS], w[3] = p[3 * WS];
-}
-
-__device__ __forceinline__ void convert_row10_packed(const uint32_t (&w)[4], int sh, Row2 &row) {
-    const uint32_t b[3] = {__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh)};
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        row.e[j] = bytes_to_float2(b[(2 * j) >> 2], (2 * j) & 3, b[(2 * j + 1) >> 2], (2 * j + 1) & 3);
-        row.o[j] = bytes_to_float2(b[(2 * j + 1) >> 2], (2 * j + 1) & 3, b[(2 * j + 2) >> 2], (2 * j + 2) & 3);
-    }
 }
 
 template <int WS>
@@ -604,9 +556,6 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // Solver kernel.
 // ------------------------------------------------------------------------------------------------
-#ifndef LANE_PREFETCH
-#define LANE_PREFETCH 0
-#endif
 #ifndef LANE_MAXREG
 #define LANE_MAXREG 0
 #endif
@@ -679,31 +628,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         a2 = args.kp2_init[gid];
                     }
                     const unsigned km = __ballot_sync(FULL, keep);
-#if LANE_PREFETCH_Q
-                    if (keep) {
-                        // A queued feature is started a few trips from now: pull what its first set-up will load
-                        // (its templates, streamed exactly once, and the rows of its top-level window) into L2 now,
-                        // with all lanes active, instead of stalling the whole warp on DRAM then.
-                        const char *tp = reinterpret_cast<const char *>(args.templates + ((size_t)(L - 1) * args.tpl_features + (size_t)gid) * kTplStride);
-                        const int tbytes = kTplStride * (int)sizeof(float);  // (the top level's record)
-                        for (int o = 0; o < tbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + tbytes - 1));
-                        const LevelView &tl = pyr.lv[L - 1];
-                        const float px = (float)(a2.x * scale_top), py = (float)(a2.y * scale_top);
-                        if (fabsf(px) < 1.0e6f && fabsf(py) < 1.0e6f) {
-                            const int pwx = (((int)floorf(px) + LO - 1 - kWinSlackL) & ~(kWinAlign - 1));
-                            const int pwy = (int)floorf(py) + LO - 1 - kWinSlackT;
-                            if (window_in_apron(tl, pwx)) {
-                                const uint8_t *pimg = tl.base[1] + (size_t)(gid / args.n_per_pair) * tl.slot;
-#pragma unroll
-                                for (int i = 0; i < kWin2Rows; ++i) {
-                                    const int ry = min(max(pwy + i, 0), tl.rows - 1);
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pimg + (ptrdiff_t)ry * tl.pitch + pwx));
-                                }
-                            }
-                        }
-                    }
-#endif
                     if (keep) {
                         const int pos = (q_tail + __popc(km & ((1u << lane) - 1u))) & (kQueue - 1);
                         sm.q_k1[warp][pos] = a1;
@@ -782,44 +706,12 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 // holding all 41 loads in flight needs ~250 registers and did not pay (profiles/README.md).
                 constexpr int kHalf = kWin2Rows / 2;
                 const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
-#if LANE_ASYNC_SETUP
-                // All copies of the set-up (49 template floats, 72 window words) go global -> shared memory by
-                // cp.async, 4 bytes each because a thread's words are interleaved with its neighbours'; they are in
-                // flight together and land while the grid coordinates of the pass are computed (waited for just
-                // before the pass).  The register-staged version made three dependent round trips per set-up
-                // (template, two window halves) with the whole warp stalled on each: a third of all stall samples.
-                if (new_level) {
-                    const float *tp = args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride;
-                    if (level > 0) {  // the next level's template will be needed a few trips from now
-                        const char *nxt = reinterpret_cast<const char *>(tp) - args.tpl_features * (kTplStride * sizeof(float));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
-                    }
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.i1[0][tid]);
-#pragma unroll
-                    for (int i = 0; i < kI1Count; ++i)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * WS * 4), "l"(tp + i) : "memory");
-                }
-                if (!no_window) {
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.win2[0][tid]);
-#pragma unroll
-                    for (int i = 0; i < kWin2Rows; ++i) {
-                        const int ry = min(max(wy0 + i, 0), lv.rows - 1);
-                        const uint8_t *rp = img2 + (ptrdiff_t)ry * lv.pitch + wx0;
-#pragma unroll
-                        for (int w = 0; w < kWin2Words; ++w)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (i * kWin2Words + w) * WS * 4), "l"(rp + 4 * w)
-                                         : "memory");
-                    }
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-#else
                 if (new_level) {
                     const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride);
                     float4 t[kTplStride / 4];
 #pragma unroll
                     for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
-                    if (!LANE_PREFETCH_Q && level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
+                    if (level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
                         const char *nxt = reinterpret_cast<const char *>(tp) - args.tpl_features * (kTplStride * sizeof(float));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
@@ -841,7 +733,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     window_load<kWin2Rows - kHalf>(img2, lv, wx0, wy0 + kHalf, wv2);
                     window_store<kWin2Rows - kHalf, WS>(wv2, &sm.win2[kHalf * kWin2Words][tid]);
                 }
-#endif
                 need_win = false;
                 state = ST_RUN;
             }
@@ -896,9 +787,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         }
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
-#if LANE_ASYNC_SETUP
-        asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's set-up copies (each thread reads only its own words)
-#endif
         const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & kPMask2) != 0u);
         if (run) {
             const LevelView &lv = pyr.lv[level];
@@ -938,9 +826,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             rowA = rowB;
             load_row10_packed<WS>(wp, 2, sh, rowB);
             sample_row_packed(OMX, XX, wyp[2 * WS], wyp[3 * WS], rowA, rowB, args.one, Sb);
-#if !LANE_UNROLL3
             rowA = rowB;
-#endif
             // One patch row per step: sample row r from pixel rows r, r+1 (PB is loaded here), then the 7 pixels of
             // patch row y = r-2 with centre samples SB = grid row r-1, SA / SC the rows above / below.
             auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[5], const float2 (&SB)[5], float2 (&SC)[5]) {
@@ -964,64 +850,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     s11 = fma(gy, gy, s11);
                 }
             };
-#if LANE_UNROLL3
-            // Three steps per trip with the roles of the three sample rows (and of three pixel-row buffers) rotating
-            // by NAME: no register moves (the rolled loop spent 31 of its 212 instructions on them).  7 steps =
-            // r 2,3,4 / 5,6,7 / 8; the body (~550 instructions) still fits the instruction caches.
-            Row2 rowC;
-#pragma unroll 1
-            for (int r = 2; r < G; r += 3) {
-                step(r, rowB, rowC, Sa, Sb, Sc);      // pixel rows: rowB = r, rowC = r+1
-                if (r + 1 >= G) break;
-                step(r + 1, rowC, rowA, Sb, Sc, Sa);
-                step(r + 2, rowA, rowB, Sc, Sa, Sb);
-            }
-#elif LANE_SWPIPE
-            // Rolled loop, software-pipelined by hand: the 13 shared-memory words of the NEXT row step (window row,
-            // row weights, template row) are loaded while this step computes, so no step starts by waiting for them.
-            uint32_t nw[4];
-            float nomy, nyy, ni1[P];
-            auto prefetch = [&](int r) {
-                load_row_words<WS>(wp, r + 1, nw);
-                nomy = wyp[(2 * r) * WS];
-                nyy = wyp[(2 * r + 1) * WS];
-                const float *i1row = i1p + ((r - 2) * P) * WS;
-#pragma unroll
-                for (int x = 0; x < P; ++x) ni1[x] = i1row[x * WS];
-            };
-            prefetch(2);
-#pragma unroll 1
-            for (int r = 2; r < G; ++r) {
-                convert_row10_packed(nw, sh, rowB);
-                const float omy_r = nomy, yy_r = nyy;
-                float ci1[P];
-#pragma unroll
-                for (int x = 0; x < P; ++x) ci1[x] = ni1[x];
-                if (r + 1 < G) prefetch(r + 1);
-                sample_row_packed(OMX, XX, omy_r, yy_r, rowA, rowB, args.one, Sc);
-                const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
-#pragma unroll
-                for (int x = 0; x < P; ++x) {
-                    const int g = x + 1;
-                    const bool on = !any_masked || (row_on && ((pmx >> x) & 1u));
-                    const double e = (double)(on ? __fadd_rn(ci1[x], -pick(Sb, g)) : 0.f);               // :65-66
-                    const double gx = (double)(on ? __fadd_rn(pick(Sb, g + 1), -pick(Sb, g - 1)) : 0.f);  // :70-71
-                    const double gy = (double)(on ? __fadd_rn(pick(Sc, g), -pick(Sa, g)) : 0.f);          // :72-73
-                    sb0 = fma(e, gx, sb0);
-                    sb1 = fma(e, gy, sb1);
-                    sc = fma(e, e, sc);
-                    s00 = fma(gx, gx, s00);
-                    s01 = fma(gx, gy, s01);
-                    s11 = fma(gy, gy, s11);
-                }
-                rowA = rowB;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    Sa[j] = Sb[j];
-                    Sb[j] = Sc[j];
-                }
-            }
-#else
+            // Rolled on purpose.  Measured alternatives, all slower on B200 (profiles/README.md): the fully unrolled
+            // pass (instruction-fetch bound), three steps per trip with the row roles rotating by name (-11 %
+            // instructions, +3 % time), manual software pipelining of the 13 shared-memory loads (+4 % time).
 #pragma unroll 1
             for (int r = 2; r < G; ++r) {
                 step(r, rowA, rowB, Sa, Sb, Sc);
@@ -1032,7 +863,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     Sb[j] = Sc[j];
                 }
             }
-#endif
 
             if (FAMILIES && (fam & kPMask2)) {
                 // multi-family level: this trip covered one (x family, y family) combination; partial sums
@@ -1083,25 +913,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     }
                     --level;
                     state = ST_LEVEL;
-#if LANE_PREFETCH
-                    {   // warm L1/L2 with what the next set-up will load: the template and the window rows
-                        const LevelView &nl = pyr.lv[level];
-                        const double Sx = (double)k1.x + (double)(k2.x - k1.x), Sy = (double)k1.y + (double)(k2.y - k1.y);
-                        if (fabs(Sx) < 1.0e6 && fabs(Sy) < 1.0e6) {
-                            const int nix = __double2int_rd(Sx + (double)(LO - 1)), niy = __double2int_rd(Sy + (double)(LO - 1));
-                            const int pwx = (nix - kWinSlackL) & ~(kWinAlign - 1), pwy = niy - kWinSlackT;
-                            if (window_in_apron(nl, pwx)) {
-                                const uint8_t *nimg = nl.base[1] + (size_t)img * nl.slot;
-#pragma unroll
-                                for (int i = 0; i < kWin2Rows; ++i) {
-                                    const int ry = min(max(pwy + i, 0), nl.rows - 1);
-                                    const uint8_t *pa = nimg + (ptrdiff_t)ry * nl.pitch + pwx;
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
-                                }
-                            }
-                        }
-                    }
-#endif
                 } else {
                     args.kp2_out[feat] = k2;
                     args.success[feat] = flag ? 1 : 0;

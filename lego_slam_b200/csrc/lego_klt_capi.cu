@@ -41,7 +41,6 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
 constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings)
-constexpr int kMaxSub = 32; // timed sub-ranges of an interleaved run
 constexpr size_t kIoStatsBytes = 256;                       // device counters (kStatCount x 8 bytes, padded)
 constexpr size_t kIoHeadBytes = kIoStatsBytes + 256;        // + work counters (4 x kMaxChunks ints)
 static_assert(kStatCount * sizeof(unsigned long long) <= kIoStatsBytes && 4 * 16 * sizeof(int) <= 256, "io head layout");
@@ -92,10 +91,6 @@ struct lego_klt_batch {
     unsigned long long *h_stats = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ring[kRing][3] = {};  // run r: [0] before pyramid, [1] after pyramid, [2] after solver
-    // interleaved runs (pyramid and template launches alternate per sub-range): [2i], [2i+1] bracket the i-th
-    // pyramid launch; created on first use
-    cudaEvent_t ring_sub[kRing][2 * kMaxSub] = {};
-    int ring_nsub[kRing] = {};
     long long runs = 0;
     int *d_work = nullptr;         // per chunk: [0] lane work counter, [1] deferred count, [2] family count,
                                    // [3] lane<FAMILIES> work counter
@@ -243,9 +238,7 @@ cudaError_t upload_set(lego_klt_batch *b, int set, const uint8_t *src, int img0,
 cudaError_t ingest_set(lego_klt_batch *b, int set, int img0, int nimg, cudaStream_t stream) {
     const size_t img_bytes = (size_t)b->rows * b->step;
     const size_t set_bytes = align_up((size_t)b->B * img_bytes + 256, 256);
-    const uint8_t *landing = b->d_tight + (size_t)set * set_bytes + (size_t)img0 * img_bytes;
     // the funnel-shift loads need a 4-byte aligned base: pass the set base and let the kernel index rows from img0
-    (void)landing;
     return launch_ingest(b->d_tight + (size_t)set * set_bytes, b->view.lv[0], set, img0, nimg, stream);
 }
 
@@ -273,21 +266,8 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     const WarpKernelMaps *maps = maps_override ? maps_override : b->maps;
     int *work = b->d_work + 4 * chunk;
     CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
-    const int ring_slot = ring ? (int)((ring - &b->ring[0][0]) / 3) : 0;
-    if (ring) {
-        b->ring_nsub[ring_slot] = 0;
-        CU_TRY(cudaEventRecord(ring[0], st));
-    }
-    // LANE path on a large range: pyramids and templates go sub-range by sub-range, so that the template kernel
-    // reads img1 pyramids that are still in L2 (a pyramid pass over all 512 images first evicts them: the
-    // template kernel was bound by DRAM latency x outstanding-miss capacity, profiles/README.md); the solver
-    // then runs once over the whole range (a persistent kernel, it wants many features per thread).
-    static const int sub_pairs = [] {
-        const char *e = getenv("LEGO_KLT_SUBRANGE");  // tuning aid; 0 = off
-        return e ? atoi(e) : 0;  // measured: 16/32/64-pair sub-ranges are 16 % / 6 % / 1 % SLOWER than one pass (launch tails)
-    }();
-    const bool interleave = !view_override && sub_pairs > 0 && nimg >= 2 * sub_pairs;
-    if (!view_override && !interleave) {
+    if (ring) CU_TRY(cudaEventRecord(ring[0], st));
+    if (!view_override) {
         CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));  // (row aprons included)
     }
     if (ring) CU_TRY(cudaEventRecord(ring[1], st));
@@ -332,8 +312,6 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         kernel = ((lane7 || lane8) && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !(lane7 || lane8))
         return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the forward 7x7 (-3..3) and 8x8 (-4..3) patches only");
-    if (interleave && !(kernel == LEGO_KLT_KERNEL_LANE && a.n_total > 0))
-        CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
@@ -346,28 +324,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         a.feat_flag = b->d_feat_flag;
         a.scratch = b->d_scratch;
         a.epoch = (int)((b->runs % 0x0fffffff) + 1);
-        if (interleave && kernel == LEGO_KLT_KERNEL_LANE) {
-            int isub = 0;
-            for (int s0 = 0; s0 < nimg; s0 += sub_pairs, ++isub) {
-                const int ns = std::min(sub_pairs, nimg - s0);
-                cudaEvent_t *se = nullptr;
-                if (ring && isub < kMaxSub) {
-                    se = &b->ring_sub[ring_slot][2 * isub];
-                    for (int i = 0; i < 2; ++i)
-                        if (!se[i]) CU_TRY(cudaEventCreate(&se[i]));
-                    b->ring_nsub[ring_slot] = isub + 1;
-                    CU_TRY(cudaEventRecord(se[0], st));
-                }
-                CU_TRY(launch_pyramid(b->plan, b->view, img0 + s0, ns, st));
-                if (se) CU_TRY(cudaEventRecord(se[1], st));
-                SolverArgs as = a;  // same lists and counters, a sub-range of the features
-                as.f0 = (img0 + s0) * b->n_active;
-                as.n_total = ns * b->n_active;
-                CU_TRY(lane8 ? launch_klt_template_p8(view, as, st) : launch_klt_template(view, as, st));
-            }
-        } else {
-            CU_TRY(lane8 ? launch_klt_template_p8(view, a, st) : launch_klt_template(view, a, st));
-        }
+        CU_TRY(lane8 ? launch_klt_template_p8(view, a, st) : launch_klt_template(view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
         CU_TRY(cudaEventRecord(b->ev_fork, st));
@@ -407,14 +364,10 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
 
 // Kernel times of run slot r: pyramid launches (incl. aprons) and everything else (templates + solver).
 cudaError_t run_times(lego_klt_batch *b, int r, float *ms_pyr, float *ms_solver) {
-    float pyr = 0.f, total = 0.f, ms = 0.f;
+    float pyr = 0.f, total = 0.f;
     cudaError_t e = cudaEventElapsedTime(&pyr, b->ring[r][0], b->ring[r][1]);
     if (e != cudaSuccess) return e;
     if ((e = cudaEventElapsedTime(&total, b->ring[r][0], b->ring[r][2])) != cudaSuccess) return e;
-    for (int i = 0; i < b->ring_nsub[r]; ++i) {
-        if ((e = cudaEventElapsedTime(&ms, b->ring_sub[r][2 * i], b->ring_sub[r][2 * i + 1])) != cudaSuccess) return e;
-        pyr += ms;
-    }
     *ms_pyr = pyr;
     *ms_solver = total - pyr;
     return cudaSuccess;
@@ -648,12 +601,9 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     pyramid_plan_destroy(&b->plan);
     for (int i = 0; i < EV_COUNT; ++i)
         if (b->ev[i]) cudaEventDestroy(b->ev[i]);
-    for (int r = 0; r < kRing; ++r) {
+    for (int r = 0; r < kRing; ++r)
         for (int i = 0; i < 3; ++i)
             if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
-        for (int i = 0; i < 2 * kMaxSub; ++i)
-            if (b->ring_sub[r][i]) cudaEventDestroy(b->ring_sub[r][i]);
-    }
     cudaFree(b->d_defer_list);
     cudaFree(b->d_fam_list);
     cudaFree(b->d_templates);
@@ -748,20 +698,10 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
     // Small batches: plain upload -> run -> download.
     // Equal chunks: more / smaller chunks shorten the pipeline tail but cost launches and solver efficiency
-    // (10 chunks with a fine tail measured 6 % slower than 8 equal ones).
+    // (measured: 10 chunks with a fine tail 6 % slower than 8 equal ones; a smaller LAST chunk of 8 or 16 pairs 5 % slower).
     int bounds[kMaxChunks + 1];
     const int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
-    // the work after the LAST upload is not hidden by any copy: an optionally smaller last chunk shortens it
-    static const int tail_pairs = [] {
-        const char *e = getenv("LEGO_KLT_E2E_TAIL");  // tuning aid; 0 = equal chunks
-        return e ? atoi(e) : 0;
-    }();
-    if (tail_pairs > 0 && n_chunks > 1 && tail_pairs < b->B / n_chunks) {
-        for (int c = 0; c < n_chunks; ++c) bounds[c] = (int)((long long)(b->B - tail_pairs) * c / (n_chunks - 1));
-        bounds[n_chunks] = b->B;
-    } else {
-        for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
-    }
+    for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
     if (n_chunks == 1) {
         int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
         if (rc) return rc;

@@ -643,8 +643,7 @@ cudaError_t pyramid_plan_create(int cols, int rows, int levels, const int *pitch
     // ---- bands: the largest top-row band whose staging fits the shared-memory budget; every band's row range
     // at every level goes into a device table (the kernel used to derive it with a chain of dependent loads) ----
     const int top = levels - 1;
-    size_t budget = 48 * 1024;  // measured on B200 (1241x376, L=4): 40-48 KB bands best, 64-100 KB 5 % slower
-    if (const char *e = getenv("LEGO_KLT_PYR_SMEM_KB")) budget = (size_t)atoi(e) * 1024;  // tuning aid
+    const size_t budget = 48 * 1024;  // measured on B200 (1241x376, L=4): 40-48 KB bands best, 64-100 KB 5 % slower
     std::vector<int2> bands;
     for (int tr = 32; tr >= 1; tr >>= 1) {
         int maxr[kMaxLevels] = {0};
