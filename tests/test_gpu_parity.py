@@ -383,3 +383,17 @@ def test_fullres_upload_tracks_like_the_halved_images(tracker, oracle):
     assert_parity(out, succ, ref, rs, l2.shape[1], l2.shape[0], "fullres ingest")
     out2, succ2, _ = tracker.track(l2, r2, k1, k1)
     assert np.array_equal(out.view(np.uint32), out2.view(np.uint32)) and np.array_equal(succ, succ2)
+
+
+@pytest.mark.gpu
+def test_ingest_reproduces_the_committed_cv2_hashes(tracker):
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows.json")) as f:
+        meta = json.load(f)
+    for name, c in meta["ingest"].items():
+        img = np.random.default_rng(c["seed"]).integers(0, 256, size=(c["rows"], c["cols"]), dtype=np.uint8)
+        out = tracker.downscale_half(img)
+        assert list(out.shape) == c["out_shape"], name
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == c["sha256"], name

@@ -60,3 +60,16 @@ def test_ingest_oracle_equals_cv2_nearest_halving(rows, cols):
     ref = cv2.resize(img, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
     got = ingest_np.downscale_half_nearest(img)
     assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_ingest_oracle_reproduces_the_committed_cv2_hashes():
+    """tests/golden/next_rows.json (tools/make_golden_next.py): SHA-256 of cv2's own INTER_NEAREST halving."""
+    import json
+    import os
+    from oracle import ingest_np
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows.json")) as f:
+        meta = json.load(f)
+    for name, c in meta["ingest"].items():
+        img = np.random.default_rng(c["seed"]).integers(0, 256, size=(c["rows"], c["cols"]), dtype=np.uint8)
+        out = ingest_np.downscale_half_nearest(img)
+        assert list(out.shape) == c["out_shape"] and _sha(out) == c["sha256"], name

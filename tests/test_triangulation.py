@@ -151,3 +151,37 @@ def test_gpu_batch_triangulate_uses_the_tracked_keypoints_in_place(tracker):
     pt, ok = batch.triangulate(cam_l, cam_r, 1e-3)
     pt_h, ok_h = tracker.triangulation_stereo(cam_l, cam_r, kp1.reshape(-1, 2), out.reshape(-1, 2), succ.reshape(-1), 1e-3)
     assert np.array_equal(pt.reshape(-1, 3).view(np.uint64), pt_h.view(np.uint64)) and np.array_equal(ok.reshape(-1), ok_h)
+
+
+# ------------------------------------------------------------------ committed golden vectors (tools/make_golden_next.py)
+def _golden_next():
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(gdir, "next_rows.json")) as f:
+        meta = json.load(f)
+    return meta, dict(np.load(os.path.join(gdir, "next_rows.npz")))
+
+
+def test_oracle_reproduces_the_committed_triangulation_vectors():
+    meta, g = _golden_next()
+    est, ok = tri.triangulation(g["kat_poses"], np.c_[g["kat_points"], np.ones(3)])
+    assert ok == bool(g["kat_ok"]) and np.allclose(est, g["kat_pt"], rtol=1e-12, atol=0)
+    k = meta["triangulation"]["kitti"]
+    pts = np.stack([tri.pixel2camera(g["stereo_kl"], k["fx"], k["fy"], k["cx"], k["cy"]),
+                    tri.pixel2camera(g["stereo_kr"], k["fx"], k["fy"], k["cx"], k["cy"])], axis=1)
+    pt, okv, ratio = tri.triangulation_batch([g["stereo_left"], g["stereo_right"]], pts, meta["triangulation"]["thr"])
+    assert_tri_parity(pt, okv, g["stereo_pt"], g["stereo_ok"], g["stereo_ratio"], meta["triangulation"]["thr"], "golden")
+    assert int(okv.sum()) == meta["triangulation"]["n_ok"]
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_the_committed_triangulation_vectors(tracker):
+    meta, g = _golden_next()
+    est, ok = tracker.triangulation(g["kat_poses"], g["kat_points"][None])
+    assert ok[0] == g["kat_ok"] and np.abs(est[0] - g["kat_pt"]).max() <= 1e-9
+    k = meta["triangulation"]["kitti"]
+    cam_l = klt.make_camera(k["fx"], k["fy"], k["cx"], k["cy"], g["stereo_left"])
+    cam_r = klt.make_camera(k["fx"], k["fy"], k["cx"], k["cy"], g["stereo_right"])
+    pt, okv = tracker.triangulation_stereo(cam_l, cam_r, g["stereo_kl"], g["stereo_kr"], None, meta["triangulation"]["thr"])
+    assert_tri_parity(pt, okv, g["stereo_pt"], g["stereo_ok"], g["stereo_ratio"], meta["triangulation"]["thr"], "golden stereo")
