@@ -472,22 +472,25 @@ def run_ours(args):
     seq = sequence_mode(trk, n, args) if world == 1 and not args.no_sequence else None
 
     # The metric text of BASELINE.json says "8x8 patch"; the reference computes 7x7 (src/algorithm.cpp:40,63-64,
-    # SURVEY.md F1), which is what `value` measures.  The literal 8x8 patch (-4..3) beside it, same batch, device-
-    # resident: the LANE solver is compiled for both patches (klt_solver_lane_p8.cu).
-    p88 = None
+    # SURVEY.md F1), which is what `value` measures.  The literal 8x8 patch (-4..3) and the 11x11 patch of the stress
+    # configuration (-5..5) beside it, same batch, device-resident (one batch in flight): the LANE solver is compiled
+    # for all three patches (klt_solver_lane.cu, _p8.cu, _p11.cu).
+    other_patches = None
     if world == 1 and not args.no_sequence:
-        params88 = klt.make_params(levels=LEVELS, patch_lo=-4, patch_hi=3)
-        batch.run(params88)
-        trk.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(3):
-            batch.run(params88)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms88 = e0.elapsed_time(e1) / 3
-        p88 = {"patch": [-4, 3], "value": n_tracks / (ms88 * 1e-3), "unit": "tracks/s", "ms_per_step": ms88,
-               "kernel": "klt_template_kernel + klt_lane_kernel compiled for offsets -4..3 (96-thread CTAs, 3 per SM)"}
+        other_patches = {}
+        for name, (plo, phi) in (("8x8", (-4, 3)), ("11x11", (-5, 5))):
+            pp = klt.make_params(levels=LEVELS, patch_lo=plo, patch_hi=phi)
+            batch.run(pp)
+            trk.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                batch.run(pp)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            msp = e0.elapsed_time(e1) / 3
+            other_patches[name] = {"patch": [plo, phi], "value": n_tracks / (msp * 1e-3), "unit": "tracks/s",
+                                   "ms_per_step": msp}
 
     value = world * n_tracks * args.steps / (ms_total * 1e-3)
     line = {
@@ -525,7 +528,7 @@ def run_ours(args):
                           "points_per_s": world * n_tracks / (tri_ms * 1e-3), "ms_per_call": tri_ms,
                           "d2h_bytes_per_call": int(tri_pt.nbytes + tri_ok.nbytes), "n_accepted": int(tri_ok.sum())},
         "sequence_mode": seq,
-        "patch_8x8": p88,
+        "other_patches": other_patches,
         "host": {"numa_binding": numa, "e2e_wall_ms_per_step": e2e_wall_s * 1e3 / args.steps},
         "cpu_baseline": cpu,
         "clocks": clocks,

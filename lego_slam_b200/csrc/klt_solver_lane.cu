@@ -51,9 +51,8 @@ namespace legoklt {
 
 namespace {
 
-// Patch bounds are compile-time: this file is compiled once per supported patch (klt_solver_lane_p8.cu includes it
-// with LANE_PATCH_LO/HI = -4/3 and a symbol suffix).  The code below is written for P <= 8: five sample pairs per
-// grid row (G <= 10), 11 window pixels per row from four words, 8-bit family masks.
+// Patch bounds are compile-time: this file is compiled once per supported patch (klt_solver_lane_p8.cu and
+// klt_solver_lane_p11.cu include it with other LANE_PATCH_LO/HI, window / CTA shapes and a symbol suffix).
 #ifndef LANE_PATCH_LO
 #define LANE_PATCH_LO (-3)
 #define LANE_PATCH_HI 3
@@ -65,9 +64,13 @@ namespace {
 #define LANE_CAT(a, b) LANE_CAT2(a, b)
 #define LANE_FN(name) LANE_CAT(name, LANE_SUFFIX)
 constexpr int LO = LANE_PATCH_LO, HI = LANE_PATCH_HI, P = HI - LO + 1, G = P + 2;
-static_assert(P >= 3 && P <= 8, "the LANE kernel's row structure (5 pairs, 4 window words) covers patches up to 8x8");
+static_assert(P >= 3 && P <= 12, "family masks hold 12 bits per axis");
+constexpr int kNP = (G + 1) / 2;                               // sample pairs per grid row: samples (2j, 2j+1), j < kNP
+constexpr int kRowWords = (2 * kNP + 1 + 3) / 4 + 1;           // window words a row step reads: 2 kNP + 1 pixels at a
+                                                              // byte offset of 0..3
 constexpr unsigned kPMask = (1u << P) - 1u;                    // one bit per patch column / row
-constexpr unsigned kPMask2 = kPMask | (kPMask << 8);           // x mask | y mask << 8 (family bookkeeping)
+constexpr int kFamY = 12, kFamSub = 24;                        // family word: x mask | y mask << kFamY | sub-pass << kFamSub
+constexpr unsigned kPMask2 = kPMask | (kPMask << kFamY);
 #ifndef LANE_WROWS
 #define LANE_WROWS (G + 3)
 #endif
@@ -259,7 +262,7 @@ __device__ __forceinline__ void window_store(const uint32_t (&v)[ROWS][kWin2Word
 // per instruction, bit-identical to the scalar ones).  A pixel row is kept as five even pairs (0,1)(2,3)..(8,9)
 // and five odd pairs (1,2)(3,4)..(9,10), so that both taps of two adjacent samples are register pairs.
 struct Row2 {
-    float2 e[5], o[5];
+    float2 e[kNP], o[kNP];
 };
 
 // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen with the __fmul2_rn/__fadd2_rn intrinsics and with
@@ -309,21 +312,24 @@ __device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, int ka, uint32_t 
 template <int WS>
 __device__ __forceinline__ void load_row10_packed(const uint32_t *wp, int i, int sh, Row2 &row) {
     const uint32_t *p = wp + i * kWin2Words * WS;
-    const uint32_t w0 = p[0], w1 = p[WS], w2 = p[2 * WS], w3 = p[3 * WS];
-    const uint32_t b[3] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh)};
+    uint32_t w[kRowWords], b[kRowWords - 1];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
+    for (int k = 0; k < kRowWords; ++k) w[k] = p[k * WS];
+#pragma unroll
+    for (int k = 0; k < kRowWords - 1; ++k) b[k] = __funnelshift_r(w[k], w[k + 1], sh);
+#pragma unroll
+    for (int j = 0; j < kNP; ++j) {
         row.e[j] = bytes_to_float2(b[(2 * j) >> 2], (2 * j) & 3, b[(2 * j + 1) >> 2], (2 * j + 1) & 3);
         row.o[j] = bytes_to_float2(b[(2 * j + 1) >> 2], (2 * j + 1) & 3, b[(2 * j + 2) >> 2], (2 * j + 2) & 3);
     }
 }
 
 // Samples g = 2j, 2j+1 of one grid row (algorithm.h:51-56 per sample, products and sums individually rounded).
-__device__ __forceinline__ void sample_row_packed(const float2 (&OMX)[5], const float2 (&XX)[5], float omy_r, float yy_r,
-                                                  const Row2 &A, const Row2 &B, float one, float2 (&out)[5]) {
+__device__ __forceinline__ void sample_row_packed(const float2 (&OMX)[kNP], const float2 (&XX)[kNP], float omy_r, float yy_r,
+                                                  const Row2 &A, const Row2 &B, float one, float2 (&out)[kNP]) {
     const float2 omy2 = make_float2(omy_r, omy_r), yy2 = make_float2(yy_r, yy_r);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
+    for (int j = 0; j < kNP; ++j) {
         float2 r = mul2_rn(mul2_rn(OMX[j], omy2), A.e[j]);
         r = add2_product(r, mul2_rn(mul2_rn(XX[j], omy2), A.o[j]), one);
         r = add2_product(r, mul2_rn(mul2_rn(OMX[j], yy2), B.e[j]), one);
@@ -332,7 +338,7 @@ __device__ __forceinline__ void sample_row_packed(const float2 (&OMX)[5], const 
     }
 }
 
-__device__ __forceinline__ float pick(const float2 (&S)[5], int g) { return (g & 1) ? S[g >> 1].y : S[g >> 1].x; }
+__device__ __forceinline__ float pick(const float2 (&S)[kNP], int g) { return (g & 1) ? S[g >> 1].y : S[g >> 1].x; }
 
 __device__ __noinline__ float sample_flat_cold(const uint8_t *img, const LevelView &lv, float x, float y) {
     return sample_flat(img, lv, x, y);
@@ -405,32 +411,27 @@ __device__ __forceinline__ float level_coord(float k0, int L, int level) {
 // Template kernel: I1 patch of every (feature, level).  Item i -> level = L-1 - i / n_total (coarse
 // levels first), feature = i % n_total, so a warp works on neighbouring features of one level.
 // ------------------------------------------------------------------------------------------------
-// Ten consecutive pixels starting at byte `ox` (0..22) of a 32-byte row held in two uint4 registers: the
-// word offset ox>>2 (0..5) is applied with a 3-stage select network (registers cannot be indexed
+// kTplPx = P + 2 consecutive pixels starting at byte `ox` (2..17) of a 32-byte row held in two uint4 registers: the
+// word offset ox>>2 (0..4) is applied with a 3-stage select network (registers cannot be indexed
 // dynamically), the byte offset with funnel shifts.  No shared memory: the first version of this kernel
 // bounced every row through shared memory and was MIO-throttled (profiles/README.md).
-__device__ __forceinline__ void row10_from_regs(const uint4 &q0, const uint4 &q1, int k, int sh, float (&row)[G + 1]) {
+constexpr int kTplPx = P + 2;
+constexpr int kTplWords = (kTplPx + 3) / 4 + 1;   // words holding kTplPx pixels at a byte offset of 0..3
+__device__ __forceinline__ void row_from_regs(const uint4 &q0, const uint4 &q1, int k, int sh, float (&row)[G + 1]) {
     const uint32_t w[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0u};
     const bool k4 = (k & 4) != 0, k2 = (k & 2) != 0, k1 = (k & 1) != 0;
-    uint32_t t[5], o[4];
+    uint32_t t[kTplWords + 1], o[kTplWords], b[kTplWords - 1];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const uint32_t a = w[j], b2 = w[min(j + 2, 8)], b4 = w[min(j + 4, 8)];
+    for (int j = 0; j < kTplWords + 1; ++j) {
+        const uint32_t a = w[min(j, 8)], b2 = w[min(j + 2, 8)], b4 = w[min(j + 4, 8)];
         t[j] = k4 ? b4 : (k2 ? b2 : a);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = k1 ? t[j + 1] : t[j];
-    const uint32_t b0 = __funnelshift_r(o[0], o[1], sh), b1 = __funnelshift_r(o[1], o[2], sh), b2 = __funnelshift_r(o[2], o[3], sh);
-    row[0] = byte_to_float(b0, 0);
-    row[1] = byte_to_float(b0, 1);
-    row[2] = byte_to_float(b0, 2);
-    row[3] = byte_to_float(b0, 3);
-    row[4] = byte_to_float(b1, 0);
-    row[5] = byte_to_float(b1, 1);
-    row[6] = byte_to_float(b1, 2);
-    row[7] = byte_to_float(b1, 3);
-    row[8] = byte_to_float(b2, 0);
-    row[9] = byte_to_float(b2, 1);
+    for (int j = 0; j < kTplWords; ++j) o[j] = k1 ? t[j + 1] : t[j];
+#pragma unroll
+    for (int j = 0; j < kTplWords - 1; ++j) b[j] = __funnelshift_r(o[j], o[j + 1], sh);
+#pragma unroll
+    for (int i = 0; i < kTplPx; ++i) row[i] = byte_to_float(b[i >> 2], i & 3);
 }
 
 template <int T>
@@ -488,9 +489,13 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
                 omy[y + 1] = ob[y + 1];
             }
     }
-    float buf[kTplStride];
+    // Patches up to 8x8 collect the record in registers and store it as float4; larger ones (121 values) go to the
+    // staging memory value by value instead, or the kernel would not fit the register file.
+    constexpr bool kDirect = (kI1Count > 64);
+    float *mine_f = reinterpret_cast<float *>(&stage[warp][lane * (kTplStride / 4)]);
+    float buf[kDirect ? 4 : kTplStride];
 #pragma unroll
-    for (int i = 0; i < kTplStride; ++i) buf[i] = 0.f;
+    for (int i = 0; i < (kDirect ? 4 : kTplStride); ++i) buf[i] = 0.f;
     if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15, 32);
     // Ownership of the feature, decided by its levels with an atomicMax (values of earlier runs are smaller):
     //   4*epoch + 2 -> exact warp kernel (irregular on some level), 4*epoch + 1 -> lane<FAMILIES> (two
@@ -509,36 +514,42 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         if (atomicMax(&args.feat_flag[f], tag) < tag) args.fam_list[atomicAdd(args.fam_count, 1)] = f;
     }
     if (regular) {
-        // the 7x7 centre of the 9x9 grid needs image rows iyn+1 .. iyn+8 and columns ixn+1 .. ixn+8
+        // the PxP centre of the GxG grid needs image rows iyn+1 .. iyn+P+1 and columns ixn+1 .. ixn+P+1
         const int wx0 = (ixn - 2) & ~15, wy0 = iyn + 1;
         const int ox = ixn - wx0;
         const int k = ox >> 2, sh = (ox & 3) * 8;
         const uint8_t *img1 = lv.base[0] + (size_t)img * lv.slot;
         uint4 q[kTplRows][2];
 #pragma unroll
-        for (int i = 0; i < kTplRows; ++i) {  // all 16 loads in flight; rows clamped, columns from the aprons
+        for (int i = 0; i < kTplRows; ++i) {  // all loads in flight; rows clamped, columns from the aprons
             const int ry = min(max(wy0 + i, 0), lv.rows - 1);
             const uint4 *rp = reinterpret_cast<const uint4 *>(img1 + (ptrdiff_t)ry * lv.pitch + wx0);
             q[i][0] = __ldg(rp);
             q[i][1] = __ldg(rp + 1);
         }
         float rowA[G + 1], rowB[G + 1];
-        row10_from_regs(q[0][0], q[0][1], k, sh, rowA);
+        row_from_regs(q[0][0], q[0][1], k, sh, rowA);
 #pragma unroll
         for (int y = 0; y < P; ++y) {
-            row10_from_regs(q[y + 1][0], q[y + 1][1], k, sh, rowB);
+            row_from_regs(q[y + 1][0], q[y + 1][1], k, sh, rowB);
 #pragma unroll
-            for (int x = 0; x < P; ++x)
-                buf[y * P + x] = bilerp(omx[x + 1], xx[x + 1], omy[y + 1], yy[y + 1], rowA[x + 1], rowA[x + 2], rowB[x + 1],
-                                        rowB[x + 2]);
+            for (int x = 0; x < P; ++x) {
+                const float v = bilerp(omx[x + 1], xx[x + 1], omy[y + 1], yy[y + 1], rowA[x + 1], rowA[x + 2], rowB[x + 1],
+                                       rowB[x + 2]);
+                if (kDirect) mine_f[y * P + x] = v;
+                else buf[y * P + x] = v;
+            }
 #pragma unroll
             for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
         }
-        buf[kI1Count] = 1.f;  // regularity flag
+        if (kDirect) mine_f[kI1Count] = 1.f;  // regularity flag
+        else buf[kI1Count] = 1.f;
     }
-    float4 *mine = &stage[warp][lane * (kTplStride / 4)];
+    if (!kDirect) {
+        float4 *mine = &stage[warp][lane * (kTplStride / 4)];
 #pragma unroll
-    for (int i = 0; i < kTplStride / 4; ++i) mine[i] = make_float4(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]);
+        for (int i = 0; i < kTplStride / 4; ++i) mine[i] = make_float4(buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]);
+    }
     __syncwarp();
     // the warp's first item is feature args.f0 + (idx - lane) of this level; n_warp of its items are valid
     const int idx0 = idx - lane;
@@ -691,7 +702,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         double e0, e1;
                         axis_families(kx, mBx, e0);  // (more than one eps per axis was filtered by the template kernel)
                         axis_families(ky, mBy, e1);
-                        fam = mBx | (mBy << 8);
+                        fam = mBx | (mBy << kFamY);
                     }
                 }
                 const double Sx = (double)kx + dx, Sy = (double)ky + dy;
@@ -749,7 +760,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             float yy[G], omy[G];
             double kxd = (double)kx, kyd = (double)ky;
             if (FAMILIES && (fam & kPMask2)) {  // this sub-pass works on one (x family, y family) combination
-                const unsigned mBx = fam & kPMask, mBy = (fam >> 8) & kPMask, sub = (fam >> 16) & 3u;
+                const unsigned mBx = fam & kPMask, mBy = (fam >> kFamY) & kPMask, sub = (fam >> kFamSub) & 3u;
                 const bool fx = mBx && (sub & 1u), fy = mBy && (mBx ? (sub >> 1) : (sub & 1u));
                 if (fx) {
                     const int c = LO + __ffs(mBx) - 1;
@@ -810,10 +821,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const uint32_t *wp = &sm.win2[(iyn - wy0) * kWin2Words + (ox >> 2)][tid];
             const float *wyp = &sm.wy[0][tid];
             Row2 rowA, rowB;
-            float2 Sa[5], Sb[5], Sc[5];  // sample rows r-2, r-1, r as pairs (2j, 2j+1); rotated by register moves
-            float2 OMX[5], XX[5];
+            float2 Sa[kNP], Sb[kNP], Sc[kNP];  // sample rows r-2, r-1, r as pairs (2j, 2j+1); rotated by register moves
+            float2 OMX[kNP], XX[kNP];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
+            for (int j = 0; j < kNP; ++j) {
                 OMX[j] = make_float2(omx[2 * j], 2 * j + 1 < G ? omx[2 * j + 1] : 0.f);
                 XX[j] = make_float2(xx[2 * j], 2 * j + 1 < G ? xx[2 * j + 1] : 0.f);
             }
@@ -829,7 +840,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             rowA = rowB;
             // One patch row per step: sample row r from pixel rows r, r+1 (PB is loaded here), then the 7 pixels of
             // patch row y = r-2 with centre samples SB = grid row r-1, SA / SC the rows above / below.
-            auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[5], const float2 (&SB)[5], float2 (&SC)[5]) {
+            auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[kNP], const float2 (&SB)[kNP], float2 (&SC)[kNP]) {
                 load_row10_packed<WS>(wp, r + 1, sh, PB);
                 sample_row_packed(OMX, XX, wyp[(2 * r) * WS], wyp[(2 * r + 1) * WS], PA, PB, args.one, SC);
                 const float *i1row = i1p + ((r - 2) * P) * WS;
@@ -858,7 +869,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 step(r, rowA, rowB, Sa, Sb, Sc);
                 rowA = rowB;
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
+                for (int j = 0; j < kNP; ++j) {
                     Sa[j] = Sb[j];
                     Sb[j] = Sc[j];
                 }
@@ -867,10 +878,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             if (FAMILIES && (fam & kPMask2)) {
                 // multi-family level: this trip covered one (x family, y family) combination; partial sums
                 // wait in global scratch until the last combination has been added (rare, so out of line)
-                const unsigned sub = (fam >> 16) & 3u;
-                const unsigned nsub = ((fam & kPMask) ? 2u : 1u) * ((fam & (kPMask << 8)) ? 2u : 1u);
+                const unsigned sub = (fam >> kFamSub) & 3u;
+                const unsigned nsub = ((fam & kPMask) ? 2u : 1u) * ((fam & (kPMask << kFamY)) ? 2u : 1u);
                 solve_now = multi_family_step(parked, sub, nsub, sb0, sb1, sc, s00, s01, s11);
-                fam = (fam & kPMask2) | (solve_now ? 0u : ((sub + 1u) << 16));
+                fam = (fam & kPMask2) | (solve_now ? 0u : ((sub + 1u) << kFamSub));
             }
             }
             if (solve_now) {
@@ -933,7 +944,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
 constexpr int kLaneThreads = LANE_T;
 constexpr int kLaneMinCtas = LANE_CTAS;
-constexpr int kTplThreads = 128;
+#ifndef LANE_TPL_T
+#define LANE_TPL_T 128
+#endif
+constexpr int kTplThreads = LANE_TPL_T;
 
 }  // namespace
 

@@ -97,6 +97,7 @@ struct lego_klt_batch {
     int *d_defer_list = nullptr;   // [B * n_cap]
     int *d_fam_list = nullptr;     // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
+    size_t templates_bytes = 0;
     int *d_feat_flag = nullptr;    // LANE path: per-feature 'handed to the warp kernel' flag
     double *d_scratch = nullptr;   // LANE kernel: per-thread partial sums of multi-family levels
     cudaStream_t side = nullptr;   // deferred features run here, concurrently with the lane kernel
@@ -242,13 +243,22 @@ cudaError_t ingest_set(lego_klt_batch *b, int set, int img0, int nimg, cudaStrea
     return launch_ingest(b->d_tight + (size_t)set * set_bytes, b->view.lv[0], set, img0, nimg, stream);
 }
 
-int ensure_lane_buffers(lego_klt_batch *b) {
-    if (b->d_templates) return LEGO_KLT_OK;
+int ensure_lane_buffers(lego_klt_batch *b, size_t template_bytes) {
+    // templates: sized for the patch in hand, re-allocated if a larger patch follows
+    if (template_bytes > b->templates_bytes) {
+        CU_TRY(cudaStreamSynchronize(b->ctx->stream));
+        if (b->d_templates) cudaFree(b->d_templates);
+        b->d_templates = nullptr;
+        b->templates_bytes = 0;
+        CU_TRY(cudaMalloc(&b->d_templates, template_bytes));
+        b->templates_bytes = template_bytes;
+    }
+    if (b->d_feat_flag) return LEGO_KLT_OK;
     const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
-    // (sized for the larger of the two compiled patch variants)
-    CU_TRY(cudaMalloc(&b->d_templates, std::max(lane_template_bytes((int)cap, b->levels), lane_template_bytes_p8((int)cap, b->levels))));
     CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
-    CU_TRY(cudaMalloc(&b->d_scratch, std::max(lane_scratch_bytes(b->ctx->sm_count), lane_scratch_bytes_p8(b->ctx->sm_count))));
+    const size_t scratch = std::max(std::max(lane_scratch_bytes(b->ctx->sm_count), lane_scratch_bytes_p8(b->ctx->sm_count)),
+                                    lane_scratch_bytes_p11(b->ctx->sm_count));
+    CU_TRY(cudaMalloc(&b->d_scratch, scratch));
     CU_TRY(cudaMemset(b->d_feat_flag, 0, cap * sizeof(int)));
     CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -307,24 +317,31 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     // AUTO: the thread-per-feature LANE kernel needs tens of thousands of features to fill the machine (57k resident
     // threads); below ~4k features of one call the warp-per-feature kernel has the lower latency (measured, 1241x376:
     // n = 2000: 0.24 vs 0.31 ms per call, n = 5000: equal, n = 20000: 0.70 vs 0.42 ms).  Same fidelity contract.
-    const bool lane7 = lane_kernel_supports(a), lane8 = lane_kernel_supports_p8(a);
+    // the LANE solver is compiled for three patches (klt_solver_lane*.cu): 0 = none, else the patch width
+    const int lane_patch = lane_kernel_supports(a) ? 7 : lane_kernel_supports_p8(a) ? 8 : lane_kernel_supports_p11(a) ? 11 : 0;
     if (kernel == LEGO_KLT_KERNEL_AUTO)
-        kernel = ((lane7 || lane8) && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
-    if (kernel == LEGO_KLT_KERNEL_LANE && !(lane7 || lane8))
-        return fail(LEGO_KLT_ERR_UNSUPPORTED, "LANE kernel supports the forward 7x7 (-3..3) and 8x8 (-4..3) patches only");
+        kernel = (lane_patch && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
+    if (kernel == LEGO_KLT_KERNEL_LANE && !lane_patch)
+        return fail(LEGO_KLT_ERR_UNSUPPORTED,
+                    "LANE kernel: forward mode with the 7x7 (-3..3), 8x8 (-4..3) or 11x11 (-5..5) patch only");
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(view, maps, a, ctx->sm_count, st));
     } else if (a.n_total > 0) {
-        int rc = ensure_lane_buffers(b);
+        const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
+        int rc = ensure_lane_buffers(b, lane_patch == 7   ? lane_template_bytes((int)cap, b->levels)
+                                        : lane_patch == 8 ? lane_template_bytes_p8((int)cap, b->levels)
+                                                          : lane_template_bytes_p11((int)cap, b->levels));
         if (rc) return rc;
         a.templates = b->d_templates;
         a.tpl_features = (unsigned long long)b->B * (unsigned long long)(b->n_cap > 0 ? b->n_cap : 1);
         a.feat_flag = b->d_feat_flag;
         a.scratch = b->d_scratch;
         a.epoch = (int)((b->runs % 0x0fffffff) + 1);
-        CU_TRY(lane8 ? launch_klt_template_p8(view, a, st) : launch_klt_template(view, a, st));
+        CU_TRY(lane_patch == 7   ? launch_klt_template(view, a, st)
+               : lane_patch == 8 ? launch_klt_template_p8(view, a, st)
+                                 : launch_klt_template_p11(view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
         CU_TRY(cudaEventRecord(b->ev_fork, st));
@@ -334,7 +351,9 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         aw.list_count = a.defer_count;
         CU_TRY(launch_klt_warp(view, maps, aw, ctx->sm_count, b->side));
         CU_TRY(cudaEventRecord(b->ev_join, b->side));
-        CU_TRY(lane8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st) : launch_klt_lane(view, a, ctx->sm_count, st));
+        CU_TRY(lane_patch == 7   ? launch_klt_lane(view, a, ctx->sm_count, st)
+               : lane_patch == 8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st)
+                                 : launch_klt_lane_p11(view, a, ctx->sm_count, st));
         CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
     }
     if (ring) CU_TRY(cudaEventRecord(ring[2], st));

@@ -15,11 +15,11 @@ FAST_KERNELS = [klt.KERNEL_WARP, klt.KERNEL_LANE]
 
 
 def _supported(kernel, kw):
-    """The LANE kernel is compiled for the reference's patch (7x7, -3..3) and for the 8x8 patch of the metric text
-    (-4..3), forward mode."""
+    """The LANE kernel is compiled for the reference's patch (7x7, -3..3), the 8x8 patch of the metric text (-4..3)
+    and the 11x11 stress patch (-5..5), forward mode."""
     if kernel != klt.KERNEL_LANE:
         return True
-    return (kw.get("patch_lo", -3), kw.get("patch_hi", 3)) in ((-3, 3), (-4, 3)) and not kw.get("inverse", False)
+    return (kw.get("patch_lo", -3), kw.get("patch_hi", 3)) in ((-3, 3), (-4, 3), (-5, 5)) and not kw.get("inverse", False)
 
 
 def _iters(st, levels):
@@ -309,21 +309,22 @@ def test_lane_kernel_rejects_unsupported_configurations(tracker):
     with pytest.raises(_lib.KltError):
         tracker.track(img, img, kp, kp, klt.make_params(levels=2, inverse=True, kernel=klt.KERNEL_LANE))
     with pytest.raises(_lib.KltError):
-        tracker.track(img, img, kp, kp, klt.make_params(levels=2, patch_lo=-5, patch_hi=5, kernel=klt.KERNEL_LANE))
+        tracker.track(img, img, kp, kp, klt.make_params(levels=2, patch_lo=-6, patch_hi=6, kernel=klt.KERNEL_LANE))
 
 
 @pytest.mark.gpu
-def test_lane_kernel_8x8_patch_on_a_large_batch_equals_exact_kernel(tracker):
-    """The 8x8 (-4..3) instance of the LANE kernel (the patch BASELINE.json's metric text names) against the
-    bit-exact EXACT kernel on a batch large enough to fill the persistent kernel: flags equal, positions within the
-    contract, identical iteration counts."""
+@pytest.mark.parametrize("lo,hi", [(-4, 3), (-5, 5)])
+def test_lane_kernel_other_patches_on_a_large_batch_equal_exact_kernel(tracker, lo, hi):
+    """The 8x8 (-4..3: the patch BASELINE.json's metric text names) and 11x11 (-5..5: the stress configuration)
+    instances of the LANE kernel against the bit-exact EXACT kernel on a batch large enough to fill the persistent
+    kernel: flags equal, positions within the contract, identical iteration counts."""
     B, rows, cols, n = 12, 376, 1241, 2000
     imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 2000)
     res = {}
     for name, k in (("exact", klt.KERNEL_EXACT), ("lane", klt.KERNEL_LANE), ("auto", klt.KERNEL_AUTO)):
         batch = tracker.batch(B, rows, cols, n, levels=4)
         batch.upload(imgs1, imgs2, kp1, kp2)
-        batch.run(klt.make_params(patch_lo=-4, patch_hi=3, kernel=k))
+        batch.run(klt.make_params(patch_lo=lo, patch_hi=hi, kernel=k))
         o, s_, st = batch.download()
         res[name] = (o.copy(), s_.copy(), _iters(st, 4))
     eo, es, ei = res["exact"]
