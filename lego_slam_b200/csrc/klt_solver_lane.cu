@@ -1,13 +1,16 @@
 // klt_solver_lane.cu -- LEGO_KLT_KERNEL_LANE: one THREAD per feature, persistent per-thread state
-// machine, all pyramid levels fused (sm_100a).  7x7 patch, forward mode (the reference's call-site
-// configuration: src/frontend_g2o.cpp:473,515 with src/algorithm.cpp:40 half_patch_size = 3).
+// machine, all pyramid levels fused (sm_100a).  Forward mode (the reference's call sites pass inverse = false:
+// src/frontend_g2o.cpp:473,515); the patch bounds are compile-time and this source is compiled once per patch:
+// here 7x7 = -3..3 (src/algorithm.cpp:40 half_patch_size = 3), in klt_solver_lane_p8.cu 8x8 = -4..3, in
+// klt_solver_lane_p11.cu 11x11 = -5..5.  The numbers quoted below are those of the 7x7 instance.
 //
 // Replaces LKOpticalFlow1Layer + LKOpticalFlowTracker::calcLKOpticalFlow (src/algorithm.cpp:11-125)
 // and the coarse-to-fine loop of LKOpticalFlow4Layer (:158-205).  Two kernels:
 //
-//   klt_template_kernel  one thread per (feature, level): the 7x7 template patch I1 of
+//   klt_template_kernel  one thread per (feature, level): the template patch I1 of
 //                        src/algorithm.cpp:65 (GetPixelValue(img1, kx+x, ky+y)), constant over the
-//                        Gauss-Newton passes of a level, written once as 49 floats + a regularity flag.
+//                        Gauss-Newton passes of a level, written once as P*P floats + a regularity flag
+//                        (level-major records, transposed through shared memory for coalesced stores).
 //   klt_lane_kernel      one thread per feature: all passes of all levels.
 //
 // Why not warp-per-feature (measured, profiles/r01_*): that mapping spends ~850 warp instructions per
@@ -17,8 +20,7 @@
 // is removed by a state machine: each trip of the main loop is exactly one pass for every runnable
 // thread; a thread that converges moves to its next level / next feature while its neighbours keep
 // iterating.  Level set-up (template fetch + img2 window staging) is a per-thread, divergent section run
-// whenever at least LANE_BATCH threads of the warp need it (measured best: 1 with three CTAs per SM, whose
-// 12 warps hide the set-up's memory round trips; 10 with two CTAs).
+// whenever at least LANE_BATCH threads of the warp need it (measured best: 1 with three CTAs per SM; 10 with two).
 //
 // Shared memory, per thread, word-interleaved  [word][T+1]  (bank = (word + thread) % 32, so a warp
 // reading "its" word w is conflict-free):  img2 window 24x12 bytes (8-byte aligned origin; the border
