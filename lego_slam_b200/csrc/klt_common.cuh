@@ -78,6 +78,8 @@ struct SolverArgs {
     int inverse;
     int has_initial;
     double eps;
+    double eps_sq;            // smallest double whose correctly rounded sqrt is >= eps: sqrt(x) < eps  <=>  x < eps_sq
+                              // (sqrt is monotone), so the fast kernels test |update|^2 and skip the fp64 sqrt
     float one;                // 1.0f, opaque to the compiler (see add2_product in klt_solver_lane.cu)
     int debug_flags;          // LEGO_KLT_DEBUG env: 1 = never use the TMA fast path, 2 = count TMA timeouts instead of trapping
     // Optional work list (used for the features the LANE kernel defers): feature ids and their count.

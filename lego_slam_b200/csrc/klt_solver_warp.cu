@@ -380,7 +380,7 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 dy = __dadd_rn(dy, u1);
                 lastCost = cost;
                 succ = true;
-                if (sqrt(__dadd_rn(__dmul_rn(u0, u0), __dmul_rn(u1, u1))) < args.eps) break;  // :113
+                if (__dadd_rn(__dmul_rn(u0, u0), __dmul_rn(u1, u1)) < args.eps_sq) break;  // :113
             }
 
             if (lane == 0) {

@@ -296,6 +296,16 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.inverse = params->inverse;
     a.has_initial = params->has_initial;
     a.eps = params->eps;
+    {   // threshold on the squared norm equivalent to `update.norm() < eps` (src/algorithm.cpp:113), see SolverArgs
+        double c = params->eps * params->eps;
+        if (params->eps > 0 && std::isfinite(c) && c > 0) {
+            while (std::sqrt(std::nextafter(c, 0.0)) >= params->eps) c = std::nextafter(c, 0.0);
+            while (std::sqrt(c) < params->eps) c = std::nextafter(c, INFINITY);
+        } else {
+            c = (params->eps > 0) ? INFINITY : 0.0;  // eps <= 0: never converged by the norm test
+        }
+        a.eps_sq = c;
+    }
     a.one = 1.0f;
     {
         const char *dbg = getenv("LEGO_KLT_DEBUG");
