@@ -22,10 +22,9 @@
 // iterating.  Level set-up (template fetch + img2 window staging) is a per-thread, divergent section run
 // whenever at least LANE_BATCH threads of the warp need it (measured best: 1 with three CTAs per SM; 10 with two).
 //
-// Shared memory, per thread, word-interleaved  [word][T+1]  (bank = (word + thread) % 32, so a warp
-// reading "its" word w is conflict-free):  img2 window 24x12 bytes (8-byte aligned origin; the border
-// semantics come from the row aprons), template 49 floats, 18 row weights -- 556 bytes per thread, so that
-// three CTAs of 128 threads fit an SM.
+// Shared memory, per thread, in 16-byte granules  [granule][T]:  img2 window 12 rows x 32 bytes (16-byte aligned
+// origin; the border semantics come from the row aprons), template 7 rows x 8 floats, 18 row weights -- 688 bytes
+// per thread, three CTAs of 96 threads per SM.  A level set-up is 38 16-byte cp.async copies from global memory.
 //
 // Bit-fidelity contract (same as the warp kernel): every fp32 value entering the sums is bit-identical
 // to the reference's; only the ORDER of the fp64 additions differs (row-major here, x-outer there; all
@@ -77,34 +76,37 @@ constexpr unsigned kPMask2 = kPMask | (kPMask << kFamY);
 #define LANE_WROWS (G + 3)
 #endif
 #ifndef LANE_WWORDS
-#define LANE_WWORDS 6
-#endif
-#ifndef LANE_PAD
-#define LANE_PAD 0
+#define LANE_WWORDS 8
 #endif
 #ifndef LANE_QUEUE
 #define LANE_QUEUE 32
 #endif
-// img2 window per thread: LANE_WROWS rows x LANE_WWORDS*4 bytes.  8 words: origin aligned to 16 bytes (two 16-byte
-// loads per row); 6 words: origin aligned to 8 bytes (three 8-byte loads per row) -- the smaller footprint lets
-// three CTAs of 128 threads share an SM.
+// img2 window per thread: LANE_WROWS rows x 32 bytes, origin aligned to 16 bytes (two 16-byte copies per row).
 constexpr int kWin2Rows = LANE_WROWS, kWin2Words = LANE_WWORDS;
 constexpr int kWinAlign = (LANE_WWORDS == 8) ? 16 : 8;
 constexpr int kWinSlackL = (LANE_WWORDS == 8) ? 2 : 3;         // footprint starts kWinSlackL..kWinSlackL+kWinAlign-1 bytes in
 constexpr int kWinSlackT = (LANE_WROWS - (G + 1)) / 2;         // rows above the footprint
-constexpr int kWin2Total = kWin2Rows * kWin2Words;            // 112 words
+static_assert(kWin2Rows >= G + 1 && kWin2Words * 4 >= G + 1 + kWinSlackL + kWinAlign - 1,
+              "the window must hold the footprint at every alignment (a footprint that never fits would re-stage forever)");
 constexpr int kTplRows = P + 1;                               // img1 window rows in the template kernel
-constexpr int kI1Count = P * P;                               // 49 floats, index y*P + x
+// The per-thread shared memory is made of 16-byte granules, [granule][T], so that a level set-up is 38 16-byte
+// cp.async copies straight from global memory, all in flight together, no register staging (the first layout,
+// [word][T] with conflict-free 32-bit accesses, needed ~170 set-up instructions incl. 121 32-bit stores: 7 % slower
+// overall, profiles/README.md).  Template rows are padded to whole granules and read with 128-bit loads; window
+// words are read one by one (4-way bank conflicts, affordable: the shared-memory pipe is far from saturated).
+constexpr int kTplPitch = (P + 3) / 4 * 4;                    // floats per template row, in the record and in shared memory
+constexpr int kI1Count = P * kTplPitch;                       // template floats, index y*kTplPitch + x
+static_assert(LANE_WWORDS == 8, "granule layout: 32-byte window rows");
 constexpr int kQueue = LANE_QUEUE;                            // feature ring entries per warp (power of two, >= 32)
 static_assert(kQueue >= 32 && (kQueue & (kQueue - 1)) == 0, "ring size");
-constexpr int kTplStride = ((P * P + 1 + 3) / 4 * 4) | 4;      // floats per (feature, level): patch + flag + pad; an ODD
+constexpr int kTplStride = ((kI1Count + 1 + 3) / 4 * 4) | 4;   // floats per (feature, level): patch + flag + pad; an ODD
                                                               // number of float4 (conflict-free transposed stores)
-static_assert(kTplStride >= P * P + 1 && (kTplStride / 4) % 2 == 1 && kTplStride % 4 == 0, "template record stride");
+static_assert(kTplStride >= kI1Count + 1 && (kTplStride / 4) % 2 == 1 && kTplStride % 4 == 0, "template record stride");
 #ifndef LANE_BATCH
 #define LANE_BATCH 1
 #endif
 #ifndef LANE_T
-#define LANE_T 128
+#define LANE_T 96
 #endif
 #ifndef LANE_CTAS
 #define LANE_CTAS 3
@@ -115,11 +117,11 @@ enum : int { ST_FETCH = 0, ST_LEVEL = 1, ST_RUN = 2, ST_DONE = 3 };
 
 template <int T>
 struct LaneSmem {
-    // word stride T + LANE_PAD: with per-thread stores and loads the bank is decided by the thread index alone,
-    // so the padding (needed by the first, warp-cooperative stager) is optional
-    uint32_t win2[kWin2Total][T + LANE_PAD];
-    float i1[kI1Count][T + LANE_PAD];
-    float wy[2 * G][T + LANE_PAD];  // per grid row: [2r] = 1-frac, [2r+1] = frac (dynamic row index in the rolled loop)
+    // granules of one thread: window rows (2 each), template rows (kTplPitch / 4 each), row weights (pairs 1-frac, frac)
+    static constexpr int kGranTpl = 2 * kWin2Rows,   // (window granules first)
+                         kGranWy = kGranTpl + kI1Count / 4,
+                         kGranTotal = kGranWy + (2 * G + 3) / 4;
+    uint4 g[kGranTotal][T];
     // per-warp ring of fetched features: one global atomic + coalesced keypoint loads per 32 features
     float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
     int q_id[T / 32][kQueue];
@@ -217,47 +219,11 @@ __device__ __forceinline__ bool axis_families(float k, unsigned &maskB, double &
     return ok;
 }
 
-// The calling thread stages ROWS x 32 bytes of `img`, nominal origin (wx0 16-aligned, wy0), into its own
-// column `dst` of a word-interleaved window (row r, word w at dst[(r*8 + w) * WS]).  Rows are clamped to
-// the image; columns outside [0, cols) come from the row aprons (LevelView), so every load is an aligned
-// 16-byte load.  The caller guarantees window_in_apron(lv, wx0).
+// A thread's window is kWin2Rows x 32 bytes of img2 with nominal origin (wx0 16-aligned, wy0).  Rows are clamped to
+// the image; columns outside [0, cols) come from the row aprons (LevelView), so every copy is an aligned 16-byte
+// copy -- provided the window lies inside the aprons:
 __device__ __forceinline__ bool window_in_apron(const LevelView &lv, int wx0, int width_bytes = kWin2Words * 4) {
     return wx0 >= -kApronL && wx0 + width_bytes <= lv.pitch - kApronL;
-}
-
-template <int ROWS>
-__device__ __forceinline__ void window_load(const uint8_t *img, const LevelView &lv, int wx0, int wy0,
-                                            uint32_t (&v)[ROWS][kWin2Words]) {
-#pragma unroll
-    for (int i = 0; i < ROWS; ++i) {
-        const int ry = min(max(wy0 + i, 0), lv.rows - 1);
-        const uint8_t *rp = img + (ptrdiff_t)ry * lv.pitch + wx0;
-        if (kWinAlign == 16) {
-#pragma unroll
-            for (int q = 0; q < kWin2Words / 4; ++q) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(rp) + q);
-                v[i][4 * q] = t.x;
-                v[i][4 * q + 1] = t.y;
-                v[i][4 * q + 2] = t.z;
-                v[i][4 * q + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < kWin2Words / 2; ++q) {
-                const uint2 t = __ldg(reinterpret_cast<const uint2 *>(rp) + q);
-                v[i][2 * q] = t.x;
-                v[i][2 * q + 1] = t.y;
-            }
-        }
-    }
-}
-
-template <int ROWS, int WS>
-__device__ __forceinline__ void window_store(const uint32_t (&v)[ROWS][kWin2Words], uint32_t *dst) {
-#pragma unroll
-    for (int i = 0; i < ROWS; ++i)
-#pragma unroll
-        for (int w = 0; w < kWin2Words; ++w) dst[(i * kWin2Words + w) * WS] = v[i][w];
 }
 
 // ---- packed FP32x2 variant of the row load / sample row (sm_100 FMUL2 / FADD2: two IEEE-rounded fp32 operations
@@ -311,12 +277,19 @@ __device__ __forceinline__ float2 bytes_to_float2(uint32_t wa, int ka, uint32_t 
     return add2_rn(p, make_float2(-8388608.0f, -8388608.0f));
 }
 
-template <int WS>
-__device__ __forceinline__ void load_row10_packed(const uint32_t *wp, int i, int sh, Row2 &row) {
-    const uint32_t *p = wp + i * kWin2Words * WS;
+// Where a thread finds the window words of its footprint: row i, k-th word = base[i * row_stride + off[k]]
+// (off[k]: the word's granule and its position inside it).
+struct WinRef {
+    const uint32_t *base;
+    int row_stride;
+    int off[kRowWords];
+};
+
+__device__ __forceinline__ void load_row10_packed(const WinRef &wr, int i, int sh, Row2 &row) {
+    const uint32_t *p = wr.base + i * wr.row_stride;
     uint32_t w[kRowWords], b[kRowWords - 1];
 #pragma unroll
-    for (int k = 0; k < kRowWords; ++k) w[k] = p[k * WS];
+    for (int k = 0; k < kRowWords; ++k) w[k] = p[wr.off[k]];
 #pragma unroll
     for (int k = 0; k < kRowWords - 1; ++k) b[k] = __funnelshift_r(w[k], w[k + 1], sh);
 #pragma unroll
@@ -353,11 +326,13 @@ __device__ __noinline__ void exact_pass(const uint8_t *img2, const LevelView &lv
                                         float ky, double dx, double dy, double (&sums)[6]) {
     double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
 #pragma unroll 1
-    for (int p = 0; p < kI1Count; ++p) {
+    for (int p = 0; p < P * P; ++p) {
         const int y = p / P, x = p - y * P;
         const float fx = kx + (float)(LO + x), fy = ky + (float)(LO + y);
         const double cx = (double)fx + dx, cy = (double)fy + dy;
-        const double e = (double)(i1p[p * ws] - sample_flat_cold(img2, lv, (float)cx, (float)cy));
+        const int idx = y * kTplPitch + x;  // (ws: floats between consecutive words / granules of this thread)
+        const float i1v = i1p[(idx >> 2) * ws + (idx & 3)];
+        const double e = (double)(i1v - sample_flat_cold(img2, lv, (float)cx, (float)cy));
         const double gx = (double)(sample_flat_cold(img2, lv, (float)(cx + 1), (float)cy) -
                                    sample_flat_cold(img2, lv, (float)(cx - 1), (float)cy));
         const double gy = (double)(sample_flat_cold(img2, lv, (float)cx, (float)(cy + 1)) -
@@ -538,8 +513,8 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
             for (int x = 0; x < P; ++x) {
                 const float v = bilerp(omx[x + 1], xx[x + 1], omy[y + 1], yy[y + 1], rowA[x + 1], rowA[x + 2], rowB[x + 1],
                                        rowB[x + 2]);
-                if (kDirect) mine_f[y * P + x] = v;
-                else buf[y * P + x] = v;
+                if (kDirect) mine_f[y * kTplPitch + x] = v;
+                else buf[y * kTplPitch + x] = v;
             }
 #pragma unroll
             for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
@@ -587,7 +562,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     LaneSmem<T> &sm = *reinterpret_cast<LaneSmem<T> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int WS = T + LANE_PAD;  // word stride between consecutive window words of one thread
     int q_head = 0, q_tail = 0;  // warp-uniform ring positions
     const int n_work = FAMILIES ? *args.list_count : args.n_total;
     bool global_done = false;
@@ -715,37 +689,34 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     wy0 = iyn - kWinSlackT;
                     no_window = !window_in_apron(lv, wx0);
                 }
-                // Template first (13 x 16 B in flight), then the window in two halves (14 x 16 B in flight each):
-                // holding all 41 loads in flight needs ~250 registers and did not pay (profiles/README.md).
-                constexpr int kHalf = kWin2Rows / 2;
+                // Everything the level needs goes global -> shared memory by 16-byte cp.async copies (template record,
+                // two per window row), in flight together; they land while the grid coordinates of the pass are
+                // computed and are waited for just before the pass.
                 const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
+                uint4 *gp = &sm.g[0][tid];
                 if (new_level) {
-                    const float4 *tp = reinterpret_cast<const float4 *>(args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride);
-                    float4 t[kTplStride / 4];
-#pragma unroll
-                    for (int i = 0; i < kTplStride / 4; ++i) t[i] = __ldg(tp + i);
-                    if (level > 0) {  // the next level's template (208 B below this one) will be needed a few trips from now
-                        const char *nxt = reinterpret_cast<const char *>(tp) - args.tpl_features * (kTplStride * sizeof(float));
+                    const char *tp = reinterpret_cast<const char *>(args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride);
+                    if (level > 0) {  // the next level's template will be needed a few trips from now
+                        const char *nxt = tp - args.tpl_features * (kTplStride * sizeof(float));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
                     }
-                    float *ip = &sm.i1[0][tid];
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(gp + LaneSmem<T>::kGranTpl * T);
 #pragma unroll
-                    for (int i = 0; i < kTplStride / 4; ++i) {
-                        if (4 * i < kI1Count) ip[(4 * i) * WS] = t[i].x;
-                        if (4 * i + 1 < kI1Count) ip[(4 * i + 1) * WS] = t[i].y;
-                        if (4 * i + 2 < kI1Count) ip[(4 * i + 2) * WS] = t[i].z;
-                        if (4 * i + 3 < kI1Count) ip[(4 * i + 3) * WS] = t[i].w;
-                    }
+                    for (int j = 0; j < kI1Count / 4; ++j)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * T * 16), "l"(tp + 16 * j) : "memory");
                 }
                 if (!no_window) {
-                    uint32_t wv[kHalf][kWin2Words];
-                    window_load<kHalf>(img2, lv, wx0, wy0, wv);
-                    window_store<kHalf, WS>(wv, &sm.win2[0][tid]);
-                    uint32_t wv2[kWin2Rows - kHalf][kWin2Words];  // (an odd row count leaves the larger half here)
-                    window_load<kWin2Rows - kHalf>(img2, lv, wx0, wy0 + kHalf, wv2);
-                    window_store<kWin2Rows - kHalf, WS>(wv2, &sm.win2[kHalf * kWin2Words][tid]);
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(gp);
+#pragma unroll
+                    for (int i = 0; i < kWin2Rows; ++i) {
+                        const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+                        const uint8_t *rp = img2 + (ptrdiff_t)ry * lv.pitch + wx0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * i) * T * 16), "l"(rp) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * i + 1) * T * 16), "l"(rp + 16) : "memory");
+                    }
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
                 need_win = false;
                 state = ST_RUN;
             }
@@ -793,23 +764,24 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 fast = true;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    sm.wy[2 * g][tid] = omy[g];
-                    sm.wy[2 * g + 1][tid] = yy[g];
+                    reinterpret_cast<float2 *>(&sm.g[LaneSmem<T>::kGranWy + (g >> 1)][tid])[g & 1] = make_float2(omy[g], yy[g]);
                 }
             }
         }
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
+        asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's set-up copies (each thread reads only its own granules)
         const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & kPMask2) != 0u);
         if (run) {
             const LevelView &lv = pyr.lv[level];
-            const float *i1p = &sm.i1[0][tid];
+            const float *i1p = reinterpret_cast<const float *>(&sm.g[LaneSmem<T>::kGranTpl][tid]);
+            constexpr int kI1Stride = T * 4;   // floats between consecutive granules of one thread
             double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
             bool solve_now = true;
             if (!fast) {
                 // the reference formulation covers the whole patch whatever its families: restart the pass
                 double sums[6];
-                exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, WS, kx, ky, dx, dy, sums);
+                exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, kI1Stride, kx, ky, dx, dy, sums);
                 sb0 = sums[0];
                 sb1 = sums[1];
                 sc = sums[2];
@@ -820,8 +792,30 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             } else {
             const int ox = ixn - wx0;
             const int sh = (ox & 3) * 8;
-            const uint32_t *wp = &sm.win2[(iyn - wy0) * kWin2Words + (ox >> 2)][tid];
-            const float *wyp = &sm.wy[0][tid];
+            WinRef wr;
+            {   // word kw + k of a row: granule (kw + k) >> 2 of the row, position (kw + k) & 3 inside it
+                const int kw = ox >> 2;
+                wr.base = reinterpret_cast<const uint32_t *>(&sm.g[2 * (iyn - wy0)][tid]);
+                wr.row_stride = 2 * T * 4;
+#pragma unroll
+                for (int k = 0; k < kRowWords; ++k) wr.off[k] = ((kw + k) >> 2) * (T * 4) + ((kw + k) & 3);
+            }
+            const float *wyg = reinterpret_cast<const float *>(&sm.g[LaneSmem<T>::kGranWy][tid]);
+            auto row_weights = [&](int r, float &om, float &fr) {  // pair r: granule r >> 1, half r & 1
+                const float2 v = *reinterpret_cast<const float2 *>(wyg + (r >> 1) * (T * 4) + (r & 1) * 2);
+                om = v.x;
+                fr = v.y;
+            };
+            auto template_row = [&](int y, float (&v)[P]) {          // kTplPitch / 4 granules per row
+#pragma unroll
+                for (int q = 0; q < kTplPitch / 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4 *>(i1p + (y * (kTplPitch / 4) + q) * (T * 4));
+                    if (4 * q < P) v[4 * q] = t.x;
+                    if (4 * q + 1 < P) v[4 * q + 1] = t.y;
+                    if (4 * q + 2 < P) v[4 * q + 2] = t.z;
+                    if (4 * q + 3 < P) v[4 * q + 3] = t.w;
+                }
+            };
             Row2 rowA, rowB;
             float2 Sa[kNP], Sb[kNP], Sc[kNP];  // sample rows r-2, r-1, r as pairs (2j, 2j+1); rotated by register moves
             float2 OMX[kNP], XX[kNP];
@@ -833,26 +827,31 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
             // The row loop is deliberately NOT unrolled: the unrolled pass (1785 SASS instructions) did
             // not fit the instruction cache and the kernel was fetch-bound (profiles/README.md).
-            load_row10_packed<WS>(wp, 0, sh, rowA);
-            load_row10_packed<WS>(wp, 1, sh, rowB);
-            sample_row_packed(OMX, XX, wyp[0], wyp[WS], rowA, rowB, args.one, Sa);
+            float om_r, fr_r;
+            load_row10_packed(wr, 0, sh, rowA);
+            load_row10_packed(wr, 1, sh, rowB);
+            row_weights(0, om_r, fr_r);
+            sample_row_packed(OMX, XX, om_r, fr_r, rowA, rowB, args.one, Sa);
             rowA = rowB;
-            load_row10_packed<WS>(wp, 2, sh, rowB);
-            sample_row_packed(OMX, XX, wyp[2 * WS], wyp[3 * WS], rowA, rowB, args.one, Sb);
+            load_row10_packed(wr, 2, sh, rowB);
+            row_weights(1, om_r, fr_r);
+            sample_row_packed(OMX, XX, om_r, fr_r, rowA, rowB, args.one, Sb);
             rowA = rowB;
             // One patch row per step: sample row r from pixel rows r, r+1 (PB is loaded here), then the 7 pixels of
             // patch row y = r-2 with centre samples SB = grid row r-1, SA / SC the rows above / below.
             auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[kNP], const float2 (&SB)[kNP], float2 (&SC)[kNP]) {
-                load_row10_packed<WS>(wp, r + 1, sh, PB);
-                sample_row_packed(OMX, XX, wyp[(2 * r) * WS], wyp[(2 * r + 1) * WS], PA, PB, args.one, SC);
-                const float *i1row = i1p + ((r - 2) * P) * WS;
+                load_row10_packed(wr, r + 1, sh, PB);
+                float om_s, fr_s, tpl[P];
+                row_weights(r, om_s, fr_s);
+                template_row(r - 2, tpl);
+                sample_row_packed(OMX, XX, om_s, fr_s, PA, PB, args.one, SC);
                 const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
 #pragma unroll
                 for (int x = 0; x < P; ++x) {
                     const int g = x + 1;
                     // any_masked (warp-uniform, FAMILIES instance only): pixels outside the sub-pass add 0
                     const bool on = !any_masked || (row_on && ((pmx >> x) & 1u));
-                    const double e = (double)(on ? __fadd_rn(i1row[x * WS], -pick(SB, g)) : 0.f);          // :65-66
+                    const double e = (double)(on ? __fadd_rn(tpl[x], -pick(SB, g)) : 0.f);                // :65-66
                     const double gx = (double)(on ? __fadd_rn(pick(SB, g + 1), -pick(SB, g - 1)) : 0.f);  // :70-71
                     const double gy = (double)(on ? __fadd_rn(pick(SC, g), -pick(SA, g)) : 0.f);          // :72-73
                     sb0 = fma(e, gx, sb0);
