@@ -246,7 +246,7 @@ def test_edge_cases(tracker, oracle, kernel):
     guess = ugly + np.array([[0.7, -0.4]], np.float32)
     guess[5] = [-30, 20]
     for kw in (dict(levels=3), dict(levels=1), dict(levels=3, inverse=True), dict(levels=3, has_initial=False),
-               dict(levels=2, patch_lo=-5, patch_hi=5)):
+               dict(levels=2, patch_lo=-5, patch_hi=5), dict(levels=3, patch_lo=-4, patch_hi=3)):
         if not _supported(kernel, kw):
             continue
         o, s, _ = tracker.track(L, R, ugly, guess, klt.make_params(kernel=kernel, **kw))
@@ -259,18 +259,20 @@ def test_edge_cases(tracker, oracle, kernel):
     assert s.all() and int(st.n_nan) == 0 and np.array_equal(o, kp + np.float32(0.25))
 
 
-def test_subpixel_keypoints_and_deferred_features(tracker, oracle):
+@pytest.mark.parametrize("lo,hi", [(-3, 3), (-4, 3), (-5, 5)])
+def test_subpixel_keypoints_and_deferred_features(tracker, oracle, lo, hi):
     """Tracked (sub-pixel) source points, as Frontend::TrackLastFrame feeds them: float(kx+c) is sometimes
     rounded near powers of two.  The LANE kernel splits such a patch into coordinate families (one extra trip
-    per pass); only patches straddling several powers of two go to the exact warp kernel."""
+    per pass); only patches straddling several powers of two go to the exact warp kernel.  All three compiled
+    patch instances."""
     rows, cols, n = 376, 1241, 4000
     L, R, kp1, kp2, _ = synth.stereo_case(rows, cols, n, seed=21)
     rng = np.random.default_rng(5)
     kp1 = (kp1 + rng.uniform(-0.5, 0.5, kp1.shape)).astype(np.float32)
     kp2 = (kp1 + rng.normal(0, 1.0, kp1.shape)).astype(np.float32)
-    ref, rs, rst = oracle.track(L, R, kp1, kp2, threads=8)
+    ref, rs, rst = oracle.track(L, R, kp1, kp2, oracle.make_params(patch_lo=lo, patch_hi=hi), threads=8)
     for kernel in FAST_KERNELS:
-        out, succ, st = tracker.track(L, R, kp1, kp2, klt.make_params(kernel=kernel))
+        out, succ, st = tracker.track(L, R, kp1, kp2, klt.make_params(kernel=kernel, patch_lo=lo, patch_hi=hi))
         assert_parity(out, succ, ref, rs, cols, rows, f"subpixel kernel={kernel}")
         assert _iters(st, 4) == _iters(rst, 4)
         if kernel == klt.KERNEL_LANE:
