@@ -262,8 +262,9 @@ def sequence_mode(trk, n_feat, args):
                 prev_h.upload(P)
             cur_h.upload(Cur)
             right_h.upload(R)
-            trk.track_images(prev_h, cur_h, kt, kt, params)       # Frontend::TrackLastFrame...4LayerSelf
-            trk.track_images(cur_h, right_h, kps, kps, params)    # Frontend::FindFeaturesInRight...4LayerSelf
+            # (no counters requested, like the C++ shim: the reference's signature has none)
+            trk.track_images(prev_h, cur_h, kt, kt, params, want_stats=False)     # Frontend::TrackLastFrame...4LayerSelf
+            trk.track_images(cur_h, right_h, kps, kps, params, want_stats=False)  # Frontend::FindFeaturesInRight...4LayerSelf
             prev_h, cur_h = cur_h, prev_h
 
     def run_pairwise(count):

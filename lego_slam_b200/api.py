@@ -174,16 +174,18 @@ class Tracker:
         """Device-resident image with a cached pyramid (sequence mode)."""
         return Image(self, rows, cols, levels, step)
 
-    def track_images(self, img1: "Image", img2: "Image", kp1, kp2, params: Params | None = None):
-        """lego_klt_track_images: solver only, on two uploaded images."""
+    def track_images(self, img1: "Image", img2: "Image", kp1, kp2, params: Params | None = None, want_stats: bool = True):
+        """lego_klt_track_images: solver only, on two uploaded images.  want_stats=False passes a null stats pointer,
+        as the C++ shim does (the reference's signature has no counters): the third result is then None."""
         params = params or make_params(img1.levels)
         kp1 = np.ascontiguousarray(kp1, np.float32).reshape(-1, 2)
         out = np.ascontiguousarray(kp2, np.float32).reshape(-1, 2).copy()
         n = kp1.shape[0]
         succ = np.zeros(max(n, 1), np.uint8)
-        st = Stats()
+        st = Stats() if want_stats else None
         _lib.check(self._lib.lego_klt_track_images(self._h, C.byref(params), img1._h, img2._h, kp1.ctypes.data,
-                                                   out.ctypes.data, succ.ctypes.data, n, C.byref(st)),
+                                                   out.ctypes.data, succ.ctypes.data, n,
+                                                   C.byref(st) if want_stats else None),
                    "lego_klt_track_images")
         return out, succ[:n], st
 

@@ -19,4 +19,8 @@ for n in (150, 500, 2000, 5000, 20000):
         for _ in range(50):
             trk.track_images(a, b, kp1, kp2, p)
         row.append(f"{name} {(time.perf_counter() - t0) / 50 * 1e3:.3f} ms")
+        t0 = time.perf_counter()
+        for _ in range(50):
+            trk.track_images(a, b, kp1, kp2, p, want_stats=False)
+        row.append(f"(no stats {(time.perf_counter() - t0) / 50 * 1e3:.3f})")
     print("  ".join(row))
