@@ -472,6 +472,36 @@ def run_ours(args):
 
     seq = sequence_mode(trk, n, args) if world == 1 and not args.no_sequence else None
 
+    # ---------------- parity report of this run, outside the timed regions ----------------
+    # The first pairs of the batch once more through the bit-exact EXACT kernel (thread per feature, reference
+    # operation order: the on-GPU checker, itself pinned to the CPU oracle by the tests), and -- at N = 1 -- pair 0
+    # through the CPU oracle (the checker; never on the product path).
+    parity = None
+    if rank == 0:
+        Bc = min(B, 16)
+        chk = trk.batch(Bc, ROWS, COLS, n, levels=LEVELS)
+        chk.upload(imgs1[:Bc], imgs2[:Bc], kp1[:Bc], kp2[:Bc])
+        res = {}
+        for name, k in (("exact", klt.KERNEL_EXACT), ("fast", args.kernel)):
+            chk.run(klt.make_params(levels=LEVELS, patch_lo=PATCH_LO, patch_hi=PATCH_HI, kernel=k))
+            o, s_, st_ = chk.download()
+            res[name] = (o.copy(), s_.copy(), [int(v) for v in st_.gn_iters][:LEVELS])
+        d = np.abs(res["fast"][0].astype(np.float64) - res["exact"][0]).max(axis=2)
+        parity = {"checked_features": int(Bc * n), "checker": "EXACT kernel (bit-identical to the CPU oracle)",
+                  "flag_mismatches": int((res["fast"][1] != res["exact"][1]).sum()),
+                  "max_abs_dpos_px": float(d.max()), "n_over_1e-3_px": int((d > 1e-3).sum()),
+                  "bit_identical_fraction": float((res["fast"][0].view(np.uint32) == res["exact"][0].view(np.uint32)).all(axis=2).mean()),
+                  "gn_iters_equal": res["fast"][2] == res["exact"][2]}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import binding as ob
+            ro, rs, rst = ob.track(np.ascontiguousarray(imgs1[0]), np.ascontiguousarray(imgs2[0]), kp1[0], kp2[0],
+                                   threads=os.cpu_count() or 1)
+            d0 = np.abs(res["fast"][0][0].astype(np.float64) - ro).max(axis=1)
+            parity["vs_cpu_oracle_pair0"] = {"features": int(n), "flag_mismatches": int((res["fast"][1][0] != rs).sum()),
+                                             "max_abs_dpos_px": float(d0.max()),
+                                             "exact_kernel_bit_identical": bool(np.array_equal(
+                                                 res["exact"][0][0].view(np.uint32), ro.view(np.uint32)))}
+
     # The metric text of BASELINE.json says "8x8 patch"; the reference computes 7x7 (src/algorithm.cpp:40,63-64,
     # SURVEY.md F1), which is what `value` measures.  The literal 8x8 patch (-4..3) and the 11x11 patch of the stress
     # configuration (-5..5) beside it, same batch, device-resident (one batch in flight): the LANE solver is compiled
@@ -528,6 +558,7 @@ def run_ours(args):
                                   "pinned host memory): legoslam::triangulation, SURVEY.md 8f N3",
                           "points_per_s": world * n_tracks / (tri_ms * 1e-3), "ms_per_call": tri_ms,
                           "d2h_bytes_per_call": int(tri_pt.nbytes + tri_ok.nbytes), "n_accepted": int(tri_ok.sum())},
+        "parity": parity,
         "sequence_mode": seq,
         "other_patches": other_patches,
         "host": {"numa_binding": numa, "e2e_wall_ms_per_step": e2e_wall_s * 1e3 / args.steps},
