@@ -76,19 +76,22 @@ bool lane_kernel_supports(const SolverArgs &args);
 size_t lane_template_bytes(int n_total, int levels);
 size_t lane_scratch_bytes(int sm_count);
 cudaError_t launch_klt_template(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
-cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
+cudaError_t launch_klt_lane(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
+                            cudaStream_t families_stream);
 // The same path compiled for the 8x8 patch, offsets -4..3 (klt_solver_lane_p8.cu).
 bool lane_kernel_supports_p8(const SolverArgs &args);
 size_t lane_template_bytes_p8(int n_total, int levels);
 size_t lane_scratch_bytes_p8(int sm_count);
 cudaError_t launch_klt_template_p8(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
-cudaError_t launch_klt_lane_p8(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
+cudaError_t launch_klt_lane_p8(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
+                            cudaStream_t families_stream);
 // ... and for the 11x11 patch, offsets -5..5 (klt_solver_lane_p11.cu).
 bool lane_kernel_supports_p11(const SolverArgs &args);
 size_t lane_template_bytes_p11(int n_total, int levels);
 size_t lane_scratch_bytes_p11(int sm_count);
 cudaError_t launch_klt_template_p11(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
-cudaError_t launch_klt_lane_p11(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream);
+cudaError_t launch_klt_lane_p11(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
+                            cudaStream_t families_stream);
 
 // ---- triangulation (triangulate_sm100.cu) ------------------------------------------------
 constexpr int kTriMaxViews = 8;

@@ -969,19 +969,15 @@ cudaError_t LANE_FN(launch_klt_template)(const PyramidView &pyr, const SolverArg
     return cudaGetLastError();
 }
 
-cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream) {
+// `stream`: the common instance (single-family features, args.f0 .. ).  `families_stream`: the FAMILIES instance, fed
+// by the template kernel's fam_list -- it may be another stream (it only depends on the template kernel), so that it
+// fills the tail of the common instance and, in the chunked end-to-end path, overlaps the next chunk.
+cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
+                                     cudaStream_t families_stream) {
     if (args.n_total <= 0) return cudaSuccess;
     const size_t smem = sizeof(LaneSmem<kLaneThreads>);
     int grid = sm_count * kLaneMinCtas;
-    {
-        auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, false>;
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
-        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, args);
-        err = cudaGetLastError();
-        if (err != cudaSuccess) return err;
-    }
+    const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
     {
         // multi-family features (sub-pixel keypoints near a power of two): the list length is only known on
         // the device, so the grid is sized for the worst case and CTAs without work exit at once
@@ -992,8 +988,15 @@ cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &a
         a2.list = args.fam_list;
         a2.list_count = args.fam_count;
         a2.work_counter = args.work_counter + 3;
-        const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
-        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, a2);
+        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, families_stream>>>(pyr, a2);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
+    {
+        auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, false>;
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, args);
         return cudaGetLastError();
     }
 }

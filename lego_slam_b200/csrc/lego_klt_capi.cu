@@ -107,6 +107,7 @@ struct lego_klt_batch {
     cudaEvent_t ev_compute_done = nullptr;
     cudaStream_t d2h = nullptr;    // chunked end-to-end path: results of chunk c leave while chunk c+1 computes
     cudaEvent_t ev_done[kMaxChunks] = {};
+    cudaEvent_t ev_join_c[kMaxChunks] = {};  // side-stream work of chunk c (deferred features, FAMILIES instance) done
     bool uploaded = false, ran = false, pyramids_valid = false, last_chunked = false;
     lego_klt_params last_params;
 };
@@ -269,7 +270,8 @@ int ensure_lane_buffers(lego_klt_batch *b, size_t template_bytes) {
 // Pyramids + aprons + solver for images [img0, img0+nimg) (features f0 = img0*n .. ), on the context stream.
 // `chunk` selects the set of device work counters; `ring` (3 events) is recorded around the kernels if given.
 int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int nimg, int chunk, cudaEvent_t *ring,
-              const PyramidView *view_override = nullptr, const WarpKernelMaps *maps_override = nullptr) {
+              const PyramidView *view_override = nullptr, const WarpKernelMaps *maps_override = nullptr,
+              cudaEvent_t deferred_join = nullptr) {
     lego_klt_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     const PyramidView &view = view_override ? *view_override : b->view;   // cached pyramids of image handles
@@ -360,11 +362,17 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         aw.list = a.defer_list;
         aw.list_count = a.defer_count;
         CU_TRY(launch_klt_warp(view, maps, aw, ctx->sm_count, b->side));
-        CU_TRY(cudaEventRecord(b->ev_join, b->side));
-        CU_TRY(lane_patch == 7   ? launch_klt_lane(view, a, ctx->sm_count, st)
-               : lane_patch == 8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st)
-                                 : launch_klt_lane_p11(view, a, ctx->sm_count, st));
-        CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
+        // the FAMILIES instance of the lane kernel (features with two coordinate families on some level) follows on
+        // the side stream: it fills the tail of the common instance and, with a deferred join, overlaps the next chunk
+        CU_TRY(lane_patch == 7   ? launch_klt_lane(view, a, ctx->sm_count, st, b->side)
+               : lane_patch == 8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st, b->side)
+                                 : launch_klt_lane_p11(view, a, ctx->sm_count, st, b->side));
+        if (deferred_join) {
+            CU_TRY(cudaEventRecord(deferred_join, b->side));   // the caller joins before it needs the results
+        } else {
+            CU_TRY(cudaEventRecord(b->ev_join, b->side));
+            CU_TRY(cudaStreamWaitEvent(st, b->ev_join, 0));
+        }
     }
     if (ring) CU_TRY(cudaEventRecord(ring[2], st));
     return LEGO_KLT_OK;
@@ -646,8 +654,10 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
         if (b->ev_chunk[i]) cudaEventDestroy(b->ev_chunk[i]);
     if (b->ev_compute_done) cudaEventDestroy(b->ev_compute_done);
     if (b->d2h) cudaStreamDestroy(b->d2h);
-    for (int i = 0; i < kMaxChunks; ++i)
+    for (int i = 0; i < kMaxChunks; ++i) {
         if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+        if (b->ev_join_c[i]) cudaEventDestroy(b->ev_join_c[i]);
+    }
     cudaFree(b->d_images);
     cudaFree(b->d_tight);
     cudaFree(b->d_io);
@@ -754,6 +764,7 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
         for (int i = 0; i < kMaxChunks; ++i) {
             CU_TRY(cudaEventCreateWithFlags(&b->ev_chunk[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&b->ev_join_c[i], cudaEventDisableTiming));
         }
         CU_TRY(cudaEventCreateWithFlags(&b->ev_compute_done, cudaEventDisableTiming));
     }
@@ -763,6 +774,7 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
     CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
     const int n = b->n_active;
+    int last_chunk = -1;
     // All keypoints first, as two copies (per-chunk keypoint copies are 256 KB each: latency-bound gaps on the link),
     // and before any result comes back: kp2_xy is both the initial guess and the output buffer.
     if (nt) {
@@ -779,16 +791,20 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
         CU_TRY(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
         CU_TRY(ingest_set(b, 0, img0, nimg, st));
         CU_TRY(ingest_set(b, 1, img0, nimg, st));
-        rc = run_range(b, params, img0, nimg, c, nullptr);
+        rc = run_range(b, params, img0, nimg, c, nullptr, nullptr, nullptr, b->ev_join_c[c]);
         if (rc) return rc;
+        last_chunk = c;
         if (n) {  // this chunk's results go home while the next chunk computes
             const size_t off = (size_t)img0 * n, cnt = (size_t)nimg * n;
             CU_TRY(cudaEventRecord(b->ev_done[c], st));
             CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_done[c], 0));
+            if (b->side) CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_join_c[c], 0));  // (its side-stream work, if any)
             CU_TRY(cudaMemcpyAsync(kp2_xy + 2 * off, b->d_kp2_out + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, b->d2h));
             CU_TRY(cudaMemcpyAsync(success + off, b->d_success + off, cnt, cudaMemcpyDeviceToHost, b->d2h));
         }
     }
+    // the side stream runs its chunks in order: the last join covers them all (counters, results)
+    if (last_chunk >= 0 && b->side) CU_TRY(cudaStreamWaitEvent(st, b->ev_join_c[last_chunk], 0));
     CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
     b->uploaded = true;
     b->pyramids_valid = true;
