@@ -739,7 +739,20 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     // Equal chunks: more / smaller chunks shorten the pipeline tail but cost launches and solver efficiency
     // (measured: 10 chunks with a fine tail 6 % slower than 8 equal ones; a smaller LAST chunk of 8 or 16 pairs 5 % slower).
     int bounds[kMaxChunks + 1];
-    const int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
+    // Chunk count (measured, 256 pairs x 2000 features): integer source keypoints (freshly detected corners) 4 / 6 / 8 /
+    // 12 chunks -> 0.97 / 1.00 / 1.01 / 0.91e8 tracks/s; sub-pixel ones (tracked points fed back) 0.88 / 0.85 / 0.74 /
+    // 0.54e8, because a quarter of them take the two-family path, whose second persistent launch needs larger chunks to
+    // stay efficient.  A sample of the keypoints decides.
+    int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
+    if (n_chunks == 8 && kp1_xy && b->n_active > 0) {
+        const size_t nt_all = (size_t)b->B * (size_t)b->n_active, stride = nt_all > 512 ? nt_all / 512 : 1;
+        int fractional = 0, seen = 0;
+        for (size_t i = 0; i < nt_all; i += stride, ++seen) {
+            const float x = kp1_xy[2 * i], y = kp1_xy[2 * i + 1];
+            fractional += (x != std::floor(x)) || (y != std::floor(y));
+        }
+        if (fractional * 10 > seen) n_chunks = 4;
+    }
     for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
     if (n_chunks == 1) {
         int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
