@@ -33,8 +33,8 @@ def make_params(levels=4, patch_lo=-3, patch_hi=3, max_iters=10, inverse=False, 
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "klt_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("klt_oracle.cpp", "resize_u8.cpp", "klt_oracle.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
     return _SO
 

@@ -15,12 +15,16 @@
  *     Eigen3 (un-pinned, CMakeLists.txt:15; 3.3.x on the reference's Ubuntu 18.04)
  *            Matrix2d::ldlt().solve()
  *
- * PARITY PINNING: the reference ships no test, golden vector or fixture for this path
- *  and its translation unit cannot be compiled here (needs OpenCV/Eigen/Sophus/
- * glog headers, none present) -> the solver part is "parity unpinned" by the reference itself.
- * What IS pinned here: the resize against Python cv2.resize (bit exact, tests/test_oracle_pyramid.py),
- * the solver against an independently written numpy restatement (oracle/klt_oracle_np.py) and
- * analytic known-answer tests; the LDLT spec is restated from Eigen 3.3 LDLT.h and cannot be pinned.
+ * PARITY PINNING: the reference ships no test, golden vector or fixture for this path, so the
+ * pin is the reference ITSELF run here: oracle/_ref/libklt_ref.so is the reference's own translation unit
+ * (/root/reference/src/algorithm.cpp + include/legoslam/algorithm.h, compiled unmodified where they lie, with the
+ * reference's flags, on stand-in OpenCV/Eigen headers -- oracle/build_ref.py, oracle/ref_stubs/), and
+ * tests/test_oracle_vs_ref.py asserts this restatement equals it BITWISE (positions, flags) on the BASELINE config
+ * shapes, both modes, has_initial on/off, 1 and 4 layers, padded steps, border / sliver / outside / sub-pixel
+ * points, flat and white-noise images; the committed golden vectors (tests/golden/) are _ref's outputs.
+ * The resize (OpenCV, third party) is pinned against Python cv2.resize (bit exact, tests/test_oracle_pyramid.py).
+ * What remains a restatement of third-party code with no pin available in this image: Eigen 3.3's 2x2 pivoted LDLT
+ * (written twice, independently structured: ldlt2_solve here, LDLT<N> in ref_stubs/eigen_stub.hpp).
  *
  * Deliberate deviations from the reference (none changes results on in-range data):
  *   - success flags are bytes, not std::vector<bool> (the reference races on the bit-packed vector)

@@ -81,7 +81,7 @@ def test_exact_kernel_reproduces_golden_vectors_bitwise(tracker, golden):
     meta, vec = golden
     for name, kw in meta["solver"].items():
         kw = dict(kw)
-        iters, nsucc = kw.pop("gn_iters"), kw.pop("n_success")
+        iters, nsucc, _src = kw.pop("gn_iters"), kw.pop("n_success"), kw.pop("source")
         p = klt.make_params(kernel=klt.KERNEL_EXACT, **kw)
         out, succ, st = tracker.track(vec["left"], vec["right"], vec["kp1"], vec["kp2"], p)
         assert np.array_equal(out.view(np.uint32), vec[f"{name}_kp2"].view(np.uint32)), name
@@ -95,7 +95,7 @@ def test_fast_kernel_matches_golden_vectors(tracker, golden, kernel):
     rows, cols = vec["left"].shape
     for name, kw in meta["solver"].items():
         kw = dict(kw)
-        iters, _ = kw.pop("gn_iters"), kw.pop("n_success")
+        iters, _, _src = kw.pop("gn_iters"), kw.pop("n_success"), kw.pop("source")
         if not _supported(kernel, kw):
             continue
         p = klt.make_params(kernel=kernel, **kw)

@@ -154,7 +154,7 @@ def test_oracle_reproduces_golden_vectors(oracle, golden):
     meta, vec = golden
     for name, kw in meta["solver"].items():
         kw = dict(kw)
-        iters, nsucc = kw.pop("gn_iters"), kw.pop("n_success")
+        iters, nsucc, _src = kw.pop("gn_iters"), kw.pop("n_success"), kw.pop("source")
         p = oracle.make_params(**kw)
         out, succ, st = oracle.track(vec["left"], vec["right"], vec["kp1"], vec["kp2"], p)
         assert np.array_equal(out.view(np.uint32), vec[f"{name}_kp2"].view(np.uint32)), name

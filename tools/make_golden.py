@@ -1,9 +1,14 @@
 """Generates tests/golden/*.npz|json (run in the BUILD container, where cv2 is importable).
 
-The reference ships no golden vectors for the KLT path and its C++ cannot be built offline, so the
-pins are: (1) OpenCV itself for the pyramid (cv2.resize, the library the reference calls at
-src/algorithm.cpp:147-150), (2) the oracle's own outputs, frozen, so later edits cannot drift, and
-cross-checked at generation time against the independent numpy restatement.
+The reference ships no golden vectors for the KLT path, so they are generated here from the reference ITSELF:
+(1) OpenCV for the pyramid (cv2.resize, the library the reference calls at src/algorithm.cpp:147-150);
+(2) the solver vectors are the outputs of oracle/_ref -- the reference's own translation unit
+    (/root/reference/src/algorithm.cpp + include/legoslam/algorithm.h compiled unmodified on stand-in headers,
+    oracle/build_ref.py) -- for every variant the reference text can express ("source": "reference_tu"; with the
+    patch / level literals substituted: "reference_tu_parametrised"); the asymmetric 8x8 patch is not expressible
+    in the reference's loops and comes from the oracle ("oracle").  At generation time the oracle and the
+    independent numpy restatement are asserted bit-equal to those outputs; iteration counts come from the oracle
+    (the reference exports none).
 
     python tools/make_golden.py
 """
@@ -19,6 +24,7 @@ sys.path.insert(0, ROOT)
 from lego_slam_b200 import synth  # noqa: E402
 from oracle import binding as ob  # noqa: E402
 from oracle import klt_oracle_np as onp  # noqa: E402
+from oracle import ref_binding as rb  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -65,9 +71,18 @@ def solver_vectors():
     for name, kw in variants.items():
         p = ob.make_params(**kw)
         o, s, st = ob.track(left, right, kp1, kp2, p)
+        source = "oracle"
+        if p.patch_lo == -p.patch_hi:
+            hp, lv = p.patch_hi, (4 if p.levels == 1 else p.levels)
+            ro, rs = rb.track(left, right, kp1, kp2, inverse=bool(p.inverse), has_initial=bool(p.has_initial),
+                              layers=p.levels, half_patch=hp, pyramids=lv)
+            assert np.array_equal(ro.view(np.uint32), o.view(np.uint32)) and np.array_equal(rs, s), name
+            o, s = ro, rs
+            source = "reference_tu" if (hp, lv) == (3, 4) else "reference_tu_parametrised"
         out[f"{name}_kp2"] = o
         out[f"{name}_succ"] = s
-        meta[name] = dict(kw, gn_iters=[int(v) for v in st.gn_iters][:p.levels], n_success=int(st.n_success))
+        meta[name] = dict(kw, gn_iters=[int(v) for v in st.gn_iters][:p.levels], n_success=int(st.n_success),
+                          source=source)
         # cross-check the first 40 + the awkward ones against the numpy restatement
         sel = np.r_[0:40, n:n + extra.shape[0]]
         p1 = ob.build_pyramid(left, p.levels)
