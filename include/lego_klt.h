@@ -91,11 +91,16 @@ typedef struct lego_klt_batch lego_klt_batch;   /* device-resident batch of B im
 typedef struct lego_klt_image lego_klt_image;   /* one device-resident image with its cached pyramid */
 
 int lego_klt_abi_version(void);
+/* Kernels of this library launched by this process so far (every <<<>>> is counted where it is issued). */
+long long lego_klt_kernel_launches(void);
 const char *lego_klt_last_error(void);           /* thread-local message of the last failure       */
 void lego_klt_default_params(lego_klt_params *p);
 int lego_klt_device_count(void);                 /* >=0, or LEGO_KLT_ERR_NO_DEVICE                 */
 
-/* Context: owns a stream, scratch device buffers and pinned staging buffers on `device`. */
+/* Context: owns a stream, scratch device buffers and pinned staging buffers on `device`.
+ * Ownership: every lego_klt_batch / lego_klt_image points into the context it was created from.  lego_klt_destroy
+ * while such handles are alive is allowed: the context is then only marked and is torn down when the last of its
+ * batches / images is destroyed; it must not be USED (passed to any other entry point) after lego_klt_destroy. */
 int lego_klt_create(int device, lego_klt_ctx **out);
 void lego_klt_destroy(lego_klt_ctx *ctx);
 /* Launch on a caller-owned stream (cudaStream_t passed as void*); NULL restores the context's own. */
@@ -171,6 +176,13 @@ int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, cons
 int lego_klt_batch_create(lego_klt_ctx *ctx, int batch, int cols, int rows, size_t step,
                           int n_per_pair, int levels, lego_klt_batch **out);
 void lego_klt_batch_destroy(lego_klt_batch *b);
+/*
+ * Ragged batches: pair b tracks only its first counts[b] (0..n_per_pair) features; the remaining slots of the pair are
+ * left untracked (kp2 out = kp2 in, success = 0, not counted).  counts == NULL returns to "every pair has n_per_pair
+ * features".  The reference's callers pass a different number of features with every call (std::vector sizes,
+ * src/frontend_g2o.cpp:457-468); a batch of such calls is ragged.  The array is copied before the call returns.
+ */
+int lego_klt_batch_set_feature_counts(lego_klt_batch *b, const int *counts);
 /* H2D of images and keypoints (asynchronous on the context stream). */
 int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t *imgs2,
                           const float *kp1_xy, const float *kp2_xy);
@@ -187,6 +199,9 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params,
                            const uint8_t *imgs1, const uint8_t *imgs2,
                            const float *kp1_xy, float *kp2_xy, uint8_t *success,
                            lego_klt_stats *stats_or_null);
+/* lego_klt_track_batched cuts large batches into `chunks` groups of pairs whose H2D copy, kernels and D2H copy overlap
+ * (1..16; 0 = the default: 6 for 32 pairs or more, 4 for 8..31, else one). */
+int lego_klt_batch_set_pipeline_chunks(lego_klt_batch *b, int chunks);
 /* Device pointers of the resident buffers (for callers that already hold data in HBM). */
 int lego_klt_batch_device_ptrs(lego_klt_batch *b, void **imgs1, void **imgs2,
                                void **kp1_xy, void **kp2_xy_init, void **kp2_xy_out, void **success);
@@ -194,6 +209,24 @@ int lego_klt_sync(lego_klt_ctx *ctx);
 
 void *lego_klt_alloc_pinned(size_t bytes);
 void lego_klt_free_pinned(void *p);
+
+/*
+ * One process, several devices (SURVEY.md 8b "device list", 8e): the B pairs are cut into contiguous blocks, one per
+ * entry of `devices` (block sizes differ by at most one; a device may be listed more than once), each block owned by
+ * a context and a batch on its device.  lego_klt_multi_track runs lego_klt_track_batched on every block concurrently,
+ * one host thread per device, on slices of the caller's (pinned) buffers; pairs are independent, so there is no
+ * exchange between devices and the result bytes equal those of a single-device call on the whole batch.
+ */
+typedef struct lego_klt_multi lego_klt_multi;
+int lego_klt_multi_create(const int *devices, int n_devices, int batch, int cols, int rows, size_t step,
+                          int n_per_pair, int levels, lego_klt_multi **out);
+void lego_klt_multi_destroy(lego_klt_multi *m);
+/* Block i: its device, first pair and pair count.  Returns the number of blocks (or a negative error). */
+int lego_klt_multi_shard(const lego_klt_multi *m, int i, int *device, int *first_pair, int *n_pairs);
+int lego_klt_multi_set_feature_counts(lego_klt_multi *m, const int *counts);   /* B entries, or NULL */
+int lego_klt_multi_track(lego_klt_multi *m, const lego_klt_params *params, const uint8_t *imgs1,
+                         const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success,
+                         lego_klt_stats *stats_or_null);
 
 /*
  * ---- Triangulation of tracked features ---------------------------------------------------

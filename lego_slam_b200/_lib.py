@@ -21,6 +21,9 @@ EXPORTS = [
     "lego_klt_batch_run", "lego_klt_batch_download", "lego_klt_batch_timings", "lego_klt_track_batched",
     "lego_klt_batch_device_ptrs", "lego_klt_sync", "lego_klt_alloc_pinned", "lego_klt_free_pinned",
     "lego_klt_image_create", "lego_klt_image_destroy", "lego_klt_image_upload", "lego_klt_track_images",
+    "lego_klt_kernel_launches", "lego_klt_batch_set_feature_counts", "lego_klt_batch_set_pipeline_chunks",
+    "lego_klt_multi_create", "lego_klt_multi_destroy", "lego_klt_multi_shard", "lego_klt_multi_set_feature_counts",
+    "lego_klt_multi_track",
 ]
 
 
@@ -101,6 +104,16 @@ def load():
     lib.lego_klt_alloc_pinned.restype = vp
     lib.lego_klt_free_pinned.argtypes = [vp]
     lib.lego_klt_free_pinned.restype = None
+    lib.lego_klt_kernel_launches.restype = C.c_longlong
+    lib.lego_klt_batch_set_feature_counts.argtypes = [vp, vp]
+    lib.lego_klt_batch_set_pipeline_chunks.argtypes = [vp, C.c_int]
+    lib.lego_klt_multi_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                                          C.POINTER(vp)]
+    lib.lego_klt_multi_destroy.argtypes = [vp]
+    lib.lego_klt_multi_destroy.restype = None
+    lib.lego_klt_multi_shard.argtypes = [vp, C.c_int, ip, ip, ip]
+    lib.lego_klt_multi_set_feature_counts.argtypes = [vp, vp]
+    lib.lego_klt_multi_track.argtypes = [vp, pp, vp, vp, vp, vp, vp, sp]
     _lib = lib
     return lib
 

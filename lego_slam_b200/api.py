@@ -195,6 +195,7 @@ class Image:
 
     def __init__(self, tracker: Tracker, rows: int, cols: int, levels: int = 4, step: int | None = None):
         self._lib = tracker._lib
+        self.tracker = tracker      # the handle points into the tracker's context: keep it alive (as Batch does)
         self.rows, self.cols, self.levels, self.step = rows, cols, levels, step or cols
         h = C.c_void_p()
         _lib.check(self._lib.lego_klt_image_create(tracker._h, cols, rows, self.step, levels, C.byref(h)),
@@ -236,6 +237,19 @@ class Batch:
 
     def close(self):
         self._fin()
+
+    def set_feature_counts(self, counts):
+        """Ragged batch: pair b tracks its first counts[b] features only (None: all n)."""
+        if counts is None:
+            _lib.check(self._lib.lego_klt_batch_set_feature_counts(self._h, None), "lego_klt_batch_set_feature_counts")
+            return
+        c = np.ascontiguousarray(counts, np.int32)
+        if c.shape != (self.B,):
+            raise ValueError("counts must have one entry per pair")
+        _lib.check(self._lib.lego_klt_batch_set_feature_counts(self._h, c.ctypes.data), "lego_klt_batch_set_feature_counts")
+
+    def set_pipeline_chunks(self, chunks: int):
+        _lib.check(self._lib.lego_klt_batch_set_pipeline_chunks(self._h, int(chunks)), "lego_klt_batch_set_pipeline_chunks")
 
     def _check_inputs(self, imgs1, imgs2, kp1, kp2):
         for a in (imgs1, imgs2):
@@ -289,6 +303,55 @@ class Batch:
                                                     imgs2.ctypes.data, kp1.ctypes.data, kp2_inout.ctypes.data,
                                                     success.ctypes.data, C.byref(st)), "lego_klt_track_batched")
         return st
+
+
+class MultiTracker:
+    """lego_klt_multi: one process driving several devices, B pairs cut into contiguous blocks (one per device)."""
+
+    def __init__(self, devices, batch: int, rows: int, cols: int, n_per_pair: int, levels: int = 4, step: int | None = None):
+        self._lib = _lib.load()
+        self.B, self.rows, self.cols, self.n, self.levels, self.step = batch, rows, cols, n_per_pair, levels, step or cols
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _lib.check(self._lib.lego_klt_multi_create(dev, len(devices), batch, cols, rows, self.step, n_per_pair, levels,
+                                                   C.byref(h)), "lego_klt_multi_create")
+        self._h = h
+        self._fin = weakref.finalize(self, self._lib.lego_klt_multi_destroy, h)
+
+    def close(self):
+        self._fin()
+
+    def shards(self):
+        """[(device, first_pair, n_pairs)] of the block partition."""
+        out, i = [], 0
+        while True:
+            d, f, c = C.c_int(), C.c_int(), C.c_int()
+            n = self._lib.lego_klt_multi_shard(self._h, i, C.byref(d), C.byref(f), C.byref(c))
+            if n < 0:
+                raise _lib.KltError(n, "lego_klt_multi_shard")
+            out.append((d.value, f.value, c.value))
+            i += 1
+            if i >= n:
+                return out
+
+    def set_feature_counts(self, counts):
+        c = None if counts is None else np.ascontiguousarray(counts, np.int32)
+        _lib.check(self._lib.lego_klt_multi_set_feature_counts(self._h, None if c is None else c.ctypes.data),
+                   "lego_klt_multi_set_feature_counts")
+
+    def track(self, imgs1, imgs2, kp1, kp2_inout, success, params: Params | None = None):
+        """lego_klt_multi_track: every block through lego_klt_track_batched on its device, concurrently."""
+        params = params or make_params(self.levels)
+        st = Stats()
+        _lib.check(self._lib.lego_klt_multi_track(self._h, C.byref(params), imgs1.ctypes.data, imgs2.ctypes.data,
+                                                  kp1.ctypes.data, kp2_inout.ctypes.data, success.ctypes.data,
+                                                  C.byref(st)), "lego_klt_multi_track")
+        return st
+
+
+def kernel_launches() -> int:
+    """Kernels this library has launched in this process so far (lego_klt_kernel_launches)."""
+    return int(_lib.load().lego_klt_kernel_launches())
 
 
 _default = {}

@@ -14,9 +14,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/lego_klt.h"
 
 namespace legoklt {
+
+// Kernel launches issued by this library since it was loaded (lego_klt_kernel_launches): every launch_* wrapper
+// calls note_launch() once per <<<>>> it issues.  Defined in lego_klt_capi.cu.
+extern std::atomic<long long> g_kernel_launches;
+inline void note_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 constexpr int kMaxLevels = LEGO_KLT_MAX_LEVELS;
 constexpr int kMaxPatch = 13;       // (patch_hi - patch_lo + 1) <= 13
@@ -70,7 +77,9 @@ struct SolverArgs {
     float2 *kp2_out;          // [B*n]
     uint8_t *success;         // [B*n]
     unsigned long long *stats;  // [kStatCount]
-    int n_per_pair;
+    int n_per_pair;           // feature slots per pair (the batch's stride); image = id / n_per_pair
+    const int *pair_count;    // [B] valid features of each pair (<= n_per_pair), or null = all: a slot at or beyond its
+                              // pair's count is not tracked (kp2_out = kp2_init, success = 0, no counters)
     int n_total;              // features in this launch: global ids f0 .. f0 + n_total - 1
     int f0;                   // first global feature id (chunked batches); image = id / n_per_pair
     int patch_lo, patch_hi;
@@ -176,6 +185,17 @@ __device__ __forceinline__ void ldlt2_solve(double h00, double h10, double h11, 
 }
 
 __device__ __forceinline__ bool not_finite(double v) { return isnan(v) || isinf(v); }
+
+// Ragged batches: is feature slot f (of image img) beyond its pair's feature count?
+__device__ __forceinline__ bool slot_unused(const SolverArgs &args, int f, int img) {
+    return args.pair_count != nullptr && (f - img * args.n_per_pair) >= __ldg(args.pair_count + img);
+}
+
+// What an unused slot receives (once, by whichever kernel meets it first).
+__device__ __forceinline__ void write_unused_slot(const SolverArgs &args, int f) {
+    args.kp2_out[f] = args.kp2_init[f];
+    args.success[f] = 0;
+}
 
 #endif  // __CUDACC__
 

@@ -16,6 +16,10 @@ klt_exact_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant_
     if (t >= args.n_total) return;
     const int i = args.f0 + t;
     const int img = i / args.n_per_pair;
+    if (slot_unused(args, i, img)) {
+        write_unused_slot(args, i);
+        return;
+    }
     const int L = pyr.levels;
     const bool inverse = args.inverse != 0;
 
@@ -117,6 +121,7 @@ cudaError_t launch_klt_exact(const PyramidView &pyr, const SolverArgs &args, cud
     int block = 128;
     int grid = (args.n_total + block - 1) / block;
     klt_exact_kernel<<<grid, block, 0, stream>>>(pyr, args);
+    note_launch();
     return cudaGetLastError();
 }
 

@@ -106,10 +106,13 @@ static_assert(kTplStride >= kI1Count + 1 && (kTplStride / 4) % 2 == 1 && kTplStr
 #define LANE_BATCH 1
 #endif
 #ifndef LANE_T
-#define LANE_T 96
+#define LANE_T 64
+#endif
+#ifndef LANE_PINGPONG
+#define LANE_PINGPONG 1
 #endif
 #ifndef LANE_CTAS
-#define LANE_CTAS 3
+#define LANE_CTAS 5
 #endif
 constexpr int kSetupBatch = LANE_BATCH;                       // blocked threads per warp that trigger set-up
 
@@ -117,10 +120,9 @@ enum : int { ST_FETCH = 0, ST_LEVEL = 1, ST_RUN = 2, ST_DONE = 3 };
 
 template <int T>
 struct LaneSmem {
-    // granules of one thread: window rows (2 each), template rows (kTplPitch / 4 each), row weights (pairs 1-frac, frac)
+    // granules of one thread: window rows (2 each), template rows (kTplPitch / 4 each)
     static constexpr int kGranTpl = 2 * kWin2Rows,   // (window granules first)
-                         kGranWy = kGranTpl + kI1Count / 4,
-                         kGranTotal = kGranWy + (2 * G + 3) / 4;
+                         kGranTotal = kGranTpl + kI1Count / 4;
     uint4 g[kGranTotal][T];
     // per-warp ring of fetched features: one global atomic + coalesced keypoint loads per 32 features
     float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
@@ -146,9 +148,9 @@ __device__ __forceinline__ float bilerp(float omx, float xx, float omy, float yy
 // One grid axis (columns or rows) of the shared sample grid.  S = kd + d, kd = double(float(k+c)) - c for the
 // pixel offsets c of one coordinate family (see axis_families); the reference forms
 // float(double(float(k+c)) + d [+-1]), which for that family is S + g - 4 up to 2 ulp64.
-// Per grid index g it yields the two bilinear factors the reference would use:
-//     om[g] = 1 - frac   (weight of the tap at the integer coordinate)
-//     fr[g] = frac       (weight of the tap at integer coordinate + 1)
+// Per grid index g, axis_factor() yields the two bilinear factors the reference would use:
+//     om = 1 - frac   (weight of the tap at the integer coordinate)
+//     fr = frac       (weight of the tap at integer coordinate + 1)
 // with the nominal integer coordinate of index g being origin + g (consecutive), and the border
 // semantics of algorithm.h:42-55 folded into the factors:
 //   * X <  0      : clamped to 0        -> (1, 0); the window holds replicated border pixels
@@ -157,42 +159,76 @@ __device__ __forceinline__ float bilerp(float omx, float xx, float omy, float yy
 //                   replicated border pixel sits one further
 //   * sliver X in (limit-1, limit), not clamped: the +1 tap is data[.. + 1] on the next row (columns:
 //     the wrap pixel, true factors) or past the buffer = 0 (rows: fr := 0, om = 1 - frac).
-// Returns 0, or the reason (kStatDefer*) the pass cannot be proven bit-identical on this grid.
-template <bool IS_ROW>
-__device__ __forceinline__ int grid_axis(double kd, double d, int limit, int &origin, float (&fr)[G], float (&om)[G]) {
-    const double S = kd + d;
-    if (!(fabs(S) < 1.0e6)) return kStatDeferRange;
+// Condition (b) of the header comment is tracked as a running minimum `near` over the indices of the axis (see
+// axis_near): the pass is provably bit-identical on this grid iff axis_ok(near) afterwards.
+// (The nominal coordinate needs no check: for |S| < 1e6 every D_g = fl64(S + n) lies within half an ulp64 of the
+// real sum, so fl32(D_g) is in [origin + g, origin + g + 1] -- integers are fp32-representable -- and a factor pair
+// (0, 1) at the nominal column equals the reference's (1, 0) one column further, term by term.)
+struct Axis {
+    double S;         // kd + d
+    int origin;       // nominal integer coordinate of grid index 0: floor(S + LO - 1)
+    float forigin;    // (float)origin
+    unsigned tie;     // 1 if an EXACT rounding tie is harmless on this axis (see axis_begin), else 0
+    bool in_range;    // |S| < 1e6
+};
+
+__device__ __forceinline__ Axis axis_begin(double kd, double d) {
+    Axis ax;
+    ax.S = kd + d;
+    ax.in_range = fabs(ax.S) < 1.0e6;
     // An EXACT tie (D on an fp32 rounding midpoint) is safe when every double sum involved is exact:
     // then all of the reference's ways of forming the coordinate give the same double, and round-half-
     // even gives the same float.  TwoSum error of S, and 4 spare low bits so that S + c stays exact.
-    const double bb = S - kd;
-    const double err = (kd - (S - bb)) + (d - bb);
-    const bool tie_ok = (err == 0.0) && ((__double2loint(S) & 0xF) == 0) && (fabs(S) >= 1.0);
-    const double D0 = S + (double)(LO - 1);
-    origin = __double2int_rd(D0);  // nominal integer coordinate of grid index 0
-    int why = 0;                   // 0 = regular, else the kStatDefer* reason
-    const float flimit = (float)limit, flast = (float)(limit - 1);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const double D = S + (double)(LO - 1 + g);
-        const float X = (float)D;
-        // (b) distance of D's discarded mantissa bits from the fp32 rounding midpoint
-        const int dist = (__double2loint(D) & 0x1FFFFFFF) - 0x10000000;
-        const bool margin_bad = (dist == 0) ? !tie_ok : (abs(dist) <= 16);
-        const bool clamp_lo = X < 0.f, clamp_hi = X >= flimit, clamped = clamp_lo || clamp_hi;
-        const float f_raw = __fadd_rn(X, -(float)(origin + g));
-        const bool nominal_bad = !clamped && !((f_raw >= 0.f) && (f_raw <= 1.f));
-        why = margin_bad ? kStatDeferMargin : why;
-        why = nominal_bad ? kStatDeferNominal : why;
-        // selects only (no branches): clamped -> (om, fr) = (1, 0), or (0, 1) at the wrap column
-        const bool at_wrap = !IS_ROW && clamp_hi && (origin + g == limit);
-        float f = clamped ? (at_wrap ? 1.f : 0.f) : f_raw;
-        const float o = clamped ? (at_wrap ? 0.f : 1.f) : __fadd_rn(1.f, -f_raw);
-        if (IS_ROW) f = (!clamped && X > flast) ? 0.f : f;  // taps below the last row read zeros
-        fr[g] = f;
-        om[g] = o;
+    const double bb = ax.S - kd;
+    const double err = (kd - (ax.S - bb)) + (d - bb);
+    ax.tie = ((err == 0.0) && ((__double2loint(ax.S) & 0xF) == 0) && (fabs(ax.S) >= 1.0)) ? 1u : 0u;
+    ax.origin = __double2int_rd(ax.S + (double)(LO - 1));
+    ax.forigin = (float)ax.origin;
+    return ax;
+}
+
+// Distance of D's discarded mantissa bits from the fp32 rounding midpoint, folded into a running minimum:
+// |dist| for a non-tie, and for an exact tie 0 (tie not provably harmless) or UINT_MAX (harmless).
+__device__ __forceinline__ unsigned axis_near(unsigned near, double D, unsigned tie) {
+    const int dist = (__double2loint(D) & 0x1FFFFFFF) - 0x10000000;
+    return min(near, (unsigned)abs(dist) - tie);
+}
+
+// (b) holds on the axis iff no index came within 16 ulp64 of a midpoint (harmless ties excepted).
+__device__ __forceinline__ bool axis_ok(unsigned near, unsigned tie) { return near >= 17u - tie; }
+
+// n = (double)(LO - 1 + g), fg = (float)(origin + g); flimit = (float)limit, flast = (float)(limit - 1).
+template <bool IS_ROW>
+__device__ __forceinline__ void axis_factor(const Axis &ax, double n, float fg, float flimit, float flast, unsigned &near,
+                                            float &om, float &fr) {
+    const double D = ax.S + n;
+    const float X = (float)D;
+    near = axis_near(near, D, ax.tie);
+    const float f_raw = __fadd_rn(X, -fg);
+    const float o_raw = __fadd_rn(1.f, -f_raw);
+    const bool clamped = (X < 0.f) || (X >= flimit);
+    if (IS_ROW) {
+        fr = ((X < 0.f) || (X > flast)) ? 0.f : f_raw;  // clamped, or taps below the last row read zeros
+        om = clamped ? 1.f : o_raw;
+    } else {
+        const float fc = ((X >= flimit) && (fg == flimit)) ? 1.f : 0.f;  // the wrap column
+        fr = clamped ? fc : f_raw;
+        om = clamped ? __fadd_rn(1.f, -fc) : o_raw;
     }
-    return why;
+}
+
+// The whole axis at once (template kernel; columns of the solver).  Returns false if the pass cannot be proven
+// bit-identical on this grid.
+template <bool IS_ROW>
+__device__ __forceinline__ bool grid_axis(double kd, double d, int limit, int &origin, float (&fr)[G], float (&om)[G]) {
+    const Axis ax = axis_begin(kd, d);
+    origin = ax.origin;
+    const float flimit = (float)limit, flast = (float)(limit - 1);
+    unsigned near = 0xFFFFFFFFu;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        axis_factor<IS_ROW>(ax, (double)(LO - 1 + g), __fadd_rn(ax.forigin, (float)g), flimit, flast, near, om[g], fr[g]);
+    return ax.in_range && axis_ok(near, ax.tie);
 }
 
 // Coordinate families of one axis (condition (a), generalised).  The reference forms the sample coordinate of
@@ -427,9 +463,10 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     const long long item = (long long)blockIdx.x * T + tid;
     const int level = L - 1 - (int)(item / n_pad);   // (coarse levels first)
     const int idx = (int)(item % n_pad);
-    const bool valid = level >= 0 && idx < args.n_total;
-    const int f = args.f0 + (valid ? idx : 0);
+    const bool in_range = level >= 0 && idx < args.n_total;
+    const int f = args.f0 + (in_range ? idx : 0);
     const int img = f / args.n_per_pair;
+    const bool valid = in_range && !slot_unused(args, f, img);  // (unused slots of a ragged batch get an empty record)
     const LevelView &lv = pyr.lv[valid ? level : 0];
     const float2 k0 = args.kp1[f];
     const float kx = level_coord(k0.x, L, level), ky = level_coord(k0.y, L, level);
@@ -441,13 +478,13 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     bool regular = valid && axis_families(kx, mBx, ex) && axis_families(ky, mBy, ey);
     if (regular) {
         // float(kx + c) == (double)kx + c + e_c exactly: the template grid is the d = 0 grid of each family
-        regular = (grid_axis<false>((double)kx, 0.0, lv.cols, ixn, xx, omx) |
-                   grid_axis<true>((double)ky, 0.0, lv.rows, iyn, yy, omy)) == 0;
+        const bool okx = grid_axis<false>((double)kx, 0.0, lv.cols, ixn, xx, omx);
+        regular = grid_axis<true>((double)ky, 0.0, lv.rows, iyn, yy, omy) && okx;
     }
     if (regular && mBx) {  // columns of family B take their factors from the grid shifted by eps
         float xb[G], ob[G];
         int ib = 0;
-        regular = grid_axis<false>((double)kx + ex, 0.0, lv.cols, ib, xb, ob) == 0 && ib == ixn;
+        regular = grid_axis<false>((double)kx + ex, 0.0, lv.cols, ib, xb, ob) && ib == ixn;
 #pragma unroll
         for (int x = 0; x < P; ++x)
             if ((mBx >> x) & 1u) {
@@ -458,7 +495,7 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     if (regular && mBy) {
         float yb[G], ob[G];
         int ib = 0;
-        regular = grid_axis<true>((double)ky + ey, 0.0, lv.rows, ib, yb, ob) == 0 && ib == iyn;
+        regular = grid_axis<true>((double)ky + ey, 0.0, lv.rows, ib, yb, ob) && ib == iyn;
 #pragma unroll
         for (int y = 0; y < P; ++y)
             if ((mBy >> y) & 1u) {
@@ -613,6 +650,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         }
                         a1 = args.kp1[gid];
                         a2 = args.kp2_init[gid];
+                        if (slot_unused(args, gid, gid / args.n_per_pair)) {  // ragged batch: nothing to track here
+                            if (!FAMILIES) write_unused_slot(args, gid);
+                            keep = false;
+                        }
                     }
                     const unsigned km = __ballot_sync(FULL, keep);
                     if (keep) {
@@ -728,9 +769,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         float xx[G], omx[G];
         int ixn = 0, iyn = 0;
         unsigned pmx = kPMask, pmy = kPMask;  // pixels (columns / rows) that belong to this sub-pass
+        Axis yax;
         if (run) {
             const LevelView &lv = pyr.lv[level];
-            float yy[G], omy[G];
             double kxd = (double)kx, kyd = (double)ky;
             if (FAMILIES && (fam & kPMask2)) {  // this sub-pass works on one (x family, y family) combination
                 const unsigned mBx = fam & kPMask, mBy = (fam >> kFamY) & kPMask, sub = (fam >> kFamSub) & 3u;
@@ -746,9 +787,12 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 pmx = fx ? mBx : (~mBx & kPMask);
                 pmy = fy ? mBy : (~mBy & kPMask);
             }
-            const int whyx = grid_axis<false>(kxd, dx, lv.cols, ixn, xx, omx);
-            const int whyy = grid_axis<true>(kyd, dy, lv.rows, iyn, yy, omy);
-            if (whyx | whyy) {
+            const bool okx = grid_axis<false>(kxd, dx, lv.cols, ixn, xx, omx);
+            // rows: only the origin here; the row factors are formed inside the row loop of the pass (axis_factor),
+            // their condition (b) is known after the loop
+            yax = axis_begin(kyd, dy);
+            iyn = yax.origin;
+            if (!(okx && yax.in_range)) {
                 // cannot prove the shared grid bit-identical for this pass (rare): exact per-pixel pass
                 atomicAdd(&sm.stats[kStatSlowPath], 1u);
             } else if (!(ixn >= wx0 && ixn + (G + 1) <= wx0 + kWin2Words * 4 && iyn >= wy0 && iyn + (G + 1) <= wy0 + kWin2Rows)) {
@@ -762,10 +806,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 atomicAdd(&sm.stats[kStatSlowPath], 1u);
             } else {
                 fast = true;
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    reinterpret_cast<float2 *>(&sm.g[LaneSmem<T>::kGranWy + (g >> 1)][tid])[g & 1] = make_float2(omy[g], yy[g]);
-                }
             }
         }
 
@@ -778,18 +818,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             constexpr int kI1Stride = T * 4;   // floats between consecutive granules of one thread
             double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
             bool solve_now = true;
-            if (!fast) {
-                // the reference formulation covers the whole patch whatever its families: restart the pass
-                double sums[6];
-                exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, kI1Stride, kx, ky, dx, dy, sums);
-                sb0 = sums[0];
-                sb1 = sums[1];
-                sc = sums[2];
-                s00 = sums[3];
-                s01 = sums[4];
-                s11 = sums[5];
-                fam &= kPMask2;
-            } else {
+            if (fast) {
             const int ox = ixn - wx0;
             const int sh = (ox & 3) * 8;
             WinRef wr;
@@ -800,11 +829,16 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < kRowWords; ++k) wr.off[k] = ((kw + k) >> 2) * (T * 4) + ((kw + k) & 3);
             }
-            const float *wyg = reinterpret_cast<const float *>(&sm.g[LaneSmem<T>::kGranWy][tid]);
-            auto row_weights = [&](int r, float &om, float &fr) {  // pair r: granule r >> 1, half r & 1
-                const float2 v = *reinterpret_cast<const float2 *>(wyg + (r >> 1) * (T * 4) + (r & 1) * 2);
-                om = v.x;
-                fr = v.y;
+            // Row factors of grid row r, formed when the row is sampled: n_r = (double)(LO - 1 + r) and
+            // fg_r = (float)(origin + r) are carried through the loop (both exact).
+            const float frows = (float)lv.rows, flastrow = (float)(lv.rows - 1);
+            double n_r = (double)(LO - 1);
+            float fg_r = yax.forigin;
+            unsigned near_y = 0xFFFFFFFFu;
+            auto row_weights = [&](float &om, float &fr) {
+                axis_factor<true>(yax, n_r, fg_r, frows, flastrow, near_y, om, fr);
+                n_r += 1.0;
+                fg_r = __fadd_rn(fg_r, 1.f);
             };
             auto template_row = [&](int y, float (&v)[P]) {          // kTplPitch / 4 granules per row
 #pragma unroll
@@ -830,11 +864,11 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             float om_r, fr_r;
             load_row10_packed(wr, 0, sh, rowA);
             load_row10_packed(wr, 1, sh, rowB);
-            row_weights(0, om_r, fr_r);
+            row_weights(om_r, fr_r);
             sample_row_packed(OMX, XX, om_r, fr_r, rowA, rowB, args.one, Sa);
             rowA = rowB;
             load_row10_packed(wr, 2, sh, rowB);
-            row_weights(1, om_r, fr_r);
+            row_weights(om_r, fr_r);
             sample_row_packed(OMX, XX, om_r, fr_r, rowA, rowB, args.one, Sb);
             rowA = rowB;
             // One patch row per step: sample row r from pixel rows r, r+1 (PB is loaded here), then the 7 pixels of
@@ -842,7 +876,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[kNP], const float2 (&SB)[kNP], float2 (&SC)[kNP]) {
                 load_row10_packed(wr, r + 1, sh, PB);
                 float om_s, fr_s, tpl[P];
-                row_weights(r, om_s, fr_s);
+                row_weights(om_s, fr_s);
                 template_row(r - 2, tpl);
                 sample_row_packed(OMX, XX, om_s, fr_s, PA, PB, args.one, SC);
                 const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
@@ -862,9 +896,33 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     s11 = fma(gy, gy, s11);
                 }
             };
-            // Rolled on purpose.  Measured alternatives, all slower on B200 (profiles/README.md): the fully unrolled
-            // pass (instruction-fetch bound), three steps per trip with the row roles rotating by name (-11 %
-            // instructions, +3 % time), manual software pipelining of the 13 shared-memory loads (+4 % time).
+            // Rolled on purpose: the fully unrolled pass was instruction-fetch bound (profiles/README.md).
+#if LANE_PINGPONG
+            // Two steps per trip: the pixel rows swap roles by name (no moves), the three sample rows are renamed with
+            // one rotation per trip (2 * kNP float2 moves per two steps instead of 4 * kNP per step).
+            int r = 2;
+            if ((G - 2) & 1) {  // odd number of steps: the first one is peeled
+                step(2, rowA, rowB, Sa, Sb, Sc);
+                rowA = rowB;
+#pragma unroll
+                for (int j = 0; j < kNP; ++j) {
+                    Sa[j] = Sb[j];
+                    Sb[j] = Sc[j];
+                }
+                r = 3;
+            }
+#pragma unroll 1
+            for (; r < G; r += 2) {
+                step(r, rowA, rowB, Sa, Sb, Sc);      // pixel row r+1 -> rowB, sample row r -> Sc
+                step(r + 1, rowB, rowA, Sb, Sc, Sa);  // pixel row r+2 -> rowA, sample row r+1 -> Sa
+#pragma unroll
+                for (int j = 0; j < kNP; ++j) {       // (older, newer) = (Sc, Sa) -> (Sa, Sb)
+                    const float2 t = Sa[j];
+                    Sa[j] = Sc[j];
+                    Sb[j] = t;
+                }
+            }
+#else
 #pragma unroll 1
             for (int r = 2; r < G; ++r) {
                 step(r, rowA, rowB, Sa, Sb, Sc);
@@ -875,15 +933,31 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     Sb[j] = Sc[j];
                 }
             }
+#endif
 
-            if (FAMILIES && (fam & kPMask2)) {
+            if (!axis_ok(near_y, yax.tie)) {  // condition (b) failed on some grid row (rare): redo the pass exactly
+                fast = false;
+                atomicAdd(&sm.stats[kStatSlowPath], 1u);
+            }
+            }
+            if (!fast) {
+                // the reference formulation covers the whole patch whatever its families: restart the pass
+                double sums[6];
+                exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, kI1Stride, kx, ky, dx, dy, sums);
+                sb0 = sums[0];
+                sb1 = sums[1];
+                sc = sums[2];
+                s00 = sums[3];
+                s01 = sums[4];
+                s11 = sums[5];
+                fam &= kPMask2;
+            } else if (FAMILIES && (fam & kPMask2)) {
                 // multi-family level: this trip covered one (x family, y family) combination; partial sums
                 // wait in global scratch until the last combination has been added (rare, so out of line)
                 const unsigned sub = (fam >> kFamSub) & 3u;
                 const unsigned nsub = ((fam & kPMask) ? 2u : 1u) * ((fam & (kPMask << kFamY)) ? 2u : 1u);
                 solve_now = multi_family_step(parked, sub, nsub, sb0, sb1, sc, s00, s01, s11);
                 fam = (fam & kPMask2) | (solve_now ? 0u : ((sub + 1u) << kFamSub));
-            }
             }
             if (solve_now) {
 
@@ -966,6 +1040,7 @@ cudaError_t LANE_FN(launch_klt_template)(const PyramidView &pyr, const SolverArg
     const long long items = (long long)((args.n_total + 31) & ~31) * pyr.levels;
     const int grid = (int)((items + kTplThreads - 1) / kTplThreads);
     kernel<<<grid, kTplThreads, 0, stream>>>(pyr, args);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -975,8 +1050,14 @@ cudaError_t LANE_FN(launch_klt_template)(const PyramidView &pyr, const SolverArg
 cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
                                      cudaStream_t families_stream) {
     if (args.n_total <= 0) return cudaSuccess;
-    const size_t smem = sizeof(LaneSmem<kLaneThreads>);
-    int grid = sm_count * kLaneMinCtas;
+#ifndef LANE_SMEM_PAD
+#define LANE_SMEM_PAD 0        // occupancy experiments: extra dynamic shared memory per CTA (fewer CTAs per SM)
+#endif
+#ifndef LANE_GRID_CTAS
+#define LANE_GRID_CTAS LANE_CTAS
+#endif
+    const size_t smem = sizeof(LaneSmem<kLaneThreads>) + LANE_SMEM_PAD;
+    int grid = sm_count * LANE_GRID_CTAS;
     const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
     {
         // multi-family features (sub-pixel keypoints near a power of two): the list length is only known on
@@ -989,6 +1070,7 @@ cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &a
         a2.list_count = args.fam_count;
         a2.work_counter = args.work_counter + 3;
         kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, families_stream>>>(pyr, a2);
+        note_launch();
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
@@ -997,6 +1079,7 @@ cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &a
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, args);
+        note_launch();
         return cudaGetLastError();
     }
 }

@@ -169,6 +169,10 @@ klt_warp_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     for (int wi = blockIdx.x * kWarpsPerCta + warp; wi < n_work; wi += warps_total) {
         const int f = args.list ? args.list[wi] : args.f0 + wi;
         const int img = f / args.n_per_pair;
+        if (slot_unused(args, f, img)) {  // (warp-uniform)
+            if (lane == 0) write_unused_slot(args, f);
+            continue;
+        }
         float2 k1 = args.kp1[f], k2 = args.kp2_init[f];
         k1.x = (float)(k1.x * scale_top);  // src/algorithm.cpp:160-169
         k1.y = (float)(k1.y * scale_top);
@@ -481,6 +485,7 @@ cudaError_t launch_klt_warp(const PyramidView &pyr, const WarpKernelMaps *maps, 
         klt_warp_kernel<4, 0><<<grid, block, 0, stream>>>(pyr, *maps, args);
     else
         klt_warp_kernel<6, 0><<<grid, block, 0, stream>>>(pyr, *maps, args);
+    note_launch();
     return cudaGetLastError();
 }
 

@@ -10,10 +10,14 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "klt_kernels.h"
 
 using namespace legoklt;
+
+std::atomic<long long> legoklt::g_kernel_launches{0};
 
 namespace {
 
@@ -70,6 +74,10 @@ struct lego_klt_ctx {
     int stage_next = 0;
     uint8_t *pin_io = nullptr;         // keypoint / result staging of the single-pair paths
     size_t pin_io_bytes = 0;
+    // Ownership: batches and images keep a pointer to their context.  lego_klt_destroy with handles still alive only
+    // marks the context; it is torn down when the last batch / image handle is destroyed (see include/lego_klt.h).
+    int live_handles = 0;
+    bool destroy_requested = false;
 };
 
 struct lego_klt_batch {
@@ -91,13 +99,20 @@ struct lego_klt_batch {
     unsigned long long *h_stats = nullptr;  // pinned
     cudaEvent_t ev[EV_COUNT] = {};
     cudaEvent_t ring[kRing][3] = {};  // run r: [0] before pyramid, [1] after pyramid, [2] after solver
-    long long runs = 0;
+    long long runs = 0;            // runs of any kind (epoch of the LANE ownership flags)
+    long long timed_runs = 0;      // runs that recorded a slot of `ring` (lego_klt_batch_timings)
+    bool lane_ready = false;       // every LANE-path allocation below exists
     int *d_work = nullptr;         // per chunk: [0] lane work counter, [1] deferred count, [2] family count,
                                    // [3] lane<FAMILIES> work counter
     int *d_defer_list = nullptr;   // [B * n_cap]
     int *d_fam_list = nullptr;     // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
     size_t templates_bytes = 0;
+    int *d_pair_count = nullptr;   // ragged batches: valid features per pair (lego_klt_batch_set_feature_counts)
+    std::vector<int> h_pair_count;
+    bool ragged = false;
+    int pipeline_chunks = 0;       // lego_klt_batch_set_pipeline_chunks (0 = default)
+    unsigned long long n_valid = 0;  // sum of the counts
     int *d_feat_flag = nullptr;    // LANE path: per-feature 'handed to the warp kernel' flag
     double *d_scratch = nullptr;   // LANE kernel: per-thread partial sums of multi-family levels
     cudaStream_t side = nullptr;   // deferred features run here, concurrently with the lane kernel
@@ -109,6 +124,8 @@ struct lego_klt_batch {
     cudaEvent_t ev_done[kMaxChunks] = {};
     cudaEvent_t ev_join_c[kMaxChunks] = {};  // side-stream work of chunk c (deferred features, FAMILIES instance) done
     bool uploaded = false, ran = false, pyramids_valid = false, last_chunked = false;
+    bool counted = false;          // created through lego_klt_batch_create (counts in ctx->live_handles)
+    bool last_timed = false;       // the last run recorded a ring slot
     lego_klt_params last_params;
 };
 
@@ -124,9 +141,29 @@ struct lego_klt_image {
     uint8_t *d_full = nullptr;     // landing buffer of lego_klt_image_upload_fullres (grow-only)
     size_t full_bytes = 0;
     bool valid = false;
+    bool counted = false;          // counts in ctx->live_handles
 };
 
 namespace {
+
+void ctx_teardown(lego_klt_ctx *ctx);
+
+void ctx_release_handle(lego_klt_ctx *ctx) {
+    if (--ctx->live_handles == 0 && ctx->destroy_requested) ctx_teardown(ctx);
+}
+
+void ctx_teardown(lego_klt_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->d_tri) cudaFree(ctx->d_tri);
+    for (auto &sl : ctx->stage) {
+        if (sl.p) cudaFreeHost(sl.p);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (ctx->pin_io) cudaFreeHost(ctx->pin_io);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
 
 int validate_params(const lego_klt_params *p, int levels_of_batch) {
     if (!p) return fail(LEGO_KLT_ERR_BAD_ARG, "params is null");
@@ -244,26 +281,48 @@ cudaError_t ingest_set(lego_klt_batch *b, int set, int img0, int nimg, cudaStrea
     return launch_ingest(b->d_tight + (size_t)set * set_bytes, b->view.lv[0], set, img0, nimg, stream);
 }
 
+void free_lane_buffers(lego_klt_batch *b) {
+    cudaFree(b->d_feat_flag);
+    cudaFree(b->d_scratch);
+    if (b->side) cudaStreamDestroy(b->side);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    b->d_feat_flag = nullptr;
+    b->d_scratch = nullptr;
+    b->side = nullptr;
+    b->ev_fork = b->ev_join = nullptr;
+    b->lane_ready = false;
+    cudaGetLastError();
+}
+
 int ensure_lane_buffers(lego_klt_batch *b, size_t template_bytes) {
-    // templates: sized for the patch in hand, re-allocated if a larger patch follows
+    // templates: sized for the patch in hand, re-allocated if a larger patch follows (both streams that read them
+    // are drained first)
     if (template_bytes > b->templates_bytes) {
         CU_TRY(cudaStreamSynchronize(b->ctx->stream));
+        if (b->side) CU_TRY(cudaStreamSynchronize(b->side));
         if (b->d_templates) cudaFree(b->d_templates);
         b->d_templates = nullptr;
         b->templates_bytes = 0;
         CU_TRY(cudaMalloc(&b->d_templates, template_bytes));
         b->templates_bytes = template_bytes;
     }
-    if (b->d_feat_flag) return LEGO_KLT_OK;
+    if (b->lane_ready) return LEGO_KLT_OK;
+    // all or nothing: a failure half way leaves no partly initialised state behind for the next call
     const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
-    CU_TRY(cudaMalloc(&b->d_feat_flag, cap * sizeof(int)));
     const size_t scratch = std::max(std::max(lane_scratch_bytes(b->ctx->sm_count), lane_scratch_bytes_p8(b->ctx->sm_count)),
                                     lane_scratch_bytes_p11(b->ctx->sm_count));
-    CU_TRY(cudaMalloc(&b->d_scratch, scratch));
-    CU_TRY(cudaMemset(b->d_feat_flag, 0, cap * sizeof(int)));
-    CU_TRY(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
-    CU_TRY(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    cudaError_t e;
+    if ((e = cudaMalloc(&b->d_feat_flag, cap * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_scratch, scratch)) != cudaSuccess ||
+        (e = cudaMemset(b->d_feat_flag, 0, cap * sizeof(int))) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
+        free_lane_buffers(b);
+        return fail(LEGO_KLT_ERR_CUDA, "allocating the LANE-path buffers: %s", cudaGetErrorString(e));
+    }
+    b->lane_ready = true;
     return LEGO_KLT_OK;
 }
 
@@ -290,6 +349,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.success = b->d_success;
     a.stats = b->d_stats;
     a.n_per_pair = b->n_active > 0 ? b->n_active : 1;
+    a.pair_count = b->ragged ? b->d_pair_count : nullptr;
     a.n_total = nimg * b->n_active;
     a.f0 = img0 * b->n_active;
     a.patch_lo = params->patch_lo;
@@ -351,6 +411,8 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         a.feat_flag = b->d_feat_flag;
         a.scratch = b->d_scratch;
         a.epoch = (int)((b->runs % 0x0fffffff) + 1);
+        if (a.epoch == 1 && b->runs > 0)  // the run counter wrapped: flags of earlier runs would look newer than this one
+            CU_TRY(cudaMemsetAsync(b->d_feat_flag, 0, cap * sizeof(int), st));
         CU_TRY(lane_patch == 7   ? launch_klt_template(view, a, st)
                : lane_patch == 8 ? launch_klt_template_p8(view, a, st)
                                  : launch_klt_template_p11(view, a, st));
@@ -386,7 +448,7 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
-    cudaEvent_t *ring = b->ring[b->runs % kRing];
+    cudaEvent_t *ring = b->ring[b->timed_runs % kRing];
     CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
     rc = run_range(b, params, 0, b->B, 0, ring);
     if (rc) return rc;
@@ -394,6 +456,8 @@ int batch_run(lego_klt_batch *b, const lego_klt_params *params) {
     CU_TRY(cudaEventRecord(b->ev[EV_PYR], ctx->stream));  // kept for the stats struct; see fill_stats
     CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
     ++b->runs;
+    ++b->timed_runs;
+    b->last_timed = true;
     b->ran = true;
     b->last_params = *params;
     return LEGO_KLT_OK;
@@ -412,7 +476,7 @@ cudaError_t run_times(lego_klt_batch *b, int r, float *ms_pyr, float *ms_solver)
 
 void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     memset(s, 0, sizeof(*s));
-    s->n_features = (uint64_t)b->B * (uint64_t)b->n_active;
+    s->n_features = b->ragged ? (uint64_t)b->n_valid : (uint64_t)b->B * (uint64_t)b->n_active;
     s->n_success = b->h_stats[kStatSuccess];
     s->n_nan = b->h_stats[kStatNan];
     s->n_out_of_image = b->h_stats[kStatOutOfImage];
@@ -423,9 +487,9 @@ void fill_stats(lego_klt_batch *b, lego_klt_stats *s) {
     for (int l = 0; l < kMaxLevels; ++l) s->gn_iters[l] = b->h_stats[kStatIters0 + l];
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev[EV_START], b->ev[EV_H2D]) == cudaSuccess) s->ms_h2d = ms;
-    if (b->runs > 0 && !b->last_chunked) {
+    if (b->timed_runs > 0 && !b->last_chunked && b->last_timed) {
         float mp = 0.f, msol = 0.f;
-        if (run_times(b, (int)((b->runs - 1) % kRing), &mp, &msol) == cudaSuccess) {
+        if (run_times(b, (int)((b->timed_runs - 1) % kRing), &mp, &msol) == cudaSuccess) {
             s->ms_pyramid = mp;
             s->ms_solver = msol;
         }
@@ -532,6 +596,8 @@ extern "C" {
 
 int lego_klt_abi_version(void) { return LEGO_KLT_ABI_VERSION; }
 
+long long lego_klt_kernel_launches(void) { return legoklt::g_kernel_launches.load(std::memory_order_relaxed); }
+
 const char *lego_klt_last_error(void) { return g_last_error.c_str(); }
 
 void lego_klt_default_params(lego_klt_params *p) {
@@ -585,18 +651,17 @@ int lego_klt_create(int device, lego_klt_ctx **out) {
 
 void lego_klt_destroy(lego_klt_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    if (ctx->single) lego_klt_batch_destroy(ctx->single);
-    if (ctx->d_tri) cudaFree(ctx->d_tri);
-    for (auto &sl : ctx->stage) {
-        if (sl.p) cudaFreeHost(sl.p);
-        if (sl.done) cudaEventDestroy(sl.done);
+    if (ctx->single) {
+        lego_klt_batch_destroy(ctx->single);
+        ctx->single = nullptr;
     }
-    if (ctx->pin_io) cudaFreeHost(ctx->pin_io);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    delete ctx;
+    if (ctx->live_handles > 0) {  // batches / images of the caller still point here: the last one tears down
+        ctx->destroy_requested = true;
+        return;
+    }
+    ctx_teardown(ctx);
 }
+
 
 int lego_klt_set_stream(lego_klt_ctx *ctx, void *cuda_stream) {
     if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
@@ -627,7 +692,12 @@ void lego_klt_free_pinned(void *p) {
 int lego_klt_batch_create(lego_klt_ctx *ctx, int batch, int cols, int rows, size_t step, int n_per_pair,
                           int levels, lego_klt_batch **out) {
     if (out) *out = nullptr;
-    return batch_alloc(ctx, batch, cols, rows, step, n_per_pair, levels, out);
+    int rc = batch_alloc(ctx, batch, cols, rows, step, n_per_pair, levels, out);
+    if (rc == LEGO_KLT_OK) {
+        (*out)->counted = true;
+        ++ctx->live_handles;
+    }
+    return rc;
 }
 
 void lego_klt_batch_destroy(lego_klt_batch *b) {
@@ -641,6 +711,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     for (int r = 0; r < kRing; ++r)
         for (int i = 0; i < 3; ++i)
             if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
+    cudaFree(b->d_pair_count);
     cudaFree(b->d_defer_list);
     cudaFree(b->d_fam_list);
     cudaFree(b->d_templates);
@@ -663,7 +734,10 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
     cudaFree(b->d_io);
     if (b->h_stats) cudaFreeHost(b->h_stats);
     cudaGetLastError();
+    lego_klt_ctx *ctx = b->ctx;
+    const bool counted = b->counted;
     delete b;
+    if (counted) ctx_release_handle(ctx);
 }
 
 int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t *imgs2, const float *kp1_xy,
@@ -686,6 +760,37 @@ int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t
     b->uploaded = true;
     b->pyramids_valid = false;
     b->last_chunked = false;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_batch_set_feature_counts(lego_klt_batch *b, const int *counts) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (b == b->ctx->single) return fail(LEGO_KLT_ERR_BAD_ARG, "internal batch");
+    if (!counts) {
+        b->ragged = false;
+        return LEGO_KLT_OK;
+    }
+    unsigned long long total = 0;
+    for (int i = 0; i < b->B; ++i) {
+        if (counts[i] < 0 || counts[i] > b->n_cap)
+            return fail(LEGO_KLT_ERR_BAD_ARG, "counts[%d] = %d is outside [0, %d]", i, counts[i], b->n_cap);
+        total += (unsigned long long)counts[i];
+    }
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    if (!b->d_pair_count) CU_TRY(cudaMalloc(&b->d_pair_count, (size_t)b->B * sizeof(int)));
+    CU_TRY(cudaStreamSynchronize(b->ctx->stream));  // an earlier copy may still read the host vector
+    b->h_pair_count.assign(counts, counts + b->B);
+    CU_TRY(cudaMemcpyAsync(b->d_pair_count, b->h_pair_count.data(), (size_t)b->B * sizeof(int), cudaMemcpyHostToDevice,
+                           b->ctx->stream));
+    b->ragged = true;
+    b->n_valid = total;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_batch_set_pipeline_chunks(lego_klt_batch *b, int chunks) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (chunks < 0 || chunks > kMaxChunks) return fail(LEGO_KLT_ERR_BAD_ARG, "chunks must be in [0, %d]", kMaxChunks);
+    b->pipeline_chunks = chunks;
     return LEGO_KLT_OK;
 }
 
@@ -715,12 +820,12 @@ int lego_klt_batch_download(lego_klt_batch *b, float *kp2_xy, uint8_t *success, 
 
 int lego_klt_batch_timings(lego_klt_batch *b, int last_n, float *ms_pyramid_avg, float *ms_solver_avg) {
     if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
-    if (last_n <= 0 || last_n > kRing || last_n > b->runs)
-        return fail(LEGO_KLT_ERR_BAD_ARG, "last_n must be in [1, min(%d, runs so far)]", kRing);
+    if (last_n <= 0 || last_n > kRing || last_n > b->timed_runs)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "last_n must be in [1, min(%d, lego_klt_batch_run calls so far)]", kRing);
     CU_TRY(cudaSetDevice(b->ctx->device));
     CU_TRY(cudaStreamSynchronize(b->ctx->stream));
     double sp = 0, ss = 0;
-    for (long long r = b->runs - last_n; r < b->runs; ++r) {
+    for (long long r = b->timed_runs - last_n; r < b->timed_runs; ++r) {
         float mp = 0.f, msol = 0.f;
         CU_TRY(run_times(b, (int)(r % kRing), &mp, &msol));
         sp += mp;
@@ -739,20 +844,13 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     // Equal chunks: more / smaller chunks shorten the pipeline tail but cost launches and solver efficiency
     // (measured: 10 chunks with a fine tail 6 % slower than 8 equal ones; a smaller LAST chunk of 8 or 16 pairs 5 % slower).
     int bounds[kMaxChunks + 1];
-    // Chunk count (measured, 256 pairs x 2000 features): integer source keypoints (freshly detected corners) 4 / 6 / 8 /
-    // 12 chunks -> 0.97 / 1.00 / 1.01 / 0.91e8 tracks/s; sub-pixel ones (tracked points fed back) 0.88 / 0.85 / 0.74 /
-    // 0.54e8, because a quarter of them take the two-family path, whose second persistent launch needs larger chunks to
-    // stay efficient.  A sample of the keypoints decides.
-    int n_chunks = b->B >= 32 ? 8 : (b->B >= 8 ? 4 : 1);
-    if (n_chunks == 8 && kp1_xy && b->n_active > 0) {
-        const size_t nt_all = (size_t)b->B * (size_t)b->n_active, stride = nt_all > 512 ? nt_all / 512 : 1;
-        int fractional = 0, seen = 0;
-        for (size_t i = 0; i < nt_all; i += stride, ++seen) {
-            const float x = kp1_xy[2 * i], y = kp1_xy[2 * i + 1];
-            fractional += (x != std::floor(x)) || (y != std::floor(y));
-        }
-        if (fractional * 10 > seen) n_chunks = 4;
-    }
+    // Chunk count (measured, 256 pairs x 2000 features, tracks/s end to end): integer source keypoints (freshly
+    // detected corners) 4 / 6 / 8 / 12 chunks -> 0.97 / 1.00 / 1.01 / 0.91e8; sub-pixel ones (tracked points fed back)
+    // 0.88 / 0.85 / 0.74 / 0.54e8, because a quarter of them take the two-family path, whose second persistent launch
+    // needs larger chunks to stay efficient.  One default for both (no look at the caller's data);
+    // lego_klt_batch_set_pipeline_chunks overrides it.
+    int n_chunks = b->B >= 32 ? 6 : (b->B >= 8 ? 4 : 1);
+    if (b->pipeline_chunks > 0) n_chunks = std::min(std::min(b->pipeline_chunks, kMaxChunks), b->B);
     for (int c = 0; c <= n_chunks; ++c) bounds[c] = (int)((long long)b->B * c / n_chunks);
     if (n_chunks == 1) {
         int rc = lego_klt_batch_upload(b, imgs1, imgs2, kp1_xy, kp2_xy);
@@ -794,27 +892,43 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
         CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
         CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, b->copy));
     }
-    for (int c = 0; c < n_chunks; ++c) {
-        const int img0 = bounds[c], img1 = bounds[c + 1];
-        const int nimg = img1 - img0;
-        if (nimg <= 0) continue;
-        CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));
-        CU_TRY(upload_set(b, 1, imgs2, img0, nimg, b->copy));
-        CU_TRY(cudaEventRecord(b->ev_chunk[c], b->copy));
-        CU_TRY(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
-        CU_TRY(ingest_set(b, 0, img0, nimg, st));
-        CU_TRY(ingest_set(b, 1, img0, nimg, st));
-        rc = run_range(b, params, img0, nimg, c, nullptr, nullptr, nullptr, b->ev_join_c[c]);
-        if (rc) return rc;
-        last_chunk = c;
-        if (n) {  // this chunk's results go home while the next chunk computes
-            const size_t off = (size_t)img0 * n, cnt = (size_t)nimg * n;
-            CU_TRY(cudaEventRecord(b->ev_done[c], st));
-            CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_done[c], 0));
-            if (b->side) CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_join_c[c], 0));  // (its side-stream work, if any)
-            CU_TRY(cudaMemcpyAsync(kp2_xy + 2 * off, b->d_kp2_out + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, b->d2h));
-            CU_TRY(cudaMemcpyAsync(success + off, b->d_success + off, cnt, cudaMemcpyDeviceToHost, b->d2h));
+    // (a failure inside the loop leaves asynchronous copies from / to the caller's buffers in flight: drain every
+    // stream before reporting it)
+    auto enqueue_chunks = [&]() -> int {
+        for (int c = 0; c < n_chunks; ++c) {
+            const int img0 = bounds[c], img1 = bounds[c + 1];
+            const int nimg = img1 - img0;
+            if (nimg <= 0) continue;
+            CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));
+            CU_TRY(upload_set(b, 1, imgs2, img0, nimg, b->copy));
+            CU_TRY(cudaEventRecord(b->ev_chunk[c], b->copy));
+            CU_TRY(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
+            CU_TRY(ingest_set(b, 0, img0, nimg, st));
+            CU_TRY(ingest_set(b, 1, img0, nimg, st));
+            int rc2 = run_range(b, params, img0, nimg, c, nullptr, nullptr, nullptr, b->ev_join_c[c]);
+            if (rc2) return rc2;
+            last_chunk = c;
+            if (n) {  // this chunk's results go home while the next chunk computes
+                const size_t off = (size_t)img0 * n, cnt = (size_t)nimg * n;
+                CU_TRY(cudaEventRecord(b->ev_done[c], st));
+                CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_done[c], 0));
+                if (b->side) CU_TRY(cudaStreamWaitEvent(b->d2h, b->ev_join_c[c], 0));  // (its side-stream work, if any)
+                CU_TRY(cudaMemcpyAsync(kp2_xy + 2 * off, b->d_kp2_out + off, cnt * sizeof(float2), cudaMemcpyDeviceToHost, b->d2h));
+                CU_TRY(cudaMemcpyAsync(success + off, b->d_success + off, cnt, cudaMemcpyDeviceToHost, b->d2h));
+            }
         }
+        return LEGO_KLT_OK;
+    };
+    rc = enqueue_chunks();
+    if (rc) {
+        const std::string why = g_last_error;
+        cudaStreamSynchronize(b->copy);
+        cudaStreamSynchronize(st);
+        if (b->side) cudaStreamSynchronize(b->side);
+        cudaStreamSynchronize(b->d2h);
+        cudaGetLastError();
+        g_last_error = why;
+        return rc;
     }
     // the side stream runs its chunks in order: the last join covers them all (counters, results)
     if (last_chunk >= 0 && b->side) CU_TRY(cudaStreamWaitEvent(st, b->ev_join_c[last_chunk], 0));
@@ -823,6 +937,7 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     b->pyramids_valid = true;
     b->ran = true;
     b->last_chunked = true;
+    b->last_timed = false;
     b->last_params = *params;
     ++b->runs;
     CU_TRY(cudaMemcpyAsync(b->h_stats, b->d_stats, kStatCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -935,6 +1050,8 @@ int lego_klt_image_create(lego_klt_ctx *ctx, int cols, int rows, size_t step, in
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "pyramid plan: %s", cudaGetErrorString(e)));
     if ((e = warp_maps_create(im->view, &im->maps)) != cudaSuccess)
         return cleanup(fail(LEGO_KLT_ERR_CUDA, "TMA descriptor creation failed: %s", cudaGetErrorString(e)));
+    im->counted = true;
+    ++ctx->live_handles;
     *out = im;
     return LEGO_KLT_OK;
 }
@@ -949,7 +1066,10 @@ void lego_klt_image_destroy(lego_klt_image *im) {
     cudaFree(im->d_tight);
     cudaFree(im->d_full);
     cudaGetLastError();
+    lego_klt_ctx *ctx = im->ctx;
+    const bool counted = im->counted;
     delete im;
+    if (counted) ctx_release_handle(ctx);
 }
 
 int lego_klt_image_upload(lego_klt_image *im, const uint8_t *data) {
@@ -1057,11 +1177,13 @@ int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, cons
         CU_TRY(cudaEventRecord(b->ev[EV_START], st));
         CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
     }
-    cudaEvent_t *ring = stats ? b->ring[b->runs % kRing] : nullptr;
+    cudaEvent_t *ring = stats ? b->ring[b->timed_runs % kRing] : nullptr;
     rc = run_range(b, params, 0, 1, 0, ring, &view, img2->maps);
     if (rc) return rc;
     if (stats) CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
     ++b->runs;
+    if (stats) ++b->timed_runs;
+    b->last_timed = stats != nullptr;
     b->ran = true;
     b->last_chunked = false;
     return single_download(ctx, b, kp2_xy, success, n, stats);
@@ -1095,7 +1217,10 @@ int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int 
         if (level_rows) level_rows[l] = lv.rows;
         if (l == 0) continue;
         const size_t nbytes = (size_t)lv.cols * lv.rows;
-        if (!out || off + nbytes > out_capacity) return fail(LEGO_KLT_ERR_BAD_ARG, "output buffer too small");
+        if (!out || off + nbytes > out_capacity) {
+            cudaStreamSynchronize(st);  // earlier level copies into `out` are still in flight
+            return fail(LEGO_KLT_ERR_BAD_ARG, "output buffer too small");
+        }
         CU_TRY(cudaMemcpy2DAsync(out + off, (size_t)lv.cols, lv.base[0], (size_t)lv.pitch, (size_t)lv.cols,
                                  (size_t)lv.rows, cudaMemcpyDeviceToHost, st));
         off += nbytes;
@@ -1206,6 +1331,123 @@ int lego_klt_batch_triangulate(lego_klt_batch *b, const lego_camera *left, const
     int rc = ensure_tri(ctx, up256(nt * 3 * sizeof(double)) + up256(nt));
     if (rc) return rc;
     return tri_stereo_device(ctx, left, right, b->d_kp1, b->d_kp2_out, b->d_success, (int)nt, sing_ratio_thr, 0, pt_world, ok);
+}
+
+// ---- one process, several devices (SURVEY.md 8b "device list", 8e) --------------------------------------------
+struct lego_klt_multi {
+    struct Shard {
+        int device = 0, first = 0, count = 0;
+        lego_klt_ctx *ctx = nullptr;
+        lego_klt_batch *batch = nullptr;
+    };
+    std::vector<Shard> shards;
+    int B = 0, cols = 0, rows = 0, n = 0, levels = 0;
+    size_t step = 0;
+};
+
+int lego_klt_multi_create(const int *devices, int n_devices, int batch, int cols, int rows, size_t step, int n_per_pair,
+                          int levels, lego_klt_multi **out) {
+    if (out) *out = nullptr;
+    if (!devices || n_devices <= 0 || !out) return fail(LEGO_KLT_ERR_BAD_ARG, "null / empty device list");
+    if (batch < n_devices) return fail(LEGO_KLT_ERR_BAD_ARG, "fewer pairs (%d) than devices (%d)", batch, n_devices);
+    lego_klt_multi *m = new (std::nothrow) lego_klt_multi();
+    if (!m) return fail(LEGO_KLT_ERR_BAD_ARG, "out of host memory");
+    m->B = batch;
+    m->cols = cols;
+    m->rows = rows;
+    m->step = step;
+    m->n = n_per_pair;
+    m->levels = levels;
+    m->shards.resize(n_devices);
+    // contiguous blocks of pairs whose sizes differ by at most one (the partition of lego_slam_b200/sharding.py)
+    const int base = batch / n_devices, rem = batch % n_devices;
+    for (int i = 0; i < n_devices; ++i) {
+        lego_klt_multi::Shard &sh = m->shards[i];
+        sh.device = devices[i];
+        sh.first = i * base + (i < rem ? i : rem);
+        sh.count = base + (i < rem ? 1 : 0);
+        int rc = lego_klt_create(sh.device, &sh.ctx);
+        if (rc == LEGO_KLT_OK) rc = lego_klt_batch_create(sh.ctx, sh.count, cols, rows, step, n_per_pair, levels, &sh.batch);
+        if (rc != LEGO_KLT_OK) {
+            const std::string why = g_last_error;
+            lego_klt_multi_destroy(m);
+            g_last_error = why;
+            return rc;
+        }
+    }
+    *out = m;
+    return LEGO_KLT_OK;
+}
+
+void lego_klt_multi_destroy(lego_klt_multi *m) {
+    if (!m) return;
+    for (auto &sh : m->shards) {
+        if (sh.batch) lego_klt_batch_destroy(sh.batch);
+        if (sh.ctx) lego_klt_destroy(sh.ctx);
+    }
+    delete m;
+}
+
+int lego_klt_multi_shard(const lego_klt_multi *m, int i, int *device, int *first_pair, int *n_pairs) {
+    if (!m || i < 0 || i >= (int)m->shards.size()) return fail(LEGO_KLT_ERR_BAD_ARG, "shard index out of range");
+    if (device) *device = m->shards[i].device;
+    if (first_pair) *first_pair = m->shards[i].first;
+    if (n_pairs) *n_pairs = m->shards[i].count;
+    return (int)m->shards.size();
+}
+
+int lego_klt_multi_set_feature_counts(lego_klt_multi *m, const int *counts) {
+    if (!m) return fail(LEGO_KLT_ERR_BAD_ARG, "multi is null");
+    for (auto &sh : m->shards) {
+        int rc = lego_klt_batch_set_feature_counts(sh.batch, counts ? counts + sh.first : nullptr);
+        if (rc) return rc;
+    }
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_multi_track(lego_klt_multi *m, const lego_klt_params *params, const uint8_t *imgs1, const uint8_t *imgs2,
+                         const float *kp1_xy, float *kp2_xy, uint8_t *success, lego_klt_stats *stats) {
+    if (!m) return fail(LEGO_KLT_ERR_BAD_ARG, "multi is null");
+    if (!params || !imgs1 || !imgs2) return fail(LEGO_KLT_ERR_BAD_ARG, "null argument");
+    const size_t img_bytes = (size_t)m->rows * m->step;
+    const int S = (int)m->shards.size();
+    std::vector<int> rcs(S, LEGO_KLT_OK);
+    std::vector<std::string> errs(S);
+    std::vector<lego_klt_stats> st(S);
+    auto work = [&](int i) {
+        const lego_klt_multi::Shard &sh = m->shards[i];
+        const size_t ko = (size_t)sh.first * (size_t)m->n;
+        rcs[i] = lego_klt_track_batched(sh.batch, params, imgs1 + (size_t)sh.first * img_bytes,
+                                        imgs2 + (size_t)sh.first * img_bytes, kp1_xy ? kp1_xy + 2 * ko : nullptr,
+                                        kp2_xy ? kp2_xy + 2 * ko : nullptr, success ? success + ko : nullptr, &st[i]);
+        if (rcs[i]) errs[i] = g_last_error;  // (thread-local in the worker)
+    };
+    // one host thread per device: each drives its own context, streams and pinned-copy pipeline; no exchange between
+    // them (pairs are independent), results land in disjoint slices of the caller's buffers
+    std::vector<std::thread> pool;
+    for (int i = 1; i < S; ++i) pool.emplace_back(work, i);
+    work(0);
+    for (auto &t : pool) t.join();
+    for (int i = 0; i < S; ++i)
+        if (rcs[i]) return fail(rcs[i], "device %d: %s", m->shards[i].device, errs[i].c_str());
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int i = 0; i < S; ++i) {
+            stats->n_features += st[i].n_features;
+            stats->n_success += st[i].n_success;
+            stats->n_nan += st[i].n_nan;
+            stats->n_out_of_image += st[i].n_out_of_image;
+            stats->n_slow_path += st[i].n_slow_path;
+            stats->n_deferred += st[i].n_deferred;
+            for (int l = 0; l < LEGO_KLT_MAX_LEVELS; ++l) stats->gn_iters[l] += st[i].gn_iters[l];
+            for (int k = 0; k < 4; ++k) stats->defer_reason[k] += st[i].defer_reason[k];
+            stats->ms_h2d = std::max(stats->ms_h2d, st[i].ms_h2d);          // devices work concurrently
+            stats->ms_pyramid = std::max(stats->ms_pyramid, st[i].ms_pyramid);
+            stats->ms_solver = std::max(stats->ms_solver, st[i].ms_solver);
+            stats->ms_d2h = std::max(stats->ms_d2h, st[i].ms_d2h);
+        }
+    }
+    return LEGO_KLT_OK;
 }
 
 }  // extern "C"

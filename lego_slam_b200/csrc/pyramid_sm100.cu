@@ -522,6 +522,7 @@ cudaError_t launch_half_nearest(const uint8_t *full, int full_cols, int full_row
     const long long total = (long long)((l0.cols + 3) / 4) * l0.rows;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     half_nearest_kernel<<<grid, 256, 0, stream>>>(full, full_cols, full_rows, full_step, l0.base[0], l0.cols, l0.rows, l0.pitch);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -533,6 +534,7 @@ cudaError_t launch_ingest(const uint8_t *tight, const LevelView &l0, int set, in
     const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     ingest_kernel<<<grid, 256, 0, stream>>>(tight, l0.base[set], l0.step, l0.pitch, (long long)img0 * l0.rows, n_rows,
                                             l0.rows, l0.slot);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -542,6 +544,7 @@ cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream
     for (int l = 0; l < pyr.levels; ++l) row_blocks += (pyr.lv[l].rows + 7) / 8;
     dim3 grid(row_blocks, n_sets * nimg);
     apron_kernel<<<grid, 256, 0, stream>>>(pyr, img0, nimg);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -708,15 +711,16 @@ cudaError_t launch_band_kernel(const PyramidPlan &plan, const PyramidView &pyr, 
     kp.bands = static_cast<const int2 *>(plan.band_tab);
     kp.img0 = img0;
     kp.nimg = nimg;
-    static thread_local size_t configured = 0;
-    if (plan.smem_bytes > 48 * 1024 && plan.smem_bytes > configured) {
+    if (plan.smem_bytes > 48 * 1024) {
+        // the attribute belongs to the current device's context, not to the calling thread: set it on every launch
+        // (a host-side table lookup) instead of caching it per thread
         cudaError_t err = cudaFuncSetAttribute(pyramid_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)plan.smem_bytes);
         if (err != cudaSuccess) return err;
-        configured = plan.smem_bytes;
     }
     dim3 grid(plan.n_bands, n_sets * nimg);
     pyramid_band_kernel<<<grid, 256, plan.smem_bytes, stream>>>(pyr, kp);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -744,6 +748,7 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int 
     if (t.x_exact2 && t.y_exact2) pyramid_l01_kernel<true, true><<<grid, 256, 0, stream>>>(pyr, p);
     else if (t.y_exact2) pyramid_l01_kernel<false, true><<<grid, 256, 0, stream>>>(pyr, p);
     else pyramid_l01_kernel<false, false><<<grid, 256, 0, stream>>>(pyr, p);
+    note_launch();
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     // levels 2..: the same pyramid seen from level 1 (the band kernel also writes the aprons of its level 0)

@@ -195,6 +195,7 @@ cudaError_t launch_triangulate(const double *poses34, int n_views, const double 
                                double *d_pt_world, uint8_t *d_ok, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     triangulate_kernel<<<(n + 127) / 128, 128, 0, stream>>>(make_poses(poses34, n_views), d_points, n, thr, d_pt_world, d_ok);
+    note_launch();
     return cudaGetLastError();
 }
 
@@ -206,6 +207,7 @@ cudaError_t launch_triangulate_stereo(const double *poses34, const double *cam_l
     const TriCamera cr = {cam_right[0], cam_right[1], cam_right[2], cam_right[3]};
     triangulate_stereo_kernel<<<(n + 127) / 128, 128, 0, stream>>>(make_poses(poses34, 2), cl, cr, d_kp_left, d_kp_right,
                                                                   d_valid, n, thr, d_pt_world, d_ok);
+    note_launch();
     return cudaGetLastError();
 }
 

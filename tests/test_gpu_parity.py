@@ -145,6 +145,17 @@ def test_config4_1080p_5_levels_inverse(tracker, oracle):
                 [klt.KERNEL_EXACT] + FAST_KERNELS, "C4")
 
 
+def test_config4_shape_forward_all_kernels(tracker, oracle):
+    """1920x1080, 5 levels, 5000 features in FORWARD mode: the LANE kernel on the C4 shape (the inverse-mode test above
+    exercises EXACT and WARP only), integer and sub-pixel source points."""
+    L, R, kp1, kp2, _ = synth.stereo_case(1080, 1920, 5000, seed=3)
+    _check_case(tracker, oracle, L, R, kp1, kp2, dict(levels=5), [klt.KERNEL_EXACT] + FAST_KERNELS, "C4 forward")
+    rng = np.random.default_rng(33)
+    kp1s = (kp1 + rng.uniform(-0.5, 0.5, kp1.shape)).astype(np.float32)
+    kp2s = (kp1s + rng.normal(0, 1.5, kp1.shape)).astype(np.float32)
+    _check_case(tracker, oracle, L, R, kp1s, kp2s, dict(levels=5), [klt.KERNEL_EXACT] + FAST_KERNELS, "C4 forward sub-pixel")
+
+
 @pytest.mark.parametrize("n,lo,hi", [(100, -3, 3), (20000, -3, 3), (3000, -5, 5), (3000, -4, 3)])
 def test_config5_stress_feature_counts_and_patches(tracker, oracle, n, lo, hi):
     L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, n, seed=4, min_dist=3 if n > 5000 else 5)
@@ -400,3 +411,135 @@ def test_ingest_reproduces_the_committed_cv2_hashes(tracker):
         out = tracker.downscale_half(img)
         assert list(out.shape) == c["out_shape"], name
         assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == c["sha256"], name
+
+
+# ------------------------------------------------------------------ handle lifetime
+def test_handles_survive_their_tracker_in_any_destruction_order():
+    """Image and Batch handles point into their context: destroying the context first must only defer its tear-down
+    (include/lego_klt.h, ownership note)."""
+    import gc
+    L, R, kp1, kp2, _ = synth.stereo_case(94, 310, 50, seed=8, min_dist=8)
+    trk = klt.Tracker(0)
+    im = trk.image(94, 310, 3).upload(L)
+    batch = trk.batch(2, 94, 310, 50, levels=3)
+    trk.close()            # lego_klt_destroy with two live handles
+    del trk
+    gc.collect()
+    batch.close()          # ... which are destroyed afterwards, the last one tears the context down
+    im.close()
+    # temporaries: the tracker object would be collected before the image without the back-reference
+    im2 = klt.Tracker(0).image(94, 310, 3)
+    gc.collect()
+    im2.upload(R)
+    im2.close()
+
+
+# ------------------------------------------------------------------ multi-rank on the GPU (SURVEY.md 4, item 7)
+def _gpu_rank(rank, world, port, out_dir, B, rows, cols, n):
+    import os
+    import torch
+    import torch.distributed as dist
+    from lego_slam_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % torch.cuda.device_count()
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 4000)
+    lo, hi = sharding.shard_range(B, rank, world)
+    trk = klt.Tracker(dev)
+    batch = trk.batch(hi - lo, rows, cols, n, levels=4)
+    succ = klt.pinned_empty((hi - lo, n), np.uint8)
+    io = klt.pinned_empty((hi - lo, n, 2), np.float32)
+    np.copyto(io, kp2[lo:hi])
+    batch.track(np.ascontiguousarray(imgs1[lo:hi]), np.ascontiguousarray(imgs2[lo:hi]),
+                np.ascontiguousarray(kp1[lo:hi]), io, succ, klt.make_params(kernel=klt.KERNEL_LANE))
+    kp_full, su_full = sharding.gather_results(torch.from_numpy(io.copy()), torch.from_numpy(succ.copy()), B)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "kp.npy"), kp_full.numpy())
+        np.save(os.path.join(out_dir, "su.npy"), su_full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_sharded_gpu_result_equals_single_gpu_bytes(tracker, tmp_path):
+    """Block partition over 2 ranks (each its own process and context; on a 1-GPU box both use cuda:0), final gather:
+    byte-for-byte what ONE context computes for the whole batch."""
+    import socket
+    import torch.multiprocessing as mp
+    B, rows, cols, n = 5, 188, 620, 1500     # uneven shards (3 + 2); > 4096 features per rank: the LANE kernel
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gpu_rank, args=(2, port, str(tmp_path), B, rows, cols, n), nprocs=2, join=True)
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 4000)
+    succ = klt.pinned_empty((B, n), np.uint8)
+    batch = tracker.batch(B, rows, cols, n, levels=4)
+    batch.track(imgs1, imgs2, kp1, kp2, succ, klt.make_params(kernel=klt.KERNEL_LANE))
+    assert np.array_equal(np.load(tmp_path / "kp.npy").view(np.uint32), kp2.view(np.uint32))
+    assert np.array_equal(np.load(tmp_path / "su.npy"), succ)
+    batch.close()
+
+
+# ------------------------------------------------------------------ ragged batches, device lists (SURVEY.md 8b)
+@pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT, klt.KERNEL_WARP, klt.KERNEL_LANE])
+def test_ragged_batch_tracks_only_the_first_counts_features_of_each_pair(tracker, kernel):
+    B, rows, cols, n = 9, 188, 620, 1200
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 5000)
+    guess = kp2.copy()
+    counts = np.array([n, 0, 1, 37, n - 1, 600, n, 999, 5], np.int32)
+    batch = tracker.batch(B, rows, cols, n, levels=4)
+    full = tracker.batch(B, rows, cols, n, levels=4)
+    succ_f = klt.pinned_empty((B, n), np.uint8)
+    kp_f = klt.pinned_empty((B, n, 2), np.float32)
+    np.copyto(kp_f, guess)
+    full.track(imgs1, imgs2, kp1, kp_f, succ_f, klt.make_params(kernel=kernel))
+    batch.set_feature_counts(counts)
+    succ = klt.pinned_empty((B, n), np.uint8)
+    succ[:] = 7
+    st = batch.track(imgs1, imgs2, kp1, kp2, succ, klt.make_params(kernel=kernel))
+    assert int(st.n_features) == int(counts.sum())
+    for b in range(B):
+        c = counts[b]
+        assert np.array_equal(kp2[b, :c].view(np.uint32), kp_f[b, :c].view(np.uint32)), b
+        assert np.array_equal(succ[b, :c], succ_f[b, :c]), b
+        assert np.array_equal(kp2[b, c:].view(np.uint32), guess[b, c:].view(np.uint32)), b   # untouched slots
+        assert not succ[b, c:].any(), b
+    assert int(st.n_success) == int(sum(succ_f[b, :counts[b]].sum() for b in range(B)))
+    batch.set_feature_counts(None)       # back to a full batch
+    np.copyto(kp2, guess)
+    batch.track(imgs1, imgs2, kp1, kp2, succ, klt.make_params(kernel=kernel))
+    assert np.array_equal(kp2.view(np.uint32), kp_f.view(np.uint32)) and np.array_equal(succ, succ_f)
+    batch.close()
+    full.close()
+
+
+def test_multi_device_entry_equals_single_context_bytes(tracker):
+    """lego_klt_multi_track over a device list (two contexts; both on cuda:0 when the box has one GPU)."""
+    import torch
+    B, rows, cols, n = 11, 188, 620, 1500
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 6000)
+    guess = kp2.copy()
+    succ1 = klt.pinned_empty((B, n), np.uint8)
+    one = tracker.batch(B, rows, cols, n, levels=4)
+    st1 = one.track(imgs1, imgs2, kp1, kp2, succ1, klt.make_params(kernel=klt.KERNEL_LANE))
+    ref = kp2.copy()
+    ndev = torch.cuda.device_count()
+    multi = klt.MultiTracker([0, 1 % ndev, 0], B, rows, cols, n, levels=4)
+    assert [s[1:] for s in multi.shards()] == [(0, 4), (4, 4), (8, 3)]
+    np.copyto(kp2, guess)
+    succ2 = klt.pinned_empty((B, n), np.uint8)
+    st2 = multi.track(imgs1, imgs2, kp1, kp2, succ2, klt.make_params(kernel=klt.KERNEL_LANE))
+    assert np.array_equal(kp2.view(np.uint32), ref.view(np.uint32)) and np.array_equal(succ1, succ2)
+    assert list(st1.gn_iters) == list(st2.gn_iters) and int(st1.n_success) == int(st2.n_success)
+    assert int(st2.n_features) == B * n
+    multi.close()
+    one.close()
+
+
+def test_kernel_launch_counter_counts_this_librarys_launches(tracker):
+    L, R, kp1, kp2, _ = synth.stereo_case(94, 310, 50, seed=8, min_dist=8)
+    before = klt.kernel_launches()
+    tracker.track(L, R, kp1, kp2, klt.make_params(levels=3, kernel=klt.KERNEL_EXACT))
+    # 2 ingest + level 0->1 + band kernel + exact solver
+    assert klt.kernel_launches() - before == 5

@@ -1,0 +1,127 @@
+// pipe_probe.cu -- issue / pipe throughput of the instruction mixes of the LANE solver on sm_100a (tuning aid).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probe/pipe_probe tools/probe/pipe_probe.cu
+// Every test is a loop of independent dependency chains in inline PTX; reported: cycles per warp-instruction per
+// SM sub-partition at 1..4 warps per sub-partition (one CTA per SM).
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITERS 2000
+
+template <int MIX>
+__global__ void probe(float *out, float seed, unsigned long long *cycles) {
+    float a0 = seed + threadIdx.x, a1 = a0 * 1.1f, a2 = a0 * 1.2f, a3 = a0 * 1.3f, a4 = a0 * 1.4f, a5 = a0 * 1.5f, a6 = a0 * 1.6f, a7 = a0 * 1.7f;
+    unsigned long long p0, p1, p2, p3, p4, p5, p6, p7, w;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p0) : "f"(a0), "f"(a1));
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p1) : "f"(a2), "f"(a3));
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(a4), "f"(a5));
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p3) : "f"(a6), "f"(a7));
+    p4 = p0; p5 = p1; p6 = p2; p7 = p3;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(w) : "f"(0.999f));
+    double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, e0, e1, e2;
+    unsigned u0 = threadIdx.x, u1 = u0 * 3, u2 = u0 * 5, u3 = u0 * 7;
+    __syncthreads();
+    unsigned long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        if (MIX == 0) {  // 8 x mul.f32x2
+            asm volatile("mul.rn.f32x2 %0, %0, %8; mul.rn.f32x2 %1, %1, %8; mul.rn.f32x2 %2, %2, %8; mul.rn.f32x2 %3, %3, %8;"
+                         "mul.rn.f32x2 %4, %4, %8; mul.rn.f32x2 %5, %5, %8; mul.rn.f32x2 %6, %6, %8; mul.rn.f32x2 %7, %7, %8;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(w));
+        } else if (MIX == 1) {  // 8 x fma.f32x2
+            asm volatile("fma.rn.f32x2 %0, %0, %8, %1; fma.rn.f32x2 %1, %1, %8, %2; fma.rn.f32x2 %2, %2, %8, %3; fma.rn.f32x2 %3, %3, %8, %4;"
+                         "fma.rn.f32x2 %4, %4, %8, %5; fma.rn.f32x2 %5, %5, %8, %6; fma.rn.f32x2 %6, %6, %8, %7; fma.rn.f32x2 %7, %7, %8, %0;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(w));
+        } else if (MIX == 2) {  // 8 x add.f32 (scalar)
+            asm volatile("add.rn.f32 %0, %0, %8; add.rn.f32 %1, %1, %8; add.rn.f32 %2, %2, %8; add.rn.f32 %3, %3, %8;"
+                         "add.rn.f32 %4, %4, %8; add.rn.f32 %5, %5, %8; add.rn.f32 %6, %6, %8; add.rn.f32 %7, %7, %8;"
+                         : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3), "+f"(a4), "+f"(a5), "+f"(a6), "+f"(a7) : "f"(seed));
+        } else if (MIX == 3) {  // 6 x fma.f64, independent
+            asm volatile("fma.rn.f64 %0, %0, %6, %0; fma.rn.f64 %1, %1, %6, %1; fma.rn.f64 %2, %2, %6, %2;"
+                         "fma.rn.f64 %3, %3, %6, %3; fma.rn.f64 %4, %4, %6, %4; fma.rn.f64 %5, %5, %6, %5;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5) : "d"(0.999));
+        } else if (MIX == 4) {  // 6 x cvt.f64.f32 (results folded with xor so that they are not dead)
+            asm volatile("cvt.f64.f32 %0, %6; cvt.f64.f32 %1, %7; cvt.f64.f32 %2, %8; cvt.f64.f32 %3, %9; cvt.f64.f32 %4, %10; cvt.f64.f32 %5, %11;"
+                         : "=d"(d0), "=d"(d1), "=d"(d2), "=d"(d3), "=d"(d4), "=d"(d5) : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5));
+            a0 += (float)it;  // 1 I2F + 1 FADD per 6: keeps the inputs changing
+        } else if (MIX == 5) {  // 8 x prmt
+            asm volatile("prmt.b32 %0, %0, %4, 0x7440; prmt.b32 %1, %1, %4, 0x7441; prmt.b32 %2, %2, %4, 0x7442; prmt.b32 %3, %3, %4, 0x7443;"
+                         "prmt.b32 %0, %0, %4, 0x7441; prmt.b32 %1, %1, %4, 0x7442; prmt.b32 %2, %2, %4, 0x7443; prmt.b32 %3, %3, %4, 0x7440;"
+                         : "+r"(u0), "+r"(u1), "+r"(u2), "+r"(u3) : "r"(0x4B000000u));
+        } else if (MIX == 6) {  // the per-pixel block: 3 add.f32, 3 cvt.f64.f32, 6 fma.f64
+            asm volatile("add.rn.f32 %6, %6, %9; add.rn.f32 %7, %7, %9; add.rn.f32 %8, %8, %9;"
+                         "cvt.f64.f32 %10, %6; cvt.f64.f32 %11, %7; cvt.f64.f32 %12, %8;"
+                         "fma.rn.f64 %0, %10, %11, %0; fma.rn.f64 %1, %10, %12, %1; fma.rn.f64 %2, %10, %10, %2;"
+                         "fma.rn.f64 %3, %11, %11, %3; fma.rn.f64 %4, %11, %12, %4; fma.rn.f64 %5, %12, %12, %5;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+f"(a0), "+f"(a1), "+f"(a2), "+f"(seed), "=d"(e0), "=d"(e1), "=d"(e2));
+        } else if (MIX == 7) {  // the sample block: 8 mul.f32x2 + 3 fma.f32x2
+            asm volatile("mul.rn.f32x2 %0, %0, %8; mul.rn.f32x2 %1, %1, %8; mul.rn.f32x2 %2, %2, %8; mul.rn.f32x2 %3, %3, %8;"
+                         "mul.rn.f32x2 %0, %0, %4; mul.rn.f32x2 %1, %1, %5; mul.rn.f32x2 %2, %2, %6; mul.rn.f32x2 %3, %3, %7;"
+                         "fma.rn.f32x2 %0, %1, %8, %0; fma.rn.f32x2 %0, %2, %8, %0; fma.rn.f32x2 %0, %3, %8, %0;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(w));
+        } else if (MIX == 8) {  // per-pixel block + sample block (the row loop's ratio is about 49 : 45)
+            asm volatile("add.rn.f32 %6, %6, %9; add.rn.f32 %7, %7, %9; add.rn.f32 %8, %8, %9;"
+                         "cvt.f64.f32 %10, %6; cvt.f64.f32 %11, %7; cvt.f64.f32 %12, %8;"
+                         "fma.rn.f64 %0, %10, %11, %0; fma.rn.f64 %1, %10, %12, %1; fma.rn.f64 %2, %10, %10, %2;"
+                         "fma.rn.f64 %3, %11, %11, %3; fma.rn.f64 %4, %11, %12, %4; fma.rn.f64 %5, %12, %12, %5;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+f"(a0), "+f"(a1), "+f"(a2), "+f"(seed), "=d"(e0), "=d"(e1), "=d"(e2));
+            asm volatile("mul.rn.f32x2 %0, %0, %8; mul.rn.f32x2 %1, %1, %8; mul.rn.f32x2 %2, %2, %8; mul.rn.f32x2 %3, %3, %8;"
+                         "mul.rn.f32x2 %0, %0, %4; mul.rn.f32x2 %1, %1, %5; mul.rn.f32x2 %2, %2, %6; mul.rn.f32x2 %3, %3, %7;"
+                         "fma.rn.f32x2 %0, %1, %8, %0; fma.rn.f32x2 %0, %2, %8, %0; fma.rn.f32x2 %0, %3, %8, %0;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(w));
+        } else if (MIX == 9) {  // 8 x mov (register rotation)
+            asm volatile("mov.b32 %0, %1; mov.b32 %1, %2; mov.b32 %2, %3; mov.b32 %3, %4; mov.b32 %4, %5; mov.b32 %5, %6; mov.b32 %6, %7; mov.b32 %7, %0;"
+                         : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3), "+f"(a4), "+f"(a5), "+f"(a6), "+f"(a7));
+        } else if (MIX == 10) {  // 6 x cvt.f64.f32 + 12 independent fma.f64 (do conversions hide behind the fp64 pipe?)
+            asm volatile("cvt.f64.f32 %6, %9; cvt.f64.f32 %7, %10; cvt.f64.f32 %8, %11;"
+                         "fma.rn.f64 %0, %6, %7, %0; fma.rn.f64 %1, %6, %8, %1; fma.rn.f64 %2, %6, %6, %2;"
+                         "fma.rn.f64 %3, %7, %7, %3; fma.rn.f64 %4, %7, %8, %4; fma.rn.f64 %5, %8, %8, %5;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "=d"(e0), "=d"(e1), "=d"(e2) : "f"(a0), "f"(a1), "f"(a2));
+        } else if (MIX == 11) {  // 8 x scalar mul.f32 with three distinct registers
+            asm volatile("mul.rn.f32 %0, %1, %8; mul.rn.f32 %1, %2, %8; mul.rn.f32 %2, %3, %8; mul.rn.f32 %3, %4, %8;"
+                         "mul.rn.f32 %4, %5, %8; mul.rn.f32 %5, %6, %8; mul.rn.f32 %6, %7, %8; mul.rn.f32 %7, %0, %8;"
+                         : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3), "+f"(a4), "+f"(a5), "+f"(a6), "+f"(a7) : "f"(seed));
+        }
+    }
+    unsigned long long t1 = clock64();
+    float2 q;
+    asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(q.x), "=f"(q.y) : "l"(p0 ^ p1 ^ p2 ^ p3 ^ p4 ^ p5 ^ p6 ^ p7));
+    out[blockIdx.x * blockDim.x + threadIdx.x] = q.x + q.y + a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + (float)(d0 + d1 + d2 + d3 + d4 + d5) + (float)(u0 ^ u1 ^ u2 ^ u3);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+template <int MIX>
+void run(const char *name, int insts_per_iter) {
+    float *out;
+    unsigned long long *cyc, h;
+    cudaMalloc(&out, 148 * 1024 * sizeof(float));
+    cudaMalloc(&cyc, 8);
+    printf("%-58s", name);
+    for (int wps = 1; wps <= 4; ++wps) {
+        probe<MIX><<<148, 128 * wps>>>(out, 1.0f, cyc);
+        probe<MIX><<<148, 128 * wps>>>(out, 1.0f, cyc);
+        cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        // cycles per warp-instruction per sub-partition
+        printf("  w%d: %5.2f", wps, (double)h / ((double)ITERS * insts_per_iter * wps));
+    }
+    printf("   (cycles per warp-instruction per SMSP)\n");
+    cudaFree(out);
+    cudaFree(cyc);
+}
+
+int main() {
+    run<0>("8 x mul.f32x2 (FMUL2)", 8);
+    run<1>("8 x fma.f32x2 (FFMA2)", 8);
+    run<2>("8 x add.f32 (FADD)", 8);
+    run<11>("8 x mul.f32 three distinct registers (FMUL)", 8);
+    run<3>("6 x fma.f64 (DFMA)", 6);
+    run<4>("6 x cvt.f64.f32 (F2F) [+1 I2F +1 FADD]", 6);
+    run<5>("8 x prmt (PRMT)", 8);
+    run<9>("8 x mov (MOV / IMAD.MOV)", 8);
+    run<10>("3 cvt.f64.f32 + 6 fma.f64", 9);
+    run<6>("pixel block: 3 FADD + 3 F2F + 6 DFMA", 12);
+    run<7>("sample block: 8 FMUL2 + 3 FFMA2", 11);
+    run<8>("pixel block + sample block", 23);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("%s\n", cudaGetErrorString(e));
+    return e != cudaSuccess;
+}
