@@ -81,8 +81,11 @@ typedef struct lego_klt_stats {
     uint64_t gn_iters[LEGO_KLT_MAX_LEVELS];      /* patch passes executed per level, level 0 = fine */
     uint64_t n_slow_path;                        /* warp kernel: passes run on the exact per-pixel path */
     uint64_t n_deferred;                         /* lane kernel: features handed to the warp kernel  */
-    uint64_t defer_reason[4];                    /* ... by reason: kx+c inexact, rounding margin,
-                                                    nominal index, coordinate range               */
+    uint64_t defer_reason[4];                    /* [0] of n_deferred: irregular template grid (kx+c with more than
+                                                    one rounding error, window outside the apron); lane kernel,
+                                                    two-family levels: [1] passes on such levels, [2] of which the
+                                                    family split changed a rounded coordinate (masked sub-passes),
+                                                    [3] warp trips through the masked row loop              */
     float ms_h2d, ms_pyramid, ms_solver, ms_d2h; /* device times (CUDA events) of the last call    */
 } lego_klt_stats;
 

@@ -64,10 +64,10 @@ enum StatSlot {
     kStatSlowPath,
     kStatTmaTimeout,
     kStatDeferred,
-    kStatDeferInexact,   // reason counters of kStatDeferred
-    kStatDeferMargin,
-    kStatDeferNominal,
-    kStatDeferRange,
+    kStatDeferInexact,   // features deferred because some level's template grid is irregular
+    kStatFamPasses,      // lane kernel: passes on a level with two coordinate families on some axis
+    kStatFamSplit,       // ... of which the split changed a rounded coordinate (extra, masked trips)
+    kStatMaskedTrips,    // lane kernel: warp trips through the masked row loop
     kStatCount
 };
 

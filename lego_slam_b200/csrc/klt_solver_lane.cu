@@ -46,6 +46,8 @@
 // y in (rows-1, rows) reads zeros below the image (the oracle's definition of the reference's
 // out-of-buffer read).  A feature that violates (a) or (b), or whose window leaves the 32-pixel apron,
 // is appended to a deferred list and finished by the exact warp kernel; its partial work is dropped.
+#include <type_traits>
+
 #include "klt_kernels.h"
 
 namespace legoklt {
@@ -111,6 +113,12 @@ static_assert(kTplStride >= kI1Count + 1 && (kTplStride / 4) % 2 == 1 && kTplStr
 #ifndef LANE_PINGPONG
 #define LANE_PINGPONG 1
 #endif
+#ifndef LANE_PARK_SMEM
+#define LANE_PARK_SMEM 1       // partial sums of two-family passes wait in shared memory (48 bytes per thread), not in registers
+#endif
+#ifndef LANE_FAM_CTAS
+#define LANE_FAM_CTAS LANE_CTAS  // CTAs per SM of the family instance's grid (measured 1 / 2 / 3 / 4 / 5 per SM on 512,000
+#endif                           // sub-pixel keypoints: 2.76 / 2.18 / 1.98 / 1.93 / 1.92 ms; CTAs without work exit at once)
 #ifndef LANE_CTAS
 #define LANE_CTAS 5
 #endif
@@ -128,6 +136,9 @@ struct LaneSmem {
     float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
     int q_id[T / 32][kQueue];
     unsigned stats[kStatCount];
+#if LANE_PARK_SMEM
+    double parked[6][T];  // partial sums between the sub-passes of a two-family pass
+#endif
 };
 
 __device__ __forceinline__ float byte_to_float(uint32_t packed, int k) {
@@ -388,30 +399,6 @@ __device__ __noinline__ void exact_pass(const uint8_t *img2, const LevelView &lv
     sums[5] = s11;
 }
 
-// Sub-pass bookkeeping of a multi-family level: adds the sums parked by the earlier sub-passes, parks the
-// running total if more sub-passes follow.  Returns true when the pass is complete (sums hold the total).
-__device__ __noinline__ bool multi_family_step(double *parked, unsigned sub, unsigned nsub, double &a0, double &a1,
-                                               double &a2, double &a3, double &a4, double &a5) {
-    if (sub > 0u) {
-        a0 += parked[0];
-        a1 += parked[1];
-        a2 += parked[2];
-        a3 += parked[3];
-        a4 += parked[4];
-        a5 += parked[5];
-    }
-    if (sub + 1u < nsub) {
-        parked[0] = a0;
-        parked[1] = a1;
-        parked[2] = a2;
-        parked[3] = a3;
-        parked[4] = a4;
-        parked[5] = a5;
-        return false;
-    }
-    return true;
-}
-
 // Level-l coordinate of a level-0 keypoint coordinate (src/algorithm.cpp:160-169 then :194 repeatedly):
 // float(k * 2^-(L-1)), then exact doublings.
 __device__ __forceinline__ float level_coord(float k0, int L, int level) {
@@ -511,10 +498,14 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 #pragma unroll
     for (int i = 0; i < (kDirect ? 4 : kTplStride); ++i) buf[i] = 0.f;
     if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15, 32);
-    // Ownership of the feature, decided by its levels with an atomicMax (values of earlier runs are smaller):
-    //   4*epoch + 2 -> exact warp kernel (irregular on some level), 4*epoch + 1 -> lane<FAMILIES> (two
-    //   coordinate families on some level), smaller -> the common lane kernel.  A feature is appended to a
-    //   list by the thread that raises its flag to that list's value; lane<FAMILIES> re-checks the flag.
+    // Class of the feature, decided by its levels with an atomicMax on its flag (values of earlier runs are smaller):
+    //   4*epoch + 2  irregular on some level -> the exact warp kernel (deferred list)
+    //   4*epoch + 1  two coordinate families on some level -> the lane kernel's SECOND phase (family list): those
+    //                features need the masked row loop, and a warp runs it whenever one of its threads does, so they
+    //                are tracked together, after the others
+    //   smaller      the lane kernel's first phase.
+    // A feature is appended to a list by the thread that raises its flag to that list's value; the lane kernel
+    // re-checks the flag (a family feature may still be raised to the deferred class by another level).
     if (!valid) {
     } else if (!regular) {
         const int tag = 4 * args.epoch + 2;
@@ -584,10 +575,14 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
 #ifndef LANE_MAXREG
 #define LANE_MAXREG 0
 #endif
-// FAMILIES = false: every feature has a single coordinate family per axis (the template kernel routes the
-// others to the FAMILIES = true instance, which takes its features from args.list); the family bookkeeping
-// costs the common instance nothing.
-template <int T, int MIN_CTAS, bool FAMILIES>
+// Two instances, launched concurrently on two streams.  FAM = false: the features whose levels all have a single
+// coordinate family per axis (every integer keypoint; the template kernel sorts the others out) -- no family code at
+// all in this instance.  FAM = true: the features of the template kernel's family list.  A level on which an axis has
+// two coordinate families (sub-pixel source keypoints near a power of two, see axis_families) takes one trip per family
+// combination for each pass, with the pixels of the other families AND-ed to zero; warps without such a thread in a
+// trip run the unmasked row loop.  Measured on 512,000 sub-pixel keypoints (tools/ab.sh): one merged instance costs
+// the integer-keypoint path 4 % (1.51 vs 1.45 ms) and tracks sub-pixel keypoints in 1.93 ms.
+template <int T, int MIN_CTAS, bool FAM>
 __global__ void
 #if LANE_MAXREG > 0
 __maxnreg__(LANE_MAXREG)
@@ -600,8 +595,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr unsigned FULL = 0xffffffffu;
     int q_head = 0, q_tail = 0;  // warp-uniform ring positions
-    const int n_work = FAMILIES ? *args.list_count : args.n_total;
-    bool global_done = false;
+    constexpr bool second_phase = FAM;  // (this instance drains the family list)
+    bool global_done = false;           // warp-uniform: no work is left
 
     if (tid < kStatCount) sm.stats[tid] = 0u;
     __syncthreads();
@@ -620,8 +615,10 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     int wx0 = 0, wy0 = 0;
     bool need_win = false, no_window = false;
     // coordinate families of this level: bits 0-6 x mask of family B, 8-14 y mask, 16-17 current sub-pass
-    unsigned fam = 0u;  // stays 0 in the FAMILIES = false instance
-    double *parked = args.scratch + ((size_t)blockIdx.x * T + tid) * 6;  // partial sums between sub-passes
+    unsigned fam = 0u;
+#if !LANE_PARK_SMEM
+    double pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, pk4 = 0, pk5 = 0;  // partial sums between the sub-passes of a pass
+#endif
 
     for (;;) {
         // ------------------------------------------------------------------ fetch new features
@@ -634,24 +631,25 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     // refill: top the ring up with consecutive feature ids (never more than its free slots),
                     // coalesced loads, compacted into the ring
                     const int want = min(32, kQueue - avail);
+                    const int n_work = second_phase ? *args.fam_count : args.n_total;
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(args.work_counter, want);
+                    if (lane == 0) base = atomicAdd(args.work_counter + (second_phase ? 3 : 0), want);
                     base = __shfl_sync(FULL, base, 0);
                     const int local = base + lane;
                     bool keep = lane < want && local < n_work;
                     float2 a1 = make_float2(0.f, 0.f), a2 = a1;
                     int gid = args.f0 + local;
                     if (keep) {
-                        if (FAMILIES) {
-                            gid = args.list[local];  // the template kernel's list of multi-family features
-                            keep = args.feat_flag[gid] == 4 * args.epoch + 1;  // (not taken over by the warp kernel)
+                        if (second_phase) {
+                            gid = args.fam_list[local];
+                            keep = args.feat_flag[gid] == 4 * args.epoch + 1;  // (not raised to the deferred class)
                         } else {
-                            keep = args.feat_flag[gid] < 4 * args.epoch;  // otherwise owned by another kernel
+                            keep = args.feat_flag[gid] < 4 * args.epoch;       // first phase: single-family features
                         }
                         a1 = args.kp1[gid];
                         a2 = args.kp2_init[gid];
                         if (slot_unused(args, gid, gid / args.n_per_pair)) {  // ragged batch: nothing to track here
-                            if (!FAMILIES) write_unused_slot(args, gid);
+                            write_unused_slot(args, gid);
                             keep = false;
                         }
                     }
@@ -714,7 +712,8 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     iter = 0;
                     lastCost = 0;
                     succ = true;
-                    if (FAMILIES) {
+                    fam = 0u;
+                    if (FAM) {
                         unsigned mBx, mBy;
                         double e0, e1;
                         axis_families(kx, mBx, e0);  // (more than one eps per axis was filtered by the template kernel)
@@ -769,12 +768,17 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         float xx[G], omx[G];
         int ixn = 0, iyn = 0;
         unsigned pmx = kPMask, pmy = kPMask;  // pixels (columns / rows) that belong to this sub-pass
+        bool masked = false;                  // this trip covers only some of the pixels (pmx / pmy)
         Axis yax;
         if (run) {
             const LevelView &lv = pyr.lv[level];
             double kxd = (double)kx, kyd = (double)ky;
-            if (FAMILIES && (fam & kPMask2)) {  // this sub-pass works on one (x family, y family) combination
+            if (FAM && (fam & kPMask2)) {  // a level with two coordinate families on some axis: this sub-pass works on one
+                                   // (x family, y family) combination.  (Measured: the shift between the families changes a
+                                   // rounded sample coordinate in 93 % of such passes -- no point in testing for it.)
                 const unsigned mBx = fam & kPMask, mBy = (fam >> kFamY) & kPMask, sub = (fam >> kFamSub) & 3u;
+                if (sub == 0u) atomicAdd(&sm.stats[kStatFamPasses], 1u);
+                masked = true;
                 const bool fx = mBx && (sub & 1u), fy = mBy && (mBx ? (sub >> 1) : (sub & 1u));
                 if (fx) {
                     const int c = LO + __ffs(mBx) - 1;
@@ -811,7 +815,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
         // ------------------------------------------------------------------ one Gauss-Newton pass
         asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's set-up copies (each thread reads only its own granules)
-        const bool any_masked = FAMILIES && __any_sync(FULL, run && fast && (fam & kPMask2) != 0u);
+        const bool any_masked = FAM && __any_sync(FULL, run && fast && masked);
         if (run) {
             const LevelView &lv = pyr.lv[level];
             const float *i1p = reinterpret_cast<const float *>(&sm.g[LaneSmem<T>::kGranTpl][tid]);
@@ -871,6 +875,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             row_weights(om_r, fr_r);
             sample_row_packed(OMX, XX, om_r, fr_r, rowA, rowB, args.one, Sb);
             rowA = rowB;
+            // The row loop, in two versions chosen per warp and trip: MASKED (some thread of the warp works on one family
+            // combination of a two-family level: its other pixels are predicated off) and plain.
+            auto rows = [&](auto masked_c) {
+            constexpr bool MASKED = decltype(masked_c)::value;
+            unsigned col_word[P];
+#pragma unroll
+            for (int x = 0; x < P; ++x) col_word[x] = (MASKED && !((pmx >> x) & 1u)) ? 0u : 0xFFFFFFFFu;
             // One patch row per step: sample row r from pixel rows r, r+1 (PB is loaded here), then the 7 pixels of
             // patch row y = r-2 with centre samples SB = grid row r-1, SA / SC the rows above / below.
             auto step = [&](int r, const Row2 &PA, Row2 &PB, const float2 (&SA)[kNP], const float2 (&SB)[kNP], float2 (&SC)[kNP]) {
@@ -879,15 +890,21 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 row_weights(om_s, fr_s);
                 template_row(r - 2, tpl);
                 sample_row_packed(OMX, XX, om_s, fr_s, PA, PB, args.one, SC);
-                const bool row_on = !any_masked || ((pmy >> (r - 2)) & 1u);
+                // MASKED: the three differences of a pixel outside this thread's sub-pass are AND-ed to +0 (one LOP3
+                // each: difference & column word & row word), so that the pixel adds exact zeros to every sum
+                const unsigned row_word = (!MASKED || ((pmy >> (r - 2)) & 1u)) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
                 for (int x = 0; x < P; ++x) {
                     const int g = x + 1;
-                    // any_masked (warp-uniform, FAMILIES instance only): pixels outside the sub-pass add 0
-                    const bool on = !any_masked || (row_on && ((pmx >> x) & 1u));
-                    const double e = (double)(on ? __fadd_rn(tpl[x], -pick(SB, g)) : 0.f);                // :65-66
-                    const double gx = (double)(on ? __fadd_rn(pick(SB, g + 1), -pick(SB, g - 1)) : 0.f);  // :70-71
-                    const double gy = (double)(on ? __fadd_rn(pick(SC, g), -pick(SA, g)) : 0.f);          // :72-73
+                    float ef = __fadd_rn(tpl[x], -pick(SB, g));                // :65-66
+                    float gxf = __fadd_rn(pick(SB, g + 1), -pick(SB, g - 1));  // :70-71
+                    float gyf = __fadd_rn(pick(SC, g), -pick(SA, g));          // :72-73
+                    if (MASKED) {
+                        ef = __uint_as_float(__float_as_uint(ef) & col_word[x] & row_word);
+                        gxf = __uint_as_float(__float_as_uint(gxf) & col_word[x] & row_word);
+                        gyf = __uint_as_float(__float_as_uint(gyf) & col_word[x] & row_word);
+                    }
+                    const double e = (double)ef, gx = (double)gxf, gy = (double)gyf;
                     sb0 = fma(e, gx, sb0);
                     sb1 = fma(e, gy, sb1);
                     sc = fma(e, e, sc);
@@ -897,7 +914,6 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 }
             };
             // Rolled on purpose: the fully unrolled pass was instruction-fetch bound (profiles/README.md).
-#if LANE_PINGPONG
             // Two steps per trip: the pixel rows swap roles by name (no moves), the three sample rows are renamed with
             // one rotation per trip (2 * kNP float2 moves per two steps instead of 4 * kNP per step).
             int r = 2;
@@ -922,18 +938,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     Sb[j] = t;
                 }
             }
-#else
-#pragma unroll 1
-            for (int r = 2; r < G; ++r) {
-                step(r, rowA, rowB, Sa, Sb, Sc);
-                rowA = rowB;
-#pragma unroll
-                for (int j = 0; j < kNP; ++j) {
-                    Sa[j] = Sb[j];
-                    Sb[j] = Sc[j];
-                }
+            };
+            if (FAM && any_masked) {
+                if (lane == __ffs(__activemask()) - 1) atomicAdd(&sm.stats[kStatMaskedTrips], 1u);
+                rows(std::true_type{});
+            } else {
+                rows(std::false_type{});
             }
-#endif
 
             if (!axis_ok(near_y, yax.tie)) {  // condition (b) failed on some grid row (rare): redo the pass exactly
                 fast = false;
@@ -951,12 +962,48 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                 s01 = sums[4];
                 s11 = sums[5];
                 fam &= kPMask2;
-            } else if (FAMILIES && (fam & kPMask2)) {
-                // multi-family level: this trip covered one (x family, y family) combination; partial sums
-                // wait in global scratch until the last combination has been added (rare, so out of line)
+            } else if (FAM && masked) {
+                // this trip covered one (x family, y family) combination; the partial sums wait in registers until the
+                // last combination has been added
                 const unsigned sub = (fam >> kFamSub) & 3u;
                 const unsigned nsub = ((fam & kPMask) ? 2u : 1u) * ((fam & (kPMask << kFamY)) ? 2u : 1u);
-                solve_now = multi_family_step(parked, sub, nsub, sb0, sb1, sc, s00, s01, s11);
+#if LANE_PARK_SMEM
+                if (sub > 0u) {  // add what the earlier combinations left
+                    sb0 += sm.parked[0][tid];
+                    sb1 += sm.parked[1][tid];
+                    sc += sm.parked[2][tid];
+                    s00 += sm.parked[3][tid];
+                    s01 += sm.parked[4][tid];
+                    s11 += sm.parked[5][tid];
+                }
+                solve_now = sub + 1u >= nsub;
+                if (!solve_now) {
+                    sm.parked[0][tid] = sb0;
+                    sm.parked[1][tid] = sb1;
+                    sm.parked[2][tid] = sc;
+                    sm.parked[3][tid] = s00;
+                    sm.parked[4][tid] = s01;
+                    sm.parked[5][tid] = s11;
+                }
+#else
+                if (sub > 0u) {  // add what the earlier combinations left
+                    sb0 += pk0;
+                    sb1 += pk1;
+                    sc += pk2;
+                    s00 += pk3;
+                    s01 += pk4;
+                    s11 += pk5;
+                }
+                solve_now = sub + 1u >= nsub;
+                if (!solve_now) {
+                    pk0 = sb0;
+                    pk1 = sb1;
+                    pk2 = sc;
+                    pk3 = s00;
+                    pk4 = s01;
+                    pk5 = s11;
+                }
+#endif
                 fam = (fam & kPMask2) | (solve_now ? 0u : ((sub + 1u) << kFamSub));
             }
             if (solve_now) {
@@ -1044,9 +1091,10 @@ cudaError_t LANE_FN(launch_klt_template)(const PyramidView &pyr, const SolverArg
     return cudaGetLastError();
 }
 
-// `stream`: the common instance (single-family features, args.f0 .. ).  `families_stream`: the FAMILIES instance, fed
-// by the template kernel's fam_list -- it may be another stream (it only depends on the template kernel), so that it
-// fills the tail of the common instance and, in the chunked end-to-end path, overlaps the next chunk.
+// `stream`: the common instance (single-family features, args.f0 ..).  `families_stream`: the family instance, fed by
+// the template kernel's fam_list.  It only depends on the template kernel, is launched FIRST and with a smaller grid:
+// its CTAs take their share of the SMs at once (or exit at once if the list is empty -- every integer-keypoint batch),
+// the common instance's persistent CTAs fill the rest and take over the SMs the family CTAs leave.
 cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
                                      cudaStream_t families_stream) {
     if (args.n_total <= 0) return cudaSuccess;
@@ -1057,31 +1105,24 @@ cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &a
 #define LANE_GRID_CTAS LANE_CTAS
 #endif
     const size_t smem = sizeof(LaneSmem<kLaneThreads>) + LANE_SMEM_PAD;
-    int grid = sm_count * LANE_GRID_CTAS;
     const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
     {
-        // multi-family features (sub-pixel keypoints near a power of two): the list length is only known on
-        // the device, so the grid is sized for the worst case and CTAs without work exit at once
         auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, true>;
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        SolverArgs a2 = args;
-        a2.list = args.fam_list;
-        a2.list_count = args.fam_count;
-        a2.work_counter = args.work_counter + 3;
-        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, families_stream>>>(pyr, a2);
+        const int grid = sm_count * (LANE_FAM_CTAS < LANE_GRID_CTAS ? LANE_FAM_CTAS : LANE_GRID_CTAS);
+        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, families_stream>>>(pyr, args);
         note_launch();
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
     }
-    {
-        auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, false>;
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, args);
-        note_launch();
-        return cudaGetLastError();
-    }
+    auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, false>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const int grid = sm_count * LANE_GRID_CTAS;
+    kernel<<<grid < needed ? grid : needed, kLaneThreads, smem, stream>>>(pyr, args);
+    note_launch();
+    return cudaGetLastError();
 }
 
 }  // namespace legoklt

@@ -424,8 +424,8 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         aw.list = a.defer_list;
         aw.list_count = a.defer_count;
         CU_TRY(launch_klt_warp(view, maps, aw, ctx->sm_count, b->side));
-        // the FAMILIES instance of the lane kernel (features with two coordinate families on some level) follows on
-        // the side stream: it fills the tail of the common instance and, with a deferred join, overlaps the next chunk
+        // the family instance of the lane kernel (features with two coordinate families on some level) goes first, on
+        // the side stream; the common instance on the context stream
         CU_TRY(lane_patch == 7   ? launch_klt_lane(view, a, ctx->sm_count, st, b->side)
                : lane_patch == 8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st, b->side)
                                  : launch_klt_lane_p11(view, a, ctx->sm_count, st, b->side));

@@ -325,6 +325,16 @@ struct L01Params {
     int img0, nimg;
 };
 
+// Output rows per warp: the lane keeps its chunk column and walks kL01Rows consecutive output rows with it, so that
+// the chunk's coefficients and tap offset are loaded once, the 2 * kL01Rows 16-byte loads of a trip are all in flight
+// together (the first version, one row per warp, was load-latency bound: DRAM 47 % of peak, issue slots 55 % active,
+// 3 trips per warp) and the CTA count drops by the same factor.
+#ifndef PYR_L01_ROWS
+#define PYR_L01_ROWS 2
+#endif
+constexpr int kL01Rows = PYR_L01_ROWS;
+constexpr int kL01RowsPerCta = 8 * kL01Rows;
+
 template <bool X2Y2, bool Y2>
 __global__ void __launch_bounds__(256)
 pyramid_l01_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__ L01Params p) {
@@ -337,65 +347,73 @@ pyramid_l01_kernel(const __grid_constant__ PyramidView pyr, const __grid_constan
     uint8_t *dst = l1.base[set] + (size_t)img * l1.slot;
     const int spitch = l0.pitch, scols = l0.cols, srows = l0.rows;
 
-    const int R = 8 * blockIdx.x + warp;
-    if (R < l1.rows) {
-    const int yo = __ldg(p.yofs + R);
-    const short2 b = __ldg(p.ycoef + R);
-    const uint8_t *s0 = src + (size_t)d_clip(yo, srows) * spitch;
-    const uint8_t *s1 = src + (size_t)d_clip(yo + 1, srows) * spitch;
-    uint8_t *drow = dst + (size_t)R * l1.pitch;
+    const int R0 = kL01RowsPerCta * blockIdx.x + kL01Rows * warp;
+    if (R0 < l1.rows) {
     const int dcols = l1.cols, nchunks = (dcols + 7) >> 3, src_last = scols - 1;
+    // per-row constants; rows past the end of the level repeat the last row (computed, not stored)
+    const uint8_t *s0[kL01Rows], *s1[kL01Rows];
+    int b0[kL01Rows], b1[kL01Rows];
+#pragma unroll
+    for (int k = 0; k < kL01Rows; ++k) {
+        const int R = min(R0 + k, l1.rows - 1);
+        const int yo = __ldg(p.yofs + R);
+        const short2 b = __ldg(p.ycoef + R);
+        s0[k] = src + (size_t)d_clip(yo, srows) * spitch;
+        s1[k] = src + (size_t)d_clip(yo + 1, srows) * spitch;
+        b0[k] = b.x;
+        b1[k] = b.y;
+    }
+    uint8_t *drow0 = dst + (size_t)R0 * l1.pitch;
+    const int nrows = min(kL01Rows, l1.rows - R0);
 
-    // chunk i = 16 source bytes per row + the word after them (for delta = 1); the loads of the next trip are
-    // issued before this trip's arithmetic (the kernel is latency-bound otherwise: profiles/)
-    uint4 a_n = make_uint4(0, 0, 0, 0), c_n = a_n;
-    uint32_t na_n = 0, nc_n = 0;
-    int info_n = -1;
-    auto fetch = [&](int i) {
-        if (i < nchunks) {
-            a_n = __ldg(reinterpret_cast<const uint4 *>(s0) + i);
-            c_n = __ldg(reinterpret_cast<const uint4 *>(s1) + i);
-            na_n = __ldg(reinterpret_cast<const uint32_t *>(s0) + 4 * i + 4);  // (the row's allocation extends 48 bytes
-            nc_n = __ldg(reinterpret_cast<const uint32_t *>(s1) + 4 * i + 4);  //  past the last pixel)
-            info_n = __ldg(p.cofs + i);
-        }
-    };
-    fetch(lane);
     for (int i = lane; i < nchunks; i += 32) {
-        const uint4 a = a_n, c = c_n;
-        const uint32_t na = na_n, nc = nc_n;
-        const int info = info_n;
-        fetch(i + 32);
+        // chunk i = 16 source bytes per source row + the word after them (for delta = 1)
+        uint4 a[kL01Rows], c[kL01Rows];
+        uint32_t na[kL01Rows], nc[kL01Rows];
+#pragma unroll
+        for (int k = 0; k < kL01Rows; ++k) {
+            a[k] = __ldg(reinterpret_cast<const uint4 *>(s0[k]) + i);
+            c[k] = __ldg(reinterpret_cast<const uint4 *>(s1[k]) + i);
+            na[k] = __ldg(reinterpret_cast<const uint32_t *>(s0[k]) + 4 * i + 4);  // (the row's allocation extends 48 bytes
+            nc[k] = __ldg(reinterpret_cast<const uint32_t *>(s1[k]) + 4 * i + 4);  //  past the last pixel)
+        }
+        const int info = __ldg(p.cofs + i);
         if (info >= 0) {
-            uint2 out;
             const int sh = (info - 16 * i) * 8;  // 0 or 8 (host-checked)
-            const uint32_t w0[4] = {__funnelshift_r(a.x, a.y, sh), __funnelshift_r(a.y, a.z, sh), __funnelshift_r(a.z, a.w, sh),
-                                    __funnelshift_r(a.w, na, sh)};
-            const uint32_t w1[4] = {__funnelshift_r(c.x, c.y, sh), __funnelshift_r(c.y, c.z, sh), __funnelshift_r(c.z, c.w, sh),
-                                    __funnelshift_r(c.w, nc, sh)};
-            if (X2Y2) {
-                uint32_t t[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    t[q] = (__byte_perm(w0[q], 0u, 0x4240) + __byte_perm(w0[q], 0u, 0x4341) + __byte_perm(w1[q], 0u, 0x4240) +
-                            __byte_perm(w1[q], 0u, 0x4341) + 0x00020002u) >> 2;
-                out.x = __byte_perm(t[0], t[1], 0x6420);
-                out.y = __byte_perm(t[2], t[3], 0x6420);
-            } else {
-                const uint4 cf0 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i);
-                const uint4 cf1 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i + 1);
-                const uint32_t cf[8] = {cf0.x, cf0.y, cf0.z, cf0.w, cf1.x, cf1.y, cf1.z, cf1.w};
-                uint32_t v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int h0 = (j & 1) ? dot2_hi(cf[j], w0[j >> 1]) : dot2_lo(cf[j], w0[j >> 1]);
-                    const int h1 = (j & 1) ? dot2_hi(cf[j], w1[j >> 1]) : dot2_lo(cf[j], w1[j >> 1]);
-                    v[j] = vertical<Y2>(h0, h1, b.x, b.y);
-                }
-                out.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-                out.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+            uint4 cf0 = make_uint4(0, 0, 0, 0), cf1 = cf0;
+            if (!X2Y2) {
+                cf0 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i);
+                cf1 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i + 1);
             }
-            reinterpret_cast<uint2 *>(drow)[i] = out;
+            const uint32_t cf[8] = {cf0.x, cf0.y, cf0.z, cf0.w, cf1.x, cf1.y, cf1.z, cf1.w};
+#pragma unroll
+            for (int k = 0; k < kL01Rows; ++k) {
+                uint2 out;
+                const uint32_t w0[4] = {__funnelshift_r(a[k].x, a[k].y, sh), __funnelshift_r(a[k].y, a[k].z, sh),
+                                        __funnelshift_r(a[k].z, a[k].w, sh), __funnelshift_r(a[k].w, na[k], sh)};
+                const uint32_t w1[4] = {__funnelshift_r(c[k].x, c[k].y, sh), __funnelshift_r(c[k].y, c[k].z, sh),
+                                        __funnelshift_r(c[k].z, c[k].w, sh), __funnelshift_r(c[k].w, nc[k], sh)};
+                if (X2Y2) {
+                    uint32_t t[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        t[q] = (__byte_perm(w0[q], 0u, 0x4240) + __byte_perm(w0[q], 0u, 0x4341) + __byte_perm(w1[q], 0u, 0x4240) +
+                                __byte_perm(w1[q], 0u, 0x4341) + 0x00020002u) >> 2;
+                    out.x = __byte_perm(t[0], t[1], 0x6420);
+                    out.y = __byte_perm(t[2], t[3], 0x6420);
+                } else {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int h0 = (j & 1) ? dot2_hi(cf[j], w0[j >> 1]) : dot2_lo(cf[j], w0[j >> 1]);
+                        const int h1 = (j & 1) ? dot2_hi(cf[j], w1[j >> 1]) : dot2_lo(cf[j], w1[j >> 1]);
+                        v[j] = vertical<Y2>(h0, h1, b0[k], b1[k]);
+                    }
+                    out.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                    out.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+                }
+                if (k < nrows) reinterpret_cast<uint2 *>(drow0 + (size_t)k * l1.pitch)[i] = out;
+            }
         }
     }
     // The irregular chunks (where the tap offset steps, and the partial chunk at the row end): one pixel per lane.
@@ -405,17 +423,23 @@ pyramid_l01_kernel(const __grid_constant__ PyramidView pyr, const __grid_constan
             const int sx = __ldg(p.xofs + col);
             const int sx1 = min(sx + 1, src_last);
             const short2 cf = __ldg(p.xcoef + col);
-            const int h0 = (int)s0[sx] * cf.x + (int)s0[sx1] * cf.y;
-            const int h1 = (int)s1[sx] * cf.x + (int)s1[sx1] * cf.y;
-            drow[col] = (uint8_t)vertical<false>(h0, h1, b.x, b.y);
+#pragma unroll
+            for (int k = 0; k < kL01Rows; ++k) {
+                const int h0 = (int)s0[k][sx] * cf.x + (int)s0[k][sx1] * cf.y;
+                const int h1 = (int)s1[k][sx] * cf.x + (int)s1[k][sx1] * cf.y;
+                if (k < nrows) drow0[(size_t)k * l1.pitch + col] = (uint8_t)vertical<false>(h0, h1, b0[k], b1[k]);
+            }
         }
     }
     }
 
-    // ---- level-0 aprons of the 16 source rows under this CTA: ONE warp, a lane per row (every warp doing two
-    // rows cost a quarter of the kernel's instructions, mostly 64-bit address arithmetic: profiles/)
-    if (warp == 7) {
-        const int Rr = 16 * blockIdx.x + (lane & 15);
+    // ---- level-0 aprons of the 2 * kL01RowsPerCta source rows under this CTA: a lane per row, as few warps as that
+    // takes (every warp doing two rows cost a quarter of the kernel's instructions, mostly 64-bit address
+    // arithmetic: profiles/)
+    constexpr int kApronWarps = (2 * kL01RowsPerCta + 15) / 16;   // 16 rows per warp: lanes 0-15 left, 16-31 right aprons
+    static_assert(kApronWarps <= 8, "apron rows per CTA");
+    if (warp >= 8 - kApronWarps) {
+        const int Rr = 2 * kL01RowsPerCta * blockIdx.x + 16 * (warp - (8 - kApronWarps)) + (lane & 15);
         if (Rr < srows) {
             uint8_t *grow = const_cast<uint8_t *>(src) + (size_t)Rr * spitch;
             const uint32_t first = grow[0], last = grow[scols - 1];
@@ -742,8 +766,10 @@ cudaError_t launch_pyramid(const PyramidPlan &plan, const PyramidView &pyr, int 
     p.n_irr = t.n_irr;
     p.img0 = img0;
     p.nimg = nimg;
-    // 8 level-1 rows and the 16 level-0 rows under them per CTA; one more CTA if an odd last level-0 row is left over
-    const int ctas = std::max((plan.rows[1] + 7) / 8, (plan.rows[0] + 15) / 16);
+    // kL01RowsPerCta level-1 rows and the twice as many level-0 rows under them per CTA; one more CTA if an odd last
+    // level-0 row is left over
+    const int ctas = std::max((plan.rows[1] + kL01RowsPerCta - 1) / kL01RowsPerCta,
+                              (plan.rows[0] + 2 * kL01RowsPerCta - 1) / (2 * kL01RowsPerCta));
     dim3 grid(ctas, n_sets * nimg);
     if (t.x_exact2 && t.y_exact2) pyramid_l01_kernel<true, true><<<grid, 256, 0, stream>>>(pyr, p);
     else if (t.y_exact2) pyramid_l01_kernel<false, true><<<grid, 256, 0, stream>>>(pyr, p);
