@@ -13,10 +13,11 @@
 //     legoslam::LKOpticalFlow4Layer(last_frame_->left_img_, current_frame_->left_img_,
 //                                   kps_last, kps_current, status, false, true);
 //
-// Header only; needs liblego_klt.so (include/lego_klt.h) at link time.  It is templated on the matrix /
-// keypoint types only so that it can be compiled and tested without OpenCV headers (tests/shim/ uses
-// look-alike PODs); with OpenCV present the non-template overloads at the bottom bind cv::Mat /
-// cv::KeyPoint.
+// Header only; needs liblego_klt.so (include/lego_klt.h) at link time.  The entry points are templates on the matrix /
+// keypoint types (any type with data / cols / rows / step and pt.x / pt.y: cv::Mat and cv::KeyPoint bind as they
+// are), so that the header compiles and is tested without OpenCV (tests/shim/ uses look-alike PODs).  Inside the
+// reference's own tree, where include/legoslam/algorithm.h already declares the two functions, define
+// LEGOSLAM_GPU_DEFINE_ENTRY_POINTS in src/algorithm.cpp instead (see the bottom of this file).
 //
 // Behaviour kept from the reference (src/algorithm.cpp):
 //   * kp2 and success are resized to kp1.size() (:17-18, :158); kp2[i].pt is overwritten, every other
@@ -24,7 +25,12 @@
 //   * has_initial == false ignores the incoming kp2 positions on the coarsest level (:47-50, :185-189);
 //   * inverse == true is the reference's inverse mode including its stale-Jacobian behaviour.
 // Differences: errors are reported (std::runtime_error with the library's message) instead of being
-// impossible / UB; nothing is printed on NaN (the reference prints "Update is NaN or INF.", :97).
+// impossible / UB; nothing is printed on NaN (the reference prints "Update is NaN or INF.", :97);
+// img1 and img2 must have the same cols, rows and step.  The reference would also accept two images of different
+// shapes (src/algorithm.cpp:128-154 builds the two pyramids independently and every GetPixelValue / IsPtInImg uses
+// the size of the image it is given), but neither of its call sites does that (last/current and left/right frames of
+// one camera rig, src/frontend_g2o.cpp:473,515), and the device layout keeps both images of a pair in one shape:
+// such a call throws here rather than computing something else.
 #ifndef LEGOSLAM_GPU_ALGORITHM_SHIM_H
 #define LEGOSLAM_GPU_ALGORITHM_SHIM_H
 
@@ -134,17 +140,30 @@ bool triangulation(const std::vector<SE3T> &poses, const std::vector<Vec3T, Allo
     return ok != 0;
 }
 
-#ifdef OPENCV_CORE_HPP  // OpenCV present: exact reference signatures (include/legoslam/algorithm.h:123-136)
-inline void LKOpticalFlow1Layer(const cv::Mat &img1, const cv::Mat &img2, const std::vector<cv::KeyPoint> &kp1,
-                                std::vector<cv::KeyPoint> &kp2, std::vector<bool> &success, bool inverse = false,
-                                bool has_initial = true) {
+// ---- the reference's own two functions, for the translation unit that used to define them ------------------------
+// include/legoslam/algorithm.h:123-136 DECLARES
+//     void LKOpticalFlow1Layer(const cv::Mat &, const cv::Mat &, const std::vector<cv::KeyPoint> &,
+//                              std::vector<cv::KeyPoint> &, std::vector<bool> &, bool inverse=false, bool has_initial=true);
+//     void LKOpticalFlow4Layer(... same ...);
+// with their default arguments, and src/algorithm.cpp DEFINES them.  A maintainer keeps the declarations as they are
+// and replaces the two definitions in src/algorithm.cpp by
+//     #define LEGOSLAM_GPU_DEFINE_ENTRY_POINTS
+//     #include "legoslam_gpu/algorithm_shim.h"
+// which expands to the two definitions below: ordinary (non-inline, non-template) functions with exactly the declared
+// signatures and NO default arguments of their own -- a default argument may be given only once, and the reference's
+// header has already given it.  Exactly one translation unit of a program may define the macro (one definition rule).
+// Needs the OpenCV core header before this one (OPENCV_CORE_HPP is its include guard).
+#if defined(LEGOSLAM_GPU_DEFINE_ENTRY_POINTS) && defined(OPENCV_CORE_HPP)
+void LKOpticalFlow1Layer(const cv::Mat &img1, const cv::Mat &img2, const std::vector<cv::KeyPoint> &kp1,
+                         std::vector<cv::KeyPoint> &kp2, std::vector<bool> &success, bool inverse, bool has_initial) {
     gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 1);
 }
-inline void LKOpticalFlow4Layer(const cv::Mat &img1, const cv::Mat &img2, const std::vector<cv::KeyPoint> &kp1,
-                                std::vector<cv::KeyPoint> &kp2, std::vector<bool> &success, bool inverse = false,
-                                bool has_initial = true) {
-    gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 4);
+void LKOpticalFlow4Layer(const cv::Mat &img1, const cv::Mat &img2, const std::vector<cv::KeyPoint> &kp1,
+                         std::vector<cv::KeyPoint> &kp2, std::vector<bool> &success, bool inverse, bool has_initial) {
+    gpu::LKOpticalFlowNLayer(img1, img2, kp1, kp2, success, inverse, has_initial, 4);  // src/algorithm.cpp:135
 }
+#elif defined(LEGOSLAM_GPU_DEFINE_ENTRY_POINTS)
+#error "LEGOSLAM_GPU_DEFINE_ENTRY_POINTS needs <opencv2/core.hpp> included first"
 #endif
 
 }  // namespace legoslam

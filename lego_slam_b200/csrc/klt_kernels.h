@@ -93,6 +93,14 @@ cudaError_t launch_klt_template_p11(const PyramidView &pyr, const SolverArgs &ar
 cudaError_t launch_klt_lane_p11(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
                             cudaStream_t families_stream);
 
+// ... and for the reference's inverse mode, 7x7 patch (klt_solver_lane_inv.cu; BASELINE config C4).
+bool lane_kernel_supports_inv(const SolverArgs &args);
+size_t lane_template_bytes_inv(int n_total, int levels);
+size_t lane_scratch_bytes_inv(int sm_count);
+cudaError_t launch_klt_template_inv(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
+cudaError_t launch_klt_lane_inv(const PyramidView &pyr, const SolverArgs &args, int sm_count, cudaStream_t stream,
+                                cudaStream_t families_stream);
+
 // ---- triangulation (triangulate_sm100.cu) ------------------------------------------------
 constexpr int kTriMaxViews = 8;
 // poses34: host, n_views x 12 (row-major 3x4); points: device, n x n_views x {x, y}; outputs: device n x 3 / n.

@@ -68,7 +68,19 @@ namespace {
 #define LANE_FN(name) LANE_CAT(name, LANE_SUFFIX)
 constexpr int LO = LANE_PATCH_LO, HI = LANE_PATCH_HI, P = HI - LO + 1, G = P + 2;
 static_assert(P >= 3 && P <= 12, "family masks hold 12 bits per axis");
-constexpr int kNP = (G + 1) / 2;                               // sample pairs per grid row: samples (2j, 2j+1), j < kNP
+// LANE_INVERSE: the reference's inverse mode INCLUDING its stale Jacobian (src/algorithm.cpp:57,74-80,83):
+// the Jacobian of a pixel is the img1 gradient at the template position, refreshed only in the first pass of a level;
+// every later pass uses the Jacobian of the LAST pixel (x = y = HI) of that first pass for all pixels, and H is the
+// first pass's.  The template kernel then also stores the two img1 gradient differences per pixel (three planes per
+// record), the solver samples img2 at the P x P pixel centres only (no +-1 taps), and after the first pass of a level
+// a thread overwrites its gradient planes with the last pixel's values, so that every pass runs the same code.
+#ifndef LANE_INVERSE
+#define LANE_INVERSE 0
+#endif
+constexpr bool kInverse = LANE_INVERSE != 0;
+constexpr int kG0 = kInverse ? 1 : 0;                          // first grid index the solver samples on img2
+constexpr int kNS = kInverse ? P : G;                          // img2 samples per grid row / sampled grid rows
+constexpr int kNP = (kNS + 1) / 2;                             // sample pairs per grid row: samples (2j, 2j+1), j < kNP
 constexpr int kRowWords = (2 * kNP + 1 + 3) / 4 + 1;           // window words a row step reads: 2 kNP + 1 pixels at a
                                                               // byte offset of 0..3
 constexpr unsigned kPMask = (1u << P) - 1u;                    // one bit per patch column / row
@@ -90,7 +102,7 @@ constexpr int kWinSlackL = (LANE_WWORDS == 8) ? 2 : 3;         // footprint star
 constexpr int kWinSlackT = (LANE_WROWS - (G + 1)) / 2;         // rows above the footprint
 static_assert(kWin2Rows >= G + 1 && kWin2Words * 4 >= G + 1 + kWinSlackL + kWinAlign - 1,
               "the window must hold the footprint at every alignment (a footprint that never fits would re-stage forever)");
-constexpr int kTplRows = P + 1;                               // img1 window rows in the template kernel
+constexpr int kTplRows = kInverse ? G + 1 : P + 1;            // img1 window rows in the template kernel
 // The per-thread shared memory is made of 16-byte granules, [granule][T], so that a level set-up is 38 16-byte
 // cp.async copies straight from global memory, all in flight together, no register staging (the first layout,
 // [word][T] with conflict-free 32-bit accesses, needed ~170 set-up instructions incl. 121 32-bit stores: 7 % slower
@@ -101,9 +113,11 @@ constexpr int kI1Count = P * kTplPitch;                       // template floats
 static_assert(LANE_WWORDS == 8, "granule layout: 32-byte window rows");
 constexpr int kQueue = LANE_QUEUE;                            // feature ring entries per warp (power of two, >= 32)
 static_assert(kQueue >= 32 && (kQueue & (kQueue - 1)) == 0, "ring size");
-constexpr int kTplStride = ((kI1Count + 1 + 3) / 4 * 4) | 4;   // floats per (feature, level): patch + flag + pad; an ODD
+constexpr int kRecPlanes = kInverse ? 3 : 1;                  // record planes: I1 [, img1 x difference, img1 y difference]
+constexpr int kRecCount = kRecPlanes * kI1Count;
+constexpr int kTplStride = ((kRecCount + 1 + 3) / 4 * 4) | 4;  // floats per (feature, level): planes + flag + pad; an ODD
                                                               // number of float4 (conflict-free transposed stores)
-static_assert(kTplStride >= kI1Count + 1 && (kTplStride / 4) % 2 == 1 && kTplStride % 4 == 0, "template record stride");
+static_assert(kTplStride >= kRecCount + 1 && (kTplStride / 4) % 2 == 1 && kTplStride % 4 == 0, "template record stride");
 #ifndef LANE_BATCH
 #define LANE_BATCH 1
 #endif
@@ -130,7 +144,7 @@ template <int T>
 struct LaneSmem {
     // granules of one thread: window rows (2 each), template rows (kTplPitch / 4 each)
     static constexpr int kGranTpl = 2 * kWin2Rows,   // (window granules first)
-                         kGranTotal = kGranTpl + kI1Count / 4;
+                         kGranTotal = kGranTpl + kRecCount / 4;
     uint4 g[kGranTotal][T];
     // per-warp ring of fetched features: one global atomic + coalesced keypoint loads per 32 features
     float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
@@ -399,6 +413,36 @@ __device__ __noinline__ void exact_pass(const uint8_t *img2, const LevelView &lv
     sums[5] = s11;
 }
 
+// The same for the inverse mode: only the img2 centre samples are taken per pixel in the reference formulation
+// (src/algorithm.cpp:65-66); the gradient differences are the record's (first pass: img1 gradients, later: stale).
+__device__ __noinline__ void exact_pass_inverse(const uint8_t *img2, const LevelView &lv, const float *rec, int ws, float kx,
+                                                float ky, double dx, double dy, double (&sums)[6]) {
+    double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
+#pragma unroll 1
+    for (int p = 0; p < P * P; ++p) {
+        const int y = p / P, x = p - y * P;
+        const float fx = kx + (float)(LO + x), fy = ky + (float)(LO + y);
+        const double cx = (double)fx + dx, cy = (double)fy + dy;
+        const int idx = y * kTplPitch + x;
+        const float i1v = rec[(idx >> 2) * ws + (idx & 3)];
+        const double e = (double)(i1v - sample_flat_cold(img2, lv, (float)cx, (float)cy));
+        const double gx = (double)rec[((kI1Count + idx) >> 2) * ws + ((kI1Count + idx) & 3)];
+        const double gy = (double)rec[((2 * kI1Count + idx) >> 2) * ws + ((2 * kI1Count + idx) & 3)];
+        sb0 = fma(e, gx, sb0);
+        sb1 = fma(e, gy, sb1);
+        sc = fma(e, e, sc);
+        s00 = fma(gx, gx, s00);
+        s01 = fma(gx, gy, s01);
+        s11 = fma(gy, gy, s11);
+    }
+    sums[0] = sb0;
+    sums[1] = sb1;
+    sums[2] = sc;
+    sums[3] = s00;
+    sums[4] = s01;
+    sums[5] = s11;
+}
+
 // Level-l coordinate of a level-0 keypoint coordinate (src/algorithm.cpp:160-169 then :194 repeatedly):
 // float(k * 2^-(L-1)), then exact doublings.
 __device__ __forceinline__ float level_coord(float k0, int L, int level) {
@@ -415,7 +459,7 @@ __device__ __forceinline__ float level_coord(float k0, int L, int level) {
 // word offset ox>>2 (0..4) is applied with a 3-stage select network (registers cannot be indexed
 // dynamically), the byte offset with funnel shifts.  No shared memory: the first version of this kernel
 // bounced every row through shared memory and was MIO-throttled (profiles/README.md).
-constexpr int kTplPx = P + 2;
+constexpr int kTplPx = kInverse ? G + 1 : P + 2;   // (inverse mode: the whole G x G grid needs G + 1 pixels per row)
 constexpr int kTplWords = (kTplPx + 3) / 4 + 1;   // words holding kTplPx pixels at a byte offset of 0..3
 __device__ __forceinline__ void row_from_regs(const uint4 &q0, const uint4 &q1, int k, int sh, float (&row)[G + 1]) {
     const uint32_t w[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, 0u};
@@ -492,12 +536,13 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     }
     // Patches up to 8x8 collect the record in registers and store it as float4; larger ones (121 values) go to the
     // staging memory value by value instead, or the kernel would not fit the register file.
-    constexpr bool kDirect = (kI1Count > 64);
+    constexpr bool kDirect = (kRecCount > 64);
     float *mine_f = reinterpret_cast<float *>(&stage[warp][lane * (kTplStride / 4)]);
     float buf[kDirect ? 4 : kTplStride];
 #pragma unroll
     for (int i = 0; i < (kDirect ? 4 : kTplStride); ++i) buf[i] = 0.f;
     if (regular) regular = window_in_apron(lv, (ixn - 2) & ~15, 32);
+    if (kInverse && regular && (mBx | mBy)) regular = false;  // (the inverse instance has no family handling: exact warp kernel)
     // Class of the feature, decided by its levels with an atomicMax on its flag (values of earlier runs are smaller):
     //   4*epoch + 2  irregular on some level -> the exact warp kernel (deferred list)
     //   4*epoch + 1  two coordinate families on some level -> the lane kernel's SECOND phase (family list): those
@@ -518,6 +563,50 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         const int tag = 4 * args.epoch + 1;
         if (atomicMax(&args.feat_flag[f], tag) < tag) args.fam_list[atomicAdd(args.fam_count, 1)] = f;
     }
+#if LANE_INVERSE
+    if (regular) {
+        // The whole G x G grid of img1 at d = 0: its P x P centre is the template, its +-1 neighbours give the Jacobian
+        // of src/algorithm.cpp:75-79.  The reference forms those coordinates in fp32, fl32(fl32(kx + x) +- 1); with
+        // kx + x exact (single coordinate family, checked above) that is fl32(kx + x +- 1), the grid's coordinate.
+        // Image rows iyn .. iyn+G and columns ixn .. ixn+G.
+        const int wx0 = (ixn - 2) & ~15, wy0 = iyn;
+        const int ox = ixn - wx0;
+        const int k = ox >> 2, sh = (ox & 3) * 8;
+        const uint8_t *img1 = lv.base[0] + (size_t)img * lv.slot;
+        float rowA[G + 1], rowB[G + 1];
+        float Sa[G], Sb[G], Sc[G];  // sample rows r-2, r-1, r
+        auto pixel_row = [&](int i, float (&row)[G + 1]) {
+            const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+            const uint4 *rp = reinterpret_cast<const uint4 *>(img1 + (ptrdiff_t)ry * lv.pitch + wx0);
+            row_from_regs(__ldg(rp), __ldg(rp + 1), k, sh, row);
+        };
+        pixel_row(0, rowA);
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+            pixel_row(r + 1, rowB);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                Sc[g] = bilerp(omx[g], xx[g], omy[r], yy[r], rowA[g], rowA[g + 1], rowB[g], rowB[g + 1]);
+            if (r >= 2) {
+                const int y = r - 2;
+#pragma unroll
+                for (int x = 0; x < P; ++x) {
+                    mine_f[y * kTplPitch + x] = Sb[x + 1];                                          // :65  I1
+                    mine_f[kI1Count + y * kTplPitch + x] = __fadd_rn(Sb[x + 2], -Sb[x]);           // :76-77
+                    mine_f[2 * kI1Count + y * kTplPitch + x] = __fadd_rn(Sc[x + 1], -Sa[x + 1]);   // :78-79
+                }
+            }
+#pragma unroll
+            for (int g = 0; g <= G; ++g) rowA[g] = rowB[g];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                Sa[g] = Sb[g];
+                Sb[g] = Sc[g];
+            }
+        }
+        mine_f[kRecCount] = 1.f;  // regularity flag
+    }
+#else
     if (regular) {
         // the PxP centre of the GxG grid needs image rows iyn+1 .. iyn+P+1 and columns ixn+1 .. ixn+P+1
         const int wx0 = (ixn - 2) & ~15, wy0 = iyn + 1;
@@ -550,6 +639,7 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         if (kDirect) mine_f[kI1Count] = 1.f;  // regularity flag
         else buf[kI1Count] = 1.f;
     }
+#endif
     if (!kDirect) {
         float4 *mine = &stage[warp][lane * (kTplStride / 4)];
 #pragma unroll
@@ -616,6 +706,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
     bool need_win = false, no_window = false;
     // coordinate families of this level: bits 0-6 x mask of family B, 8-14 y mask, 16-17 current sub-pass
     unsigned fam = 0u;
+    double H00s = 0, H01s = 0, H11s = 0;  // inverse mode: the normal matrix of the level's first pass (src/algorithm.cpp:59,85-87)
 #if !LANE_PARK_SMEM
     double pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, pk4 = 0, pk5 = 0;  // partial sums between the sub-passes of a pass
 #endif
@@ -743,7 +834,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     }
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(gp + LaneSmem<T>::kGranTpl * T);
 #pragma unroll
-                    for (int j = 0; j < kI1Count / 4; ++j)
+                    for (int j = 0; j < kRecCount / 4; ++j)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * T * 16), "l"(tp + 16 * j) : "memory");
                 }
                 if (!no_window) {
@@ -823,12 +914,12 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
             bool solve_now = true;
             if (fast) {
-            const int ox = ixn - wx0;
+            const int ox = ixn + kG0 - wx0;   // (inverse mode samples grid indices 1..P only)
             const int sh = (ox & 3) * 8;
             WinRef wr;
             {   // word kw + k of a row: granule (kw + k) >> 2 of the row, position (kw + k) & 3 inside it
                 const int kw = ox >> 2;
-                wr.base = reinterpret_cast<const uint32_t *>(&sm.g[2 * (iyn - wy0)][tid]);
+                wr.base = reinterpret_cast<const uint32_t *>(&sm.g[2 * (iyn + kG0 - wy0)][tid]);
                 wr.row_stride = 2 * T * 4;
 #pragma unroll
                 for (int k = 0; k < kRowWords; ++k) wr.off[k] = ((kw + k) >> 2) * (T * 4) + ((kw + k) & 3);
@@ -836,15 +927,15 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             // Row factors of grid row r, formed when the row is sampled: n_r = (double)(LO - 1 + r) and
             // fg_r = (float)(origin + r) are carried through the loop (both exact).
             const float frows = (float)lv.rows, flastrow = (float)(lv.rows - 1);
-            double n_r = (double)(LO - 1);
-            float fg_r = yax.forigin;
+            double n_r = (double)(LO - 1 + kG0);
+            float fg_r = __fadd_rn(yax.forigin, (float)kG0);
             unsigned near_y = 0xFFFFFFFFu;
             auto row_weights = [&](float &om, float &fr) {
                 axis_factor<true>(yax, n_r, fg_r, frows, flastrow, near_y, om, fr);
                 n_r += 1.0;
                 fg_r = __fadd_rn(fg_r, 1.f);
             };
-            auto template_row = [&](int y, float (&v)[P]) {          // kTplPitch / 4 granules per row
+            auto template_row = [&](int y, float (&v)[P]) {          // kTplPitch / 4 granules per row (y: row of any plane)
 #pragma unroll
                 for (int q = 0; q < kTplPitch / 4; ++q) {
                     const float4 t = *reinterpret_cast<const float4 *>(i1p + (y * (kTplPitch / 4) + q) * (T * 4));
@@ -859,9 +950,36 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             float2 OMX[kNP], XX[kNP];
 #pragma unroll
             for (int j = 0; j < kNP; ++j) {
-                OMX[j] = make_float2(omx[2 * j], 2 * j + 1 < G ? omx[2 * j + 1] : 0.f);
-                XX[j] = make_float2(xx[2 * j], 2 * j + 1 < G ? xx[2 * j + 1] : 0.f);
+                OMX[j] = make_float2(omx[kG0 + 2 * j], 2 * j + 1 < kNS ? omx[kG0 + 2 * j + 1] : 0.f);
+                XX[j] = make_float2(xx[kG0 + 2 * j], 2 * j + 1 < kNS ? xx[kG0 + 2 * j + 1] : 0.f);
             }
+#if LANE_INVERSE
+            // Inverse mode: one img2 sample per pixel (its centre); the gradient differences come from the record --
+            // the img1 gradients of the first pass, or, in later passes, the last pixel's copied over all pixels.
+            load_row10_packed(wr, 0, sh, rowA);
+#pragma unroll 1
+            for (int y = 0; y < P; ++y) {
+                load_row10_packed(wr, y + 1, sh, rowB);
+                float om_s, fr_s, tpl[P], rgx[P], rgy[P];
+                row_weights(om_s, fr_s);
+                template_row(y, tpl);
+                template_row(P + y, rgx);
+                template_row(2 * P + y, rgy);
+                sample_row_packed(OMX, XX, om_s, fr_s, rowA, rowB, args.one, Sc);
+#pragma unroll
+                for (int x = 0; x < P; ++x) {
+                    const double e = (double)__fadd_rn(tpl[x], -pick(Sc, x));  // :65-66
+                    const double gx = (double)rgx[x], gy = (double)rgy[x];     // :75-79 (first pass) / stale J (:57)
+                    sb0 = fma(e, gx, sb0);
+                    sb1 = fma(e, gy, sb1);
+                    sc = fma(e, e, sc);
+                    s00 = fma(gx, gx, s00);
+                    s01 = fma(gx, gy, s01);
+                    s11 = fma(gy, gy, s11);
+                }
+                rowA = rowB;
+            }
+#else
 
             // The row loop is deliberately NOT unrolled: the unrolled pass (1785 SASS instructions) did
             // not fit the instruction cache and the kernel was fetch-bound (profiles/README.md).
@@ -945,6 +1063,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             } else {
                 rows(std::false_type{});
             }
+#endif
 
             if (!axis_ok(near_y, yax.tie)) {  // condition (b) failed on some grid row (rare): redo the pass exactly
                 fast = false;
@@ -954,7 +1073,11 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             if (!fast) {
                 // the reference formulation covers the whole patch whatever its families: restart the pass
                 double sums[6];
+#if LANE_INVERSE
+                exact_pass_inverse(lv.base[1] + (size_t)img * lv.slot, lv, i1p, kI1Stride, kx, ky, dx, dy, sums);
+#else
                 exact_pass(lv.base[1] + (size_t)img * lv.slot, lv, i1p, kI1Stride, kx, ky, dx, dy, sums);
+#endif
                 sb0 = sums[0];
                 sb1 = sums[1];
                 sc = sums[2];
@@ -1010,6 +1133,29 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
 
             // J = -0.5 * g: rescaling the sums by exact powers of two commutes with every rounding
             const double b0 = 0.5 * sb0, b1 = 0.5 * sb1, cost = sc;
+            if (kInverse) {  // H is accumulated in the first pass of a level only and never reset (:59,85-87)
+                if (iter == 0) {
+                    H00s = s00;
+                    H01s = s01;
+                    H11s = s11;
+                    // from now on every pixel uses the Jacobian of the first pass's LAST pixel (:57,74-80,83): copy its
+                    // two gradient differences over the gradient planes of this thread's record
+                    float *rec = const_cast<float *>(i1p);
+                    const int last = (P - 1) * kTplPitch + (P - 1);
+                    const float gxl = rec[((kI1Count + last) >> 2) * kI1Stride + ((kI1Count + last) & 3)];
+                    const float gyl = rec[((2 * kI1Count + last) >> 2) * kI1Stride + ((2 * kI1Count + last) & 3)];
+                    const float4 vx = make_float4(gxl, gxl, gxl, gxl), vy = make_float4(gyl, gyl, gyl, gyl);
+#pragma unroll 1
+                    for (int q = 0; q < kI1Count / 4; ++q) {
+                        *reinterpret_cast<float4 *>(rec + (kI1Count / 4 + q) * kI1Stride) = vx;
+                        *reinterpret_cast<float4 *>(rec + (2 * (kI1Count / 4) + q) * kI1Stride) = vy;
+                    }
+                } else {
+                    s00 = H00s;
+                    s01 = H01s;
+                    s11 = H11s;
+                }
+            }
             const double H00 = 0.25 * s00, H01 = 0.25 * s01, H11 = 0.25 * s11;
             ++iter;
             bool level_done = false;
@@ -1074,7 +1220,8 @@ constexpr int kTplThreads = LANE_TPL_T;
 }  // namespace
 
 bool LANE_FN(lane_kernel_supports)(const SolverArgs &args) {
-    return args.patch_lo == LO && args.patch_hi == HI && !args.inverse && args.max_iters >= 1 && args.max_iters <= 15;
+    return args.patch_lo == LO && args.patch_hi == HI && (args.inverse != 0) == kInverse && args.max_iters >= 1 &&
+           args.max_iters <= 15;
 }
 
 size_t LANE_FN(lane_template_bytes)(int n_total, int levels) { return (size_t)n_total * levels * kTplStride * sizeof(float); }
@@ -1106,7 +1253,7 @@ cudaError_t LANE_FN(launch_klt_lane)(const PyramidView &pyr, const SolverArgs &a
 #endif
     const size_t smem = sizeof(LaneSmem<kLaneThreads>) + LANE_SMEM_PAD;
     const int needed = (args.n_total + kLaneThreads - 1) / kLaneThreads;
-    {
+    if (!kInverse) {  // (the inverse instance has no family handling: the template kernel defers those features)
         auto kernel = klt_lane_kernel<kLaneThreads, kLaneMinCtas, true>;
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;

@@ -13,6 +13,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 #include "klt_kernels.h"
 
 using namespace legoklt;
@@ -42,6 +44,13 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// NVTX range around a host-side phase (ranges around K1 / K2 / H2D): the kernels and copies enqueued
+// inside it are attributed to it by the profilers.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 enum { EV_START = 0, EV_H2D, EV_PYR, EV_SOLVE, EV_D2H, EV_COUNT };
 constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings)
@@ -339,9 +348,11 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
     if (ring) CU_TRY(cudaEventRecord(ring[0], st));
     if (!view_override) {
+        NvtxRange r("lego_klt K1 pyramid");
         CU_TRY(launch_pyramid(b->plan, b->view, img0, nimg, st));  // (row aprons included)
     }
     if (ring) CU_TRY(cudaEventRecord(ring[1], st));
+    NvtxRange solver_range("lego_klt K2 solver");
     SolverArgs a;
     a.kp1 = b->d_kp1;
     a.kp2_init = b->d_kp2_init;
@@ -390,21 +401,28 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     // threads); below ~4k features of one call the warp-per-feature kernel has the lower latency (measured, 1241x376:
     // n = 2000: 0.24 vs 0.31 ms per call, n = 5000: equal, n = 20000: 0.70 vs 0.42 ms).  Same fidelity contract.
     // the LANE solver is compiled for three patches (klt_solver_lane*.cu): 0 = none, else the patch width
-    const int lane_patch = lane_kernel_supports(a) ? 7 : lane_kernel_supports_p8(a) ? 8 : lane_kernel_supports_p11(a) ? 11 : 0;
+    // (-7: the reference's inverse mode, 7x7)
+    const int lane_patch = lane_kernel_supports(a)       ? 7
+                           : lane_kernel_supports_p8(a)  ? 8
+                           : lane_kernel_supports_p11(a) ? 11
+                           : lane_kernel_supports_inv(a) ? -7
+                                                         : 0;
     if (kernel == LEGO_KLT_KERNEL_AUTO)
         kernel = (lane_patch && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_patch)
         return fail(LEGO_KLT_ERR_UNSUPPORTED,
-                    "LANE kernel: forward mode with the 7x7 (-3..3), 8x8 (-4..3) or 11x11 (-5..5) patch only");
+                    "LANE kernel: forward mode with the 7x7 (-3..3), 8x8 (-4..3) or 11x11 (-5..5) patch, or inverse mode "
+                    "with the 7x7 patch");
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(view, maps, a, ctx->sm_count, st));
     } else if (a.n_total > 0) {
         const size_t cap = (size_t)b->B * (size_t)(b->n_cap > 0 ? b->n_cap : 1);
-        int rc = ensure_lane_buffers(b, lane_patch == 7   ? lane_template_bytes((int)cap, b->levels)
-                                        : lane_patch == 8 ? lane_template_bytes_p8((int)cap, b->levels)
-                                                          : lane_template_bytes_p11((int)cap, b->levels));
+        int rc = ensure_lane_buffers(b, lane_patch == 7    ? lane_template_bytes((int)cap, b->levels)
+                                        : lane_patch == 8  ? lane_template_bytes_p8((int)cap, b->levels)
+                                        : lane_patch == 11 ? lane_template_bytes_p11((int)cap, b->levels)
+                                                           : lane_template_bytes_inv((int)cap, b->levels));
         if (rc) return rc;
         a.templates = b->d_templates;
         a.tpl_features = (unsigned long long)b->B * (unsigned long long)(b->n_cap > 0 ? b->n_cap : 1);
@@ -413,9 +431,10 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         a.epoch = (int)((b->runs % 0x0fffffff) + 1);
         if (a.epoch == 1 && b->runs > 0)  // the run counter wrapped: flags of earlier runs would look newer than this one
             CU_TRY(cudaMemsetAsync(b->d_feat_flag, 0, cap * sizeof(int), st));
-        CU_TRY(lane_patch == 7   ? launch_klt_template(view, a, st)
-               : lane_patch == 8 ? launch_klt_template_p8(view, a, st)
-                                 : launch_klt_template_p11(view, a, st));
+        CU_TRY(lane_patch == 7    ? launch_klt_template(view, a, st)
+               : lane_patch == 8  ? launch_klt_template_p8(view, a, st)
+               : lane_patch == 11 ? launch_klt_template_p11(view, a, st)
+                                  : launch_klt_template_inv(view, a, st));
         // features with an irregular template (kx+c inexact in fp32, ...) are solved by the exact warp
         // kernel on a second stream while the lane kernel solves the rest
         CU_TRY(cudaEventRecord(b->ev_fork, st));
@@ -426,9 +445,10 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         CU_TRY(launch_klt_warp(view, maps, aw, ctx->sm_count, b->side));
         // the family instance of the lane kernel (features with two coordinate families on some level) goes first, on
         // the side stream; the common instance on the context stream
-        CU_TRY(lane_patch == 7   ? launch_klt_lane(view, a, ctx->sm_count, st, b->side)
-               : lane_patch == 8 ? launch_klt_lane_p8(view, a, ctx->sm_count, st, b->side)
-                                 : launch_klt_lane_p11(view, a, ctx->sm_count, st, b->side));
+        CU_TRY(lane_patch == 7    ? launch_klt_lane(view, a, ctx->sm_count, st, b->side)
+               : lane_patch == 8  ? launch_klt_lane_p8(view, a, ctx->sm_count, st, b->side)
+               : lane_patch == 11 ? launch_klt_lane_p11(view, a, ctx->sm_count, st, b->side)
+                                  : launch_klt_lane_inv(view, a, ctx->sm_count, st, b->side));
         if (deferred_join) {
             CU_TRY(cudaEventRecord(deferred_join, b->side));   // the caller joins before it needs the results
         } else {
@@ -747,6 +767,7 @@ int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t
     const size_t nt = (size_t)b->B * (size_t)b->n_active;
     if (nt && (!kp1_xy || !kp2_xy)) return fail(LEGO_KLT_ERR_BAD_ARG, "keypoint pointer is null");
     CU_TRY(cudaSetDevice(b->ctx->device));
+    NvtxRange range("lego_klt H2D");
     cudaStream_t st = b->ctx->stream;
     CU_TRY(cudaEventRecord(b->ev[EV_START], st));
     CU_TRY(upload_set(b, 0, imgs1, 0, b->B, st));
@@ -805,6 +826,7 @@ int lego_klt_batch_download(lego_klt_batch *b, float *kp2_xy, uint8_t *success, 
     const size_t nt = (size_t)b->B * (size_t)b->n_active;
     if (nt && (!kp2_xy || !success)) return fail(LEGO_KLT_ERR_BAD_ARG, "output pointer is null");
     CU_TRY(cudaSetDevice(b->ctx->device));
+    NvtxRange range("lego_klt D2H");
     cudaStream_t st = b->ctx->stream;
     if (nt) {
         CU_TRY(cudaMemcpyAsync(kp2_xy, b->d_kp2_out, nt * sizeof(float2), cudaMemcpyDeviceToHost, st));
@@ -899,8 +921,11 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
             const int img0 = bounds[c], img1 = bounds[c + 1];
             const int nimg = img1 - img0;
             if (nimg <= 0) continue;
-            CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));
-            CU_TRY(upload_set(b, 1, imgs2, img0, nimg, b->copy));
+            {
+                NvtxRange range("lego_klt H2D chunk");
+                CU_TRY(upload_set(b, 0, imgs1, img0, nimg, b->copy));
+                CU_TRY(upload_set(b, 1, imgs2, img0, nimg, b->copy));
+            }
             CU_TRY(cudaEventRecord(b->ev_chunk[c], b->copy));
             CU_TRY(cudaStreamWaitEvent(st, b->ev_chunk[c], 0));
             CU_TRY(ingest_set(b, 0, img0, nimg, st));

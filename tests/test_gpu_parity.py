@@ -19,7 +19,8 @@ def _supported(kernel, kw):
     and the 11x11 stress patch (-5..5), forward mode."""
     if kernel != klt.KERNEL_LANE:
         return True
-    return (kw.get("patch_lo", -3), kw.get("patch_hi", 3)) in ((-3, 3), (-4, 3), (-5, 5)) and not kw.get("inverse", False)
+    patch = (kw.get("patch_lo", -3), kw.get("patch_hi", 3))
+    return patch == (-3, 3) if kw.get("inverse", False) else patch in ((-3, 3), (-4, 3), (-5, 5))
 
 
 def _iters(st, levels):
@@ -319,10 +320,11 @@ def test_lane_kernel_rejects_unsupported_configurations(tracker):
     from lego_slam_b200 import _lib
     img = np.zeros((64, 64), np.uint8)
     kp = np.full((1, 2), 30, np.float32)
-    with pytest.raises(_lib.KltError):
-        tracker.track(img, img, kp, kp, klt.make_params(levels=2, inverse=True, kernel=klt.KERNEL_LANE))
+    with pytest.raises(_lib.KltError):   # inverse mode is compiled for the reference's 7x7 patch only
+        tracker.track(img, img, kp, kp, klt.make_params(levels=2, inverse=True, patch_lo=-4, patch_hi=3, kernel=klt.KERNEL_LANE))
     with pytest.raises(_lib.KltError):
         tracker.track(img, img, kp, kp, klt.make_params(levels=2, patch_lo=-6, patch_hi=6, kernel=klt.KERNEL_LANE))
+    tracker.track(img, img, kp, kp, klt.make_params(levels=2, inverse=True, kernel=klt.KERNEL_LANE))   # supported
 
 
 @pytest.mark.gpu
