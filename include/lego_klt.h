@@ -214,6 +214,31 @@ void *lego_klt_alloc_pinned(size_t bytes);
 void lego_klt_free_pinned(void *p);
 
 /*
+ * ---- Feature detection -------------------------------------------------------------------
+ * Frontend::DetectFeatures (src/frontend_g2o.cpp:279-297): cv::GFTTDetector::create(num_features, 0.01, 20) (:16) on the
+ * left image, under a mask that is 0 in the rectangle pt +- (10, 10) around every feature the frame already has
+ * (:280-284).  OpenCV's goodFeaturesToTrack (third party: Shi-Tomasi minimum eigenvalue of the 3x3 structure tensor of
+ * Sobel derivatives, threshold at quality_level * max, 3x3 non-maximum suppression, greedy minimum-distance selection in
+ * score order) restated on the device; pinned against Python cv2 to a stated tolerance (tests/test_gftt.py).
+ *   mask (may be NULL)        rows x cols bytes, mask_step per row: candidates only where != 0      (cv::Mat mask)
+ *   exclude_xy (may be NULL)  n_exclude x {x, y}: the mask is additionally cleared in pt +- exclude_half around each, both
+ *                             corners inclusive (cv::rectangle(mask, pt - (h,h), pt + (h,h), 0, CV_FILLED))
+ *   corners_xy                max_corners x {x, y} out, in OpenCV's order (by decreasing score); scores (may be NULL)
+ *   *n_corners                number of corners found (<= max_corners)
+ */
+int lego_klt_detect_features(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step, const uint8_t *mask,
+                             size_t mask_step, const float *exclude_xy, int n_exclude, float exclude_half, int max_corners,
+                             double quality_level, double min_distance, float *corners_xy, float *scores_or_null,
+                             int *n_corners);
+/* The same on an uploaded image handle (its level 0 where it lies in HBM): only the exclusion list goes up and the
+ * corners come back. */
+int lego_klt_image_detect_features(lego_klt_image *img, const float *exclude_xy, int n_exclude, float exclude_half,
+                                   int max_corners, double quality_level, double min_distance, float *corners_xy,
+                                   float *scores_or_null, int *n_corners);
+/* Test hook: the minimum-eigenvalue map (rows x cols floats) of the context's last detection. */
+int lego_klt_debug_read_eig(lego_klt_ctx *ctx, float *out, size_t capacity, int *cols, int *rows);
+
+/*
  * One process, several devices (SURVEY.md 8b "device list", 8e): the B pairs are cut into contiguous blocks, one per
  * entry of `devices` (block sizes differ by at most one; a device may be listed more than once), each block owned by
  * a context and a batch on its device.  lego_klt_multi_track runs lego_klt_track_batched on every block concurrently,

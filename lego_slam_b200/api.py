@@ -167,6 +167,42 @@ class Tracker:
                                                        C.byref(left)), "lego_klt_debug_read_level")
         return out[:rows * pitch.value].reshape(rows, pitch.value).copy(), left.value
 
+    def detect_features(self, img, max_corners: int, quality_level: float = 0.01, min_distance: float = 20.0, mask=None,
+                        exclude=None, exclude_half: float = 10.0):
+        """Frontend::DetectFeatures (src/frontend_g2o.cpp:279-297) = cv::goodFeaturesToTrack under a mask that is cleared
+        around the existing features.  `img`: a uint8 array or an uploaded Image handle.  Returns (corners (n,2) float32,
+        scores (n,) float32) in OpenCV's order."""
+        out = np.zeros((max(max_corners, 1), 2), np.float32)
+        sc = np.zeros(max(max_corners, 1), np.float32)
+        n = C.c_int(0)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, np.float32).reshape(-1, 2)
+        n_ex = 0 if ex is None else ex.shape[0]
+        if isinstance(img, Image):
+            if mask is not None:
+                raise ValueError("image handles take an exclusion list, not a mask")
+            _lib.check(self._lib.lego_klt_image_detect_features(img._h, None if not n_ex else ex.ctypes.data, n_ex, exclude_half,
+                                                                max_corners, quality_level, min_distance, out.ctypes.data,
+                                                                sc.ctypes.data, C.byref(n)), "lego_klt_image_detect_features")
+        else:
+            rows, cols, step = _img_args(img)
+            if mask is not None and (mask.dtype != np.uint8 or mask.shape != img.shape or mask.strides[1] != 1):
+                raise ValueError("mask must be a uint8 array of the image's shape")
+            _lib.check(self._lib.lego_klt_detect_features(self._h, img.ctypes.data, cols, rows, step,
+                                                          None if mask is None else mask.ctypes.data,
+                                                          0 if mask is None else mask.strides[0],
+                                                          None if not n_ex else ex.ctypes.data, n_ex, exclude_half, max_corners,
+                                                          quality_level, min_distance, out.ctypes.data, sc.ctypes.data, C.byref(n)),
+                       "lego_klt_detect_features")
+        return out[:n.value].copy(), sc[:n.value].copy()
+
+    def debug_read_eig(self, rows: int, cols: int):
+        out = np.zeros((rows, cols), np.float32)
+        c, r = C.c_int(0), C.c_int(0)
+        _lib.check(self._lib.lego_klt_debug_read_eig(self._h, out.ctypes.data, out.size, C.byref(c), C.byref(r)),
+                   "lego_klt_debug_read_eig")
+        assert (r.value, c.value) == (rows, cols)
+        return out
+
     def batch(self, batch: int, rows: int, cols: int, n_per_pair: int, levels: int = 4, step: int | None = None):
         return Batch(self, batch, rows, cols, n_per_pair, levels, step)
 

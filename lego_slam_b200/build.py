@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("LEGO_KLT_LIB") or os.path.join(HERE, "liblego_klt.so")  # override: tuning experiments only
 SOURCES = ["lego_klt_capi.cu", "pyramid_sm100.cu", "klt_solver_exact.cu", "klt_solver_warp.cu",
            "klt_solver_lane.cu", "klt_solver_lane_p8.cu", "klt_solver_lane_p11.cu", "klt_solver_lane_inv.cu",
-           "triangulate_sm100.cu"]
+           "triangulate_sm100.cu", "gftt_sm100.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
     # parity: the reference CPU build has no fused multiply-add; fused ops are

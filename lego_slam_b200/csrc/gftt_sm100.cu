@@ -1,0 +1,288 @@
+// gftt_sm100.cu -- feature detection of the reference's frontend on the device.
+//
+// Reference: Frontend::DetectFeatures, src/frontend_g2o.cpp:279-297, with gftt_ = cv::GFTTDetector::create(num_features,
+// 0.01, 20) (:16): a mask that is 0 in the rectangle pt +- (10, 10) around every existing left feature, then
+// cv::goodFeaturesToTrack(left_img, maxCorners, 0.01, 20, mask, blockSize 3, Shi-Tomasi).  OpenCV is third party; its
+// algorithm is restated (oracle/gftt_np.py lists the steps and pins them against Python cv2):
+//   gftt_eig_kernel        Sobel 3x3 (fp32, scale 1/3060, BORDER_REFLECT_101) -> products -> 3x3 box sums
+//                          (BORDER_REFLECT_101) -> min eigenvalue, fused; also the masked maximum (block reduce + atomicMax)
+//   gftt_candidates_kernel threshold at max * qualityLevel, 3x3 non-maximum suppression, mask -> 64-bit keys
+//                          (score bits << 32 | flat index), appended with one atomic per warp
+//   cub::DeviceRadixSort   keys descending = score descending, ties by higher address first (OpenCV's greaterThanPtr)
+//   gftt_select_kernel     the greedy minimum-distance selection, in candidate order, one CTA: every chunk of 1024
+//                          candidates is filtered in parallel against the corners accepted so far (a cell grid finer than
+//                          minDistance / sqrt 2: at most one corner per cell), the few survivors are taken in order.
+// Every fp32 operation is individually rounded and in the oracle's order (this library is built with -fmad=false), so the
+// eigenvalue map -- and with it the corner list -- equals the numpy oracle's bit for bit; against OpenCV itself the pin is
+// tolerance-aware (its box filter's summation order is not fixed by its published behaviour): tests/test_gftt.py.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "klt_kernels.h"
+
+namespace legoklt {
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+constexpr int kTW = 32, kTH = 8;   // output tile of gftt_eig_kernel; block = kTW x kTH threads
+
+// Monotone map float -> unsigned (for atomicMax on floats of either sign).
+__device__ __forceinline__ unsigned float_key(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_float(unsigned k) {
+    const unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+__global__ void __launch_bounds__(kTW *kTH)
+gftt_eig_kernel(const uint8_t *__restrict__ img, int cols, int rows, int pitch, const uint8_t *__restrict__ mask, int mask_pitch,
+                float *__restrict__ eig, unsigned *__restrict__ max_key) {
+    __shared__ float cxx[kTH + 2][kTW + 2], cxy[kTH + 2][kTW + 2], cyy[kTH + 2][kTW + 2];
+    __shared__ unsigned block_max;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTW + tx;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    if (tid == 0) block_max = 0u;
+    const float s = 1.0f / 3060.0f;
+    // products of the scaled Sobel derivatives at the tile and its one-pixel ring; positions outside the image take the
+    // value of their BORDER_REFLECT_101 mirror position (the box filter's border rule on the product images)
+    for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kTW * kTH) {
+        const int ly = i / (kTW + 2), lx = i - ly * (kTW + 2);
+        const int y = reflect101(y0 + ly - 1, rows), x = reflect101(x0 + lx - 1, cols);
+        const int xm = reflect101(x - 1, cols), xp = reflect101(x + 1, cols);
+        const uint8_t *r0 = img + (size_t)reflect101(y - 1, rows) * pitch, *r1 = img + (size_t)y * pitch,
+                      *r2 = img + (size_t)reflect101(y + 1, rows) * pitch;
+        const float a0 = (float)__ldg(r0 + xm), a1 = (float)__ldg(r0 + x), a2 = (float)__ldg(r0 + xp);
+        const float b0 = (float)__ldg(r1 + xm), b1 = (float)__ldg(r1 + x), b2 = (float)__ldg(r1 + xp);
+        const float c0 = (float)__ldg(r2 + xm), c1 = (float)__ldg(r2 + x), c2 = (float)__ldg(r2 + xp);
+        // Dx: row pass (p[x+1] - p[x-1]) * s, column pass [1 2 1];  Dy: row pass [1 2 1], column pass (below - above) * s
+        const float rx0 = __fmul_rn(__fadd_rn(a2, -a0), s), rx1 = __fmul_rn(__fadd_rn(b2, -b0), s), rx2 = __fmul_rn(__fadd_rn(c2, -c0), s);
+        const float dx = __fadd_rn(__fadd_rn(rx0, __fmul_rn(rx1, 2.f)), rx2);
+        const float sx0 = __fadd_rn(__fadd_rn(a0, __fmul_rn(a1, 2.f)), a2), sx2 = __fadd_rn(__fadd_rn(c0, __fmul_rn(c1, 2.f)), c2);
+        const float dy = __fmul_rn(__fadd_rn(sx2, -sx0), s);
+        cxx[ly][lx] = __fmul_rn(dx, dx);
+        cxy[ly][lx] = __fmul_rn(dx, dy);
+        cyy[ly][lx] = __fmul_rn(dy, dy);
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x < cols && y < rows) {
+        auto box = [&](const float(&c)[kTH + 2][kTW + 2]) {   // rows first, then the three row sums
+            float r[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r[j] = __fadd_rn(__fadd_rn(c[ty + j][tx], c[ty + j][tx + 1]), c[ty + j][tx + 2]);
+            return __fadd_rn(__fadd_rn(r[0], r[1]), r[2]);
+        };
+        const float a = __fmul_rn(box(cxx), 0.5f), b = box(cxy), c = __fmul_rn(box(cyy), 0.5f);
+        const float amc = __fadd_rn(a, -c);
+        const float e = __fadd_rn(__fadd_rn(a, c), -__fsqrt_rn(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
+        eig[(size_t)y * cols + x] = e;
+        if (!mask || mask[(size_t)y * mask_pitch + x]) atomicMax(&block_max, float_key(e));
+    }
+    __syncthreads();
+    if (tid == 0 && block_max) atomicMax(max_key, block_max);
+}
+
+// Mask of DetectFeatures (src/frontend_g2o.cpp:280-284): 255, then 0 in pt +- (h, h) for every listed point, both corners
+// inclusive; cv::Point2f -> cv::Point rounds half to even (cvRound).
+__global__ void gftt_exclusion_kernel(uint8_t *__restrict__ mask, int cols, int rows, const float2 *__restrict__ pts, int n, float half) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const float2 p = pts[i];
+    const int x1 = max(__float2int_rn(__fadd_rn(p.x, -half)), 0), y1 = max(__float2int_rn(__fadd_rn(p.y, -half)), 0);
+    const int x2 = min(__float2int_rn(__fadd_rn(p.x, half)), cols - 1), y2 = min(__float2int_rn(__fadd_rn(p.y, half)), rows - 1);
+    const int w = x2 - x1 + 1, h = y2 - y1 + 1;
+    if (w <= 0 || h <= 0) return;
+    for (int k = threadIdx.x; k < w * h; k += blockDim.x) mask[(size_t)(y1 + k / w) * cols + x1 + k % w] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+gftt_candidates_kernel(const float *__restrict__ eig, int cols, int rows, const uint8_t *__restrict__ mask, int mask_pitch,
+                       const unsigned *__restrict__ max_key, double quality, unsigned long long *__restrict__ keys,
+                       unsigned *__restrict__ count) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    // cv::threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO) on a CV_32F image compares with (float)thresh
+    const float thr = (float)((double)key_float(*max_key) * quality);
+    bool cand = false;
+    float v = 0.f;
+    if (x >= 1 && y >= 1 && x < cols - 1 && y < rows - 1) {
+        v = eig[(size_t)y * cols + x];
+        v = v > thr ? v : 0.f;
+        if (v != 0.f && (!mask || mask[(size_t)y * mask_pitch + x])) {
+            float m = v;   // 3x3 dilation of the thresholded map (all eight neighbours exist here)
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const float w = eig[(size_t)(y + dy) * cols + x + dx];
+                    m = fmaxf(m, w > thr ? w : 0.f);
+                }
+            cand = (v == m);
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+    if (ballot) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == __ffs(ballot) - 1) base = atomicAdd(count, (unsigned)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
+        if (cand)
+            keys[base + __popc(ballot & ((1u << lane) - 1u))] =
+                ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * cols + x);
+    }
+}
+
+// Greedy selection in candidate order.  cell_of[] (gw x gh ints, -1 = empty) holds the flat pixel index of the corner
+// accepted in a cell of side `cell` <= minDistance / sqrt 2, so a cell never holds two corners and every corner closer
+// than minDistance lies within `reach` cells.
+__global__ void __launch_bounds__(1024)
+gftt_select_kernel(const unsigned long long *__restrict__ keys, unsigned n, int cols, int max_corners, float min_dist, int cell,
+                   int reach, int gw, int gh, int *__restrict__ cell_of, float2 *__restrict__ corners, float *__restrict__ scores,
+                   int *__restrict__ n_out) {
+    __shared__ unsigned char alive[1024];
+    __shared__ int accepted;
+    const int tid = threadIdx.x;
+    if (tid == 0) accepted = 0;
+    const float md2 = min_dist * min_dist;
+    auto blocked = [&](int x, int y) {
+        const int cx = x / cell, cy = y / cell;
+        for (int gy = max(cy - reach, 0); gy <= min(cy + reach, gh - 1); ++gy)
+            for (int gx = max(cx - reach, 0); gx <= min(cx + reach, gw - 1); ++gx) {
+                const int q = cell_of[gy * gw + gx];
+                if (q >= 0) {
+                    const int dx = q % cols - x, dy = q / cols - y;
+                    if ((float)(dx * dx + dy * dy) < md2) return true;
+                }
+            }
+        return false;
+    };
+    __syncthreads();
+    for (unsigned base = 0; base < n; base += 1024) {
+        const unsigned i = base + tid;
+        int x = 0, y = 0;
+        bool live = false;
+        if (i < n) {
+            const unsigned idx = (unsigned)(keys[i] & 0xffffffffull);
+            x = idx % cols;
+            y = idx / cols;
+            live = min_dist < 1.f || !blocked(x, y);   // against the corners of earlier chunks
+        }
+        alive[tid] = live ? 1 : 0;
+        __syncthreads();
+        if (tid == 0) {   // the survivors, in order, against the corners accepted in this chunk as well
+            const unsigned m = min(1024u, n - base);
+            for (unsigned k = 0; k < m && accepted < max_corners; ++k) {
+                if (!alive[k]) continue;
+                const unsigned long long key = keys[base + k];
+                const unsigned idx = (unsigned)(key & 0xffffffffull);
+                const int px = idx % cols, py = idx / cols;
+                if (min_dist >= 1.f) {
+                    if (blocked(px, py)) continue;
+                    cell_of[(py / cell) * gw + px / cell] = (int)idx;
+                }
+                corners[accepted] = make_float2((float)px, (float)py);
+                if (scores) scores[accepted] = __uint_as_float((unsigned)(key >> 32));
+                ++accepted;
+            }
+        }
+        __syncthreads();
+        if (accepted >= max_corners) break;
+    }
+    if (tid == 0) *n_out = accepted;
+}
+
+}  // namespace
+
+size_t gftt_workspace_bytes(int cols, int rows, float min_distance) {
+    const size_t px = (size_t)cols * rows;
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortKeysDescending(nullptr, sort_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                             (int)px);
+    (void)min_distance;
+    return px * 4 /*eig*/ + px /*mask*/ + 2 * px * 8 /*keys, sorted keys*/ + px * 4 /*cell grid, worst case*/ + sort_tmp + 4096;
+}
+
+cudaError_t launch_gftt(const uint8_t *d_img, int cols, int rows, int pitch, const uint8_t *d_mask_in, const float2 *d_exclude,
+                        int n_exclude, float exclude_half, int max_corners, double quality, float min_distance, uint8_t *ws,
+                        size_t ws_bytes, float2 *d_corners, float *d_scores_or_null, int *d_n_out, int *h_n_candidates,
+                        cudaStream_t stream) {
+    const size_t px = (size_t)cols * rows;
+    if (ws_bytes < gftt_workspace_bytes(cols, rows, min_distance)) return cudaErrorInvalidValue;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    float *eig = reinterpret_cast<float *>(ws + off);
+    off += up(px * 4);
+    uint8_t *mask = ws + off;
+    off += up(px);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + off);
+    off += up(px * 8);
+    unsigned long long *sorted = reinterpret_cast<unsigned long long *>(ws + off);
+    off += up(px * 8);
+    int *cell_of = reinterpret_cast<int *>(ws + off);
+    off += up(px * 4);
+    unsigned *scalars = reinterpret_cast<unsigned *>(ws + off);   // [0] max key, [1] candidate count
+    off += 256;
+    uint8_t *sort_tmp = ws + off;
+    size_t sort_tmp_bytes = ws_bytes - off;
+
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(scalars, 0, 8, stream)) != cudaSuccess) return e;
+    const uint8_t *mask_used = nullptr;
+    if (d_mask_in || n_exclude > 0) {
+        if (d_mask_in) e = cudaMemcpyAsync(mask, d_mask_in, px, cudaMemcpyDeviceToDevice, stream);
+        else e = cudaMemsetAsync(mask, 255, px, stream);
+        if (e != cudaSuccess) return e;
+        if (n_exclude > 0) {
+            gftt_exclusion_kernel<<<n_exclude, 128, 0, stream>>>(mask, cols, rows, d_exclude, n_exclude, exclude_half);
+            note_launch();
+        }
+        mask_used = mask;
+    }
+    dim3 grid((cols + kTW - 1) / kTW, (rows + kTH - 1) / kTH);
+    gftt_eig_kernel<<<grid, dim3(kTW, kTH), 0, stream>>>(d_img, cols, rows, pitch, mask_used, cols, eig, scalars);
+    note_launch();
+    gftt_candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), 256, 0, stream>>>(eig, cols, rows, mask_used, cols, scalars,
+                                                                                      quality, keys, scalars + 1);
+    note_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    unsigned n_cand = 0;   // the sort needs the count on the host: one 4-byte read-back
+    if ((e = cudaMemcpyAsync(&n_cand, scalars + 1, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    if (h_n_candidates) *h_n_candidates = (int)n_cand;
+    if (n_cand > 0) {
+        e = cub::DeviceRadixSort::SortKeysDescending(sort_tmp, sort_tmp_bytes, keys, sorted, (int)n_cand, 0, 64, stream);
+        if (e != cudaSuccess) return e;
+        note_launch(3);   // (cub: histogram, scan, onesweep passes)
+    }
+    int cell = 1, reach = 0, gw = 1, gh = 1;
+    if (min_distance >= 1.f) {
+        cell = (int)floorf(min_distance / 1.41421356f);
+        if (cell < 1) cell = 1;
+        reach = (int)ceilf(min_distance / (float)cell);
+        gw = (cols + cell - 1) / cell;
+        gh = (rows + cell - 1) / cell;
+        if ((e = cudaMemsetAsync(cell_of, 0xff, (size_t)gw * gh * sizeof(int), stream)) != cudaSuccess) return e;
+    }
+    gftt_select_kernel<<<1, 1024, 0, stream>>>(sorted, n_cand, cols, max_corners, min_distance, cell, reach, gw, gh, cell_of,
+                                               d_corners, d_scores_or_null, d_n_out);
+    note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gftt_debug_eig(const uint8_t *ws, int cols, int rows, float *h_eig, cudaStream_t stream) {
+    cudaError_t e = cudaMemcpyAsync(h_eig, ws, (size_t)cols * rows * 4, cudaMemcpyDeviceToHost, stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
+}
+
+}  // namespace legoklt

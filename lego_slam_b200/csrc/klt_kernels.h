@@ -111,4 +111,17 @@ cudaError_t launch_triangulate_stereo(const double *poses34, const double *cam_l
                                       const float2 *d_kp_left, const float2 *d_kp_right, const uint8_t *d_valid, int n,
                                       double thr, double *d_pt_world, uint8_t *d_ok, cudaStream_t stream);
 
+// ---- feature detection (gftt_sm100.cu) -----------------------------------------------------
+// cv::goodFeaturesToTrack (Shi-Tomasi, blockSize 3) on a device image of `pitch` bytes per row.  d_mask_in (tight,
+// cols bytes per row) and / or an exclusion list (0 in pt +- half around each point) restrict the candidates.  `ws` is a
+// device workspace of gftt_workspace_bytes(); corners / scores / n_out are device outputs (corners in acceptance order).
+// Synchronises the stream once (the candidate count is needed on the host to size the sort).
+size_t gftt_workspace_bytes(int cols, int rows, float min_distance);
+cudaError_t launch_gftt(const uint8_t *d_img, int cols, int rows, int pitch, const uint8_t *d_mask_in, const float2 *d_exclude,
+                        int n_exclude, float exclude_half, int max_corners, double quality, float min_distance, uint8_t *ws,
+                        size_t ws_bytes, float2 *d_corners, float *d_scores_or_null, int *d_n_out, int *h_n_candidates,
+                        cudaStream_t stream);
+// Test hook: the eigenvalue map of the last launch_gftt on this workspace (rows x cols floats) to host memory.
+cudaError_t gftt_debug_eig(const uint8_t *ws, int cols, int rows, float *h_eig, cudaStream_t stream);
+
 }  // namespace legoklt

@@ -72,6 +72,9 @@ struct lego_klt_ctx {
     size_t pinned_bytes = 0;
     uint8_t *d_tri = nullptr;          // triangulation scratch (grow-only)
     size_t tri_bytes = 0;
+    uint8_t *d_gftt = nullptr;         // feature detection: workspace | image | mask | exclusion list | outputs (grow-only)
+    size_t gftt_bytes = 0;
+    int gftt_cols = 0, gftt_rows = 0;  // shape of the last detection (lego_klt_debug_read_eig)
     // image-upload staging: a ring of pinned slots, each guarded by an event, so that an upload does not have to
     // drain the stream before it may overwrite the staging memory (lego_klt_image_upload*)
     struct Stage {
@@ -164,6 +167,7 @@ void ctx_release_handle(lego_klt_ctx *ctx) {
 void ctx_teardown(lego_klt_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->d_tri) cudaFree(ctx->d_tri);
+    if (ctx->d_gftt) cudaFree(ctx->d_gftt);
     for (auto &sl : ctx->stage) {
         if (sl.p) cudaFreeHost(sl.p);
         if (sl.done) cudaEventDestroy(sl.done);
@@ -1356,6 +1360,136 @@ int lego_klt_batch_triangulate(lego_klt_batch *b, const lego_camera *left, const
     int rc = ensure_tri(ctx, up256(nt * 3 * sizeof(double)) + up256(nt));
     if (rc) return rc;
     return tri_stereo_device(ctx, left, right, b->d_kp1, b->d_kp2_out, b->d_success, (int)nt, sing_ratio_thr, 0, pt_world, ok);
+}
+
+// ---- feature detection -------------------------------------------------------------------
+namespace {
+
+struct GfttArgs {
+    const uint8_t *mask;
+    size_t mask_step;
+    const float *exclude_xy;
+    int n_exclude;
+    float exclude_half;
+    int max_corners;
+    double quality;
+    double min_distance;
+};
+
+int gftt_check(const GfttArgs &g, const float *corners, const int *n_corners) {
+    if (!corners || !n_corners) return fail(LEGO_KLT_ERR_BAD_ARG, "output pointer is null");
+    if (g.max_corners <= 0) return fail(LEGO_KLT_ERR_BAD_ARG, "max_corners must be positive");
+    if (!(g.quality > 0.0) || !(g.min_distance >= 0.0)) return fail(LEGO_KLT_ERR_BAD_ARG, "bad quality level / minimum distance");
+    if (g.n_exclude < 0 || (g.n_exclude > 0 && !g.exclude_xy)) return fail(LEGO_KLT_ERR_BAD_ARG, "bad exclusion list");
+    return LEGO_KLT_OK;
+}
+
+// d_img: device image (pitch bytes per row).  If d_img is null the image is uploaded from `host_img` (host_step).
+int gftt_run(lego_klt_ctx *ctx, const uint8_t *d_img, int pitch, const uint8_t *host_img, size_t host_step, int cols, int rows,
+             const GfttArgs &g, float *corners_xy, float *scores, int *n_corners) {
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t px = (size_t)cols * rows;
+    const size_t ws = align_up(gftt_workspace_bytes(cols, rows, (float)g.min_distance), 256);
+    const size_t img_b = d_img ? 0 : align_up((size_t)rows * host_step, 256), mask_b = g.mask ? align_up(px, 256) : 0;
+    const size_t ex_b = align_up((size_t)g.n_exclude * sizeof(float2) + 8, 256);
+    const size_t out_b = align_up((size_t)g.max_corners * (sizeof(float2) + sizeof(float)) + 64, 256);
+    const size_t need = ws + img_b + mask_b + ex_b + out_b;
+    if (need > ctx->gftt_bytes) {
+        CU_TRY(cudaStreamSynchronize(st));
+        if (ctx->d_gftt) cudaFree(ctx->d_gftt);
+        ctx->d_gftt = nullptr;
+        ctx->gftt_bytes = 0;
+        CU_TRY(cudaMalloc(&ctx->d_gftt, need));
+        ctx->gftt_bytes = need;
+    }
+    uint8_t *p = ctx->d_gftt + ws;
+    uint8_t *d_up = p;
+    p += img_b;
+    uint8_t *d_mask = g.mask ? p : nullptr;
+    p += mask_b;
+    float2 *d_ex = reinterpret_cast<float2 *>(p);
+    p += ex_b;
+    float2 *d_corners = reinterpret_cast<float2 *>(p);
+    float *d_scores = reinterpret_cast<float *>(d_corners + g.max_corners);
+    int *d_n = reinterpret_cast<int *>(d_scores + g.max_corners);
+    // host inputs go through one pinned staging slot (caller memory is usually pageable)
+    const size_t stage_b = img_b + mask_b + ex_b;
+    if (stage_b > ex_b || g.n_exclude > 0) {
+        lego_klt_ctx::Stage *sl = nullptr;
+        int rc = acquire_stage(ctx, stage_b, &sl);
+        if (rc) return rc;
+        uint8_t *h = sl->p;
+        if (!d_img) {
+            const size_t valid = (size_t)(rows - 1) * host_step + (size_t)cols;   // what a cv::Mat guarantees
+            memcpy(h, host_img, valid);
+            CU_TRY(cudaMemcpyAsync(d_up, h, valid, cudaMemcpyHostToDevice, st));
+            h += img_b;
+        }
+        if (g.mask) {
+            for (int r = 0; r < rows; ++r) memcpy(h + (size_t)r * cols, g.mask + (size_t)r * g.mask_step, (size_t)cols);
+            CU_TRY(cudaMemcpyAsync(d_mask, h, px, cudaMemcpyHostToDevice, st));
+            h += mask_b;
+        }
+        if (g.n_exclude > 0) {
+            memcpy(h, g.exclude_xy, (size_t)g.n_exclude * sizeof(float2));
+            CU_TRY(cudaMemcpyAsync(d_ex, h, (size_t)g.n_exclude * sizeof(float2), cudaMemcpyHostToDevice, st));
+        }
+        rc = release_stage(ctx, sl);
+        if (rc) return rc;
+    }
+    NvtxRange range("lego_klt detect features");
+    CU_TRY(launch_gftt(d_img ? d_img : d_up, cols, rows, d_img ? pitch : (int)host_step, d_mask, d_ex, g.n_exclude,
+                       g.exclude_half, g.max_corners, g.quality, (float)g.min_distance, ctx->d_gftt, ws, d_corners, d_scores, d_n,
+                       nullptr, st));
+    ctx->gftt_cols = cols;
+    ctx->gftt_rows = rows;
+    int n = 0;
+    CU_TRY(cudaMemcpyAsync(&n, d_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (n > 0) {
+        CU_TRY(cudaMemcpyAsync(corners_xy, d_corners, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, st));
+        if (scores) CU_TRY(cudaMemcpyAsync(scores, d_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    *n_corners = n;
+    return LEGO_KLT_OK;
+}
+
+}  // namespace
+
+int lego_klt_detect_features(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step, const uint8_t *mask,
+                             size_t mask_step, const float *exclude_xy, int n_exclude, float exclude_half, int max_corners,
+                             double quality_level, double min_distance, float *corners_xy, float *scores, int *n_corners) {
+    if (!ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "ctx is null");
+    if (!img || cols < 3 || rows < 3 || step < (size_t)cols) return fail(LEGO_KLT_ERR_BAD_ARG, "bad image arguments");
+    if (mask && mask_step < (size_t)cols) return fail(LEGO_KLT_ERR_BAD_ARG, "bad mask step");
+    const GfttArgs g{mask, mask_step, exclude_xy, n_exclude, exclude_half, max_corners, quality_level, min_distance};
+    int rc = gftt_check(g, corners_xy, n_corners);
+    if (rc) return rc;
+    return gftt_run(ctx, nullptr, 0, img, step, cols, rows, g, corners_xy, scores, n_corners);
+}
+
+int lego_klt_image_detect_features(lego_klt_image *im, const float *exclude_xy, int n_exclude, float exclude_half, int max_corners,
+                                   double quality_level, double min_distance, float *corners_xy, float *scores, int *n_corners) {
+    if (!im) return fail(LEGO_KLT_ERR_BAD_ARG, "image is null");
+    if (!im->valid) return fail(LEGO_KLT_ERR_STATE, "lego_klt_image_detect_features before lego_klt_image_upload");
+    if (im->cols < 3 || im->rows < 3) return fail(LEGO_KLT_ERR_BAD_ARG, "image too small");
+    const GfttArgs g{nullptr, 0, exclude_xy, n_exclude, exclude_half, max_corners, quality_level, min_distance};
+    int rc = gftt_check(g, corners_xy, n_corners);
+    if (rc) return rc;
+    const LevelView &lv = im->view.lv[0];
+    return gftt_run(im->ctx, lv.base[0], lv.pitch, nullptr, 0, im->cols, im->rows, g, corners_xy, scores, n_corners);
+}
+
+int lego_klt_debug_read_eig(lego_klt_ctx *ctx, float *out, size_t capacity, int *cols, int *rows) {
+    if (!ctx || !ctx->d_gftt || ctx->gftt_cols <= 0) return fail(LEGO_KLT_ERR_STATE, "lego_klt_debug_read_eig before a detection");
+    if (!out || capacity < (size_t)ctx->gftt_cols * ctx->gftt_rows) return fail(LEGO_KLT_ERR_BAD_ARG, "output buffer too small");
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(gftt_debug_eig(ctx->d_gftt, ctx->gftt_cols, ctx->gftt_rows, out, ctx->stream));
+    if (cols) *cols = ctx->gftt_cols;
+    if (rows) *rows = ctx->gftt_rows;
+    return LEGO_KLT_OK;
 }
 
 // ---- one process, several devices (SURVEY.md 8b "device list", 8e) --------------------------------------------
