@@ -796,6 +796,30 @@ def single_call_record(trk, args):
             rec["cpu_baseline_forward"] = {"ms_per_call": dt * 1e3, "tracks_per_s": nf / dt, "cores": 1, "kind": arm.kind,
                                            "sample": f"{reps} calls; the reference's parallel_for_ run as one stripe"}
         out[name] = rec
+    # the step before tracking on the device as well: Frontend::DetectFeatures (src/frontend_g2o.cpp:279-297)
+    L, R, kp1, kp2, _ = synth.stereo_case(ROWS, COLS, 150, seed=1)
+    h = trk.image(ROWS, COLS, LEVELS).upload(L)
+    det = {"workload": f"cv::goodFeaturesToTrack(150, 0.01, 20) on one {COLS}x{ROWS} image, 40 existing features masked out"}
+    existing = kp1[:40]
+    for name, fn in (("host_image", lambda: trk.detect_features(L, 150, 0.01, 20.0, exclude=existing)),
+                     ("image_handle", lambda: trk.detect_features(h, 150, 0.01, 20.0, exclude=existing))):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            pts, _ = fn()
+        det[name] = {"ms_per_call": (time.perf_counter() - t0) / 20 * 1e3, "corners": int(len(pts))}
+    try:
+        import cv2
+        from oracle import gftt_np
+        mask = gftt_np.exclusion_mask(ROWS, COLS, existing, 10.0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cv2.goodFeaturesToTrack(L, 150, 0.01, 20.0, mask=mask)
+        det["cpu_cv2"] = {"ms_per_call": (time.perf_counter() - t0) / 5 * 1e3, "threads": cv2.getNumThreads()}
+    except Exception:  # noqa: BLE001
+        pass
+    out["detect_features"] = det
     return out
 
 
