@@ -702,7 +702,10 @@ int lego_klt_sync(lego_klt_ctx *ctx) {
 
 void *lego_klt_alloc_pinned(size_t bytes) {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    // LEGO_KLT_PINNED_WC=1 (experiment): write-combined pinned memory -- faster for the device to read on some hosts,
+    // very slow for the CPU to read back
+    static const bool wc = getenv("LEGO_KLT_PINNED_WC") && atoi(getenv("LEGO_KLT_PINNED_WC")) != 0;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
