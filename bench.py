@@ -854,6 +854,18 @@ def sequence_mode(trk, n_feat, args):
             trk.track_images(cur_h, right_h, kps, kps, params, want_stats=False)  # Frontend::FindFeaturesInRight...4LayerSelf
             prev_h, cur_h = cur_h, prev_h
 
+    def run_fused(count):
+        # the whole frame in ONE call: temporal track + device-chained stereo match of the kept features
+        nonlocal prev_h, cur_h
+        for i in range(count):
+            P, Cur, kt = frames[i % len(frames)]
+            if i == 0:
+                prev_h.upload(P)
+            cur_h.upload(Cur)
+            right_h.upload(R)
+            trk.track_frame(prev_h, cur_h, right_h, kt, kt, params)
+            prev_h, cur_h = cur_h, prev_h
+
     def run_pairwise(count):
         for i in range(count):
             P, Cur, kt = frames[i % len(frames)]
@@ -861,7 +873,7 @@ def sequence_mode(trk, n_feat, args):
             trk.track(L, R, kps, kps, params)
 
     res = {"workload": f"C2: sequence, per frame temporal + stereo track of {n_feat} features, {COLS}x{ROWS}, {LEVELS} levels"}
-    for name, fn in (("handles", run_handles), ("pairwise", run_pairwise)):
+    for name, fn in (("handles", run_handles), ("fused_frame_call", run_fused), ("pairwise", run_pairwise)):
         fn(5)
         trk.sync()
         t0 = time.perf_counter()

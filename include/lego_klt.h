@@ -171,6 +171,23 @@ int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, cons
                           lego_klt_stats *stats_or_null);
 
 /*
+ * One frame of Frontend::Track in one call (SURVEY.md 8f N1 "temporal + stereo tracking of a frame as one submission"):
+ * the temporal track last left -> current left (src/frontend_g2o.cpp:247-256, 453-492) and, chained on the device, the
+ * stereo match current left -> current right (:299-308, 495-535) of the features the temporal track kept -- the tracked
+ * positions are the stereo source points and its initial guesses (:508) without leaving HBM; one keypoint upload, one
+ * synchronisation, both result groups in one read-back.  Equal, byte for byte, to lego_klt_track_images(prev, cur)
+ * followed by lego_klt_track_images(cur, right) on the kept features.
+ *   kp_cur_xy       : in: initial guesses of the temporal track, out: tracked positions      success_temporal : n bytes
+ *   kp_right_xy     : out: matched positions in the right image (a slot whose temporal track failed: its tracked
+ *                     position, success_stereo = 0, no counters)                              success_stereo   : n bytes
+ * The three handles must have been uploaded (lego_klt_image_upload is asynchronous on the same stream).
+ */
+int lego_klt_track_frame(lego_klt_ctx *ctx, const lego_klt_params *params, const lego_klt_image *prev_left,
+                         const lego_klt_image *cur_left, const lego_klt_image *cur_right, const float *kp_prev_xy,
+                         float *kp_cur_xy, uint8_t *success_temporal, float *kp_right_xy, uint8_t *success_stereo, int n,
+                         lego_klt_stats *stats_temporal_or_null, lego_klt_stats *stats_stereo_or_null);
+
+/*
  * Batched path (north star (3)): B independent image pairs of one shape, n features per pair.
  * Host buffers should come from lego_klt_alloc_pinned for asynchronous copies.
  *   imgs1, imgs2 : B images, image b at  base + b * rows * step

@@ -226,6 +226,28 @@ class Tracker:
         return out, succ[:n], st
 
 
+def _track_frame(self, prev_left, cur_left, cur_right, kp_prev, kp_cur_guess, params=None, want_stats=False):
+    """lego_klt_track_frame: temporal track prev_left -> cur_left, then (chained on the device) the stereo match
+    cur_left -> cur_right of the kept features.  Returns (kp_cur, success_temporal, kp_right, success_stereo[, stats_t,
+    stats_s])."""
+    params = params or make_params(prev_left.levels)
+    kp1 = np.ascontiguousarray(kp_prev, np.float32).reshape(-1, 2)
+    cur = np.ascontiguousarray(kp_cur_guess, np.float32).reshape(-1, 2).copy()
+    n = kp1.shape[0]
+    right = np.zeros((max(n, 1), 2), np.float32)
+    st_, ss_ = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.uint8)
+    a, b = (Stats(), Stats()) if want_stats else (None, None)
+    _lib.check(self._lib.lego_klt_track_frame(self._h, C.byref(params), prev_left._h, cur_left._h, cur_right._h, kp1.ctypes.data,
+                                              cur.ctypes.data, st_.ctypes.data, right.ctypes.data, ss_.ctypes.data, n,
+                                              C.byref(a) if want_stats else None, C.byref(b) if want_stats else None),
+               "lego_klt_track_frame")
+    res = (cur, st_[:n], right[:n], ss_[:n])
+    return res + (a, b) if want_stats else res
+
+
+Tracker.track_frame = _track_frame
+
+
 class Image:
     """lego_klt_image: one uploaded image and its cached pyramid."""
 

@@ -80,6 +80,8 @@ struct SolverArgs {
     int n_per_pair;           // feature slots per pair (the batch's stride); image = id / n_per_pair
     const int *pair_count;    // [B] valid features of each pair (<= n_per_pair), or null = all: a slot at or beyond its
                               // pair's count is not tracked (kp2_out = kp2_init, success = 0, no counters)
+    const uint8_t *slot_valid;  // [B*n] or null: a slot whose byte is 0 is not tracked either (same outputs) -- the fused
+                              // frame call chains the stereo match on the features the temporal track kept
     int n_total;              // features in this launch: global ids f0 .. f0 + n_total - 1
     int f0;                   // first global feature id (chunked batches); image = id / n_per_pair
     int patch_lo, patch_hi;
@@ -188,6 +190,7 @@ __device__ __forceinline__ bool not_finite(double v) { return isnan(v) || isinf(
 
 // Ragged batches: is feature slot f (of image img) beyond its pair's feature count?
 __device__ __forceinline__ bool slot_unused(const SolverArgs &args, int f, int img) {
+    if (args.slot_valid != nullptr && args.slot_valid[f] == 0) return true;   // (written by an earlier kernel: no __ldg)
     return args.pair_count != nullptr && (f - img * args.n_per_pair) >= __ldg(args.pair_count + img);
 }
 

@@ -68,6 +68,7 @@ struct lego_klt_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     lego_klt_batch *single = nullptr;  // cached B=1 batch behind lego_klt_track / build_pyramid
+    lego_klt_batch *single_b = nullptr;  // second one: the stereo half of lego_klt_track_frame
     uint8_t *pinned = nullptr;         // staging for the single-pair path
     size_t pinned_bytes = 0;
     uint8_t *d_tri = nullptr;          // triangulation scratch (grow-only)
@@ -120,6 +121,7 @@ struct lego_klt_batch {
     int *d_fam_list = nullptr;     // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
     size_t templates_bytes = 0;
+    const uint8_t *d_slot_valid = nullptr;  // per-slot mask in force (lego_klt_track_frame), not owned
     int *d_pair_count = nullptr;   // ragged batches: valid features per pair (lego_klt_batch_set_feature_counts)
     std::vector<int> h_pair_count;
     bool ragged = false;
@@ -365,6 +367,7 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.stats = b->d_stats;
     a.n_per_pair = b->n_active > 0 ? b->n_active : 1;
     a.pair_count = b->ragged ? b->d_pair_count : nullptr;
+    a.slot_valid = b->d_slot_valid;
     a.n_total = nimg * b->n_active;
     a.f0 = img0 * b->n_active;
     a.patch_lo = params->patch_lo;
@@ -604,14 +607,14 @@ int single_download(lego_klt_ctx *ctx, lego_klt_batch *b, float *kp2_xy, uint8_t
 }
 
 // (Re)creates the cached single-pair batch when the shape changes or more features are needed.
-int ensure_single(lego_klt_ctx *ctx, int cols, int rows, size_t step, int n, int levels) {
-    lego_klt_batch *s = ctx->single;
+int ensure_single(lego_klt_ctx *ctx, int cols, int rows, size_t step, int n, int levels, lego_klt_batch **slot = nullptr) {
+    lego_klt_batch *&s = slot ? *slot : ctx->single;
     if (s && s->cols == cols && s->rows == rows && s->step == step && s->levels == levels && s->n_cap >= n)
         return LEGO_KLT_OK;
     if (s) lego_klt_batch_destroy(s);
-    ctx->single = nullptr;
+    s = nullptr;
     int cap = n < 256 ? 256 : (int)align_up((size_t)n, 256);
-    return batch_alloc(ctx, 1, cols, rows, step, cap, levels, &ctx->single);
+    return batch_alloc(ctx, 1, cols, rows, step, cap, levels, &s);
 }
 
 }  // namespace
@@ -678,6 +681,10 @@ void lego_klt_destroy(lego_klt_ctx *ctx) {
     if (ctx->single) {
         lego_klt_batch_destroy(ctx->single);
         ctx->single = nullptr;
+    }
+    if (ctx->single_b) {
+        lego_klt_batch_destroy(ctx->single_b);
+        ctx->single_b = nullptr;
     }
     if (ctx->live_handles > 0) {  // batches / images of the caller still point here: the last one tears down
         ctx->destroy_requested = true;
@@ -1219,6 +1226,94 @@ int lego_klt_track_images(lego_klt_ctx *ctx, const lego_klt_params *params, cons
     b->ran = true;
     b->last_chunked = false;
     return single_download(ctx, b, kp2_xy, success, n, stats);
+}
+
+int lego_klt_track_frame(lego_klt_ctx *ctx, const lego_klt_params *params, const lego_klt_image *prev_left,
+                         const lego_klt_image *cur_left, const lego_klt_image *cur_right, const float *kp_prev_xy,
+                         float *kp_cur_xy, uint8_t *success_temporal, float *kp_right_xy, uint8_t *success_stereo, int n,
+                         lego_klt_stats *stats_temporal, lego_klt_stats *stats_stereo) {
+    if (!ctx || !params || !prev_left || !cur_left || !cur_right) return fail(LEGO_KLT_ERR_BAD_ARG, "null argument");
+    const lego_klt_image *ims[3] = {prev_left, cur_left, cur_right};
+    for (const lego_klt_image *im : ims) {
+        if (im->ctx != ctx) return fail(LEGO_KLT_ERR_BAD_ARG, "image belongs to another context");
+        if (!im->valid) return fail(LEGO_KLT_ERR_STATE, "lego_klt_track_frame before lego_klt_image_upload");
+        if (im->cols != prev_left->cols || im->rows != prev_left->rows || im->step != prev_left->step ||
+            im->levels != prev_left->levels)
+            return fail(LEGO_KLT_ERR_BAD_ARG, "the three images must have the same shape, step and levels");
+    }
+    if (params->levels != prev_left->levels)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "params->levels (%d) != cached pyramid levels (%d)", params->levels, prev_left->levels);
+    if (n < 0 || (n > 0 && (!kp_prev_xy || !kp_cur_xy || !success_temporal || !kp_right_xy || !success_stereo)))
+        return fail(LEGO_KLT_ERR_BAD_ARG, "bad keypoint arguments");
+    int rc = ensure_single(ctx, prev_left->cols, prev_left->rows, prev_left->step, n, params->levels);
+    if (rc == LEGO_KLT_OK) rc = ensure_single(ctx, prev_left->cols, prev_left->rows, prev_left->step, n, params->levels, &ctx->single_b);
+    if (rc) return rc;
+    lego_klt_batch *bt = ctx->single, *bs = ctx->single_b;
+    rc = validate_params(params, bt->levels);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(cudaSetDevice(ctx->device));
+    NvtxRange range("lego_klt frame: temporal + stereo");
+    // temporal track: last left -> current left (Frontend::TrackLastFrame, src/frontend_g2o.cpp:247-256, 453-492)
+    rc = single_upload_keypoints(ctx, bt, kp_prev_xy, kp_cur_xy, n);
+    if (rc) return rc;
+    PyramidView vt = prev_left->view;
+    for (int l = 0; l < vt.levels; ++l) vt.lv[l].base[1] = cur_left->view.lv[l].base[0];
+    CU_TRY(cudaMemsetAsync(bt->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    bt->d_slot_valid = nullptr;
+    rc = run_range(bt, params, 0, 1, 0, nullptr, &vt, cur_left->maps);
+    if (rc) return rc;
+    // stereo match of the features the temporal track kept (Frontend::FindFeaturesInRight, :299-308, 495-535: the
+    // current frame's left features are the tracked ones; initial guess = the same pixel, :508): chained on the device,
+    // the tracked positions never leave HBM between the two solves
+    bs->n_active = n;
+    bs->d_kp2_init = bs->d_kp1 + n;
+    bs->d_success = reinterpret_cast<uint8_t *>(bs->d_kp2_out + n);
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(bs->d_kp1, bt->d_kp2_out, (size_t)n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        CU_TRY(cudaMemcpyAsync(bs->d_kp2_init, bt->d_kp2_out, (size_t)n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    }
+    PyramidView vs = cur_left->view;
+    for (int l = 0; l < vs.levels; ++l) vs.lv[l].base[1] = cur_right->view.lv[l].base[0];
+    CU_TRY(cudaMemsetAsync(bs->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    lego_klt_params ps = *params;
+    ps.has_initial = 1;
+    bs->d_slot_valid = bt->d_success;
+    rc = run_range(bs, &ps, 0, 1, 0, nullptr, &vs, cur_right->maps);
+    bs->d_slot_valid = nullptr;
+    if (rc) return rc;
+    ++bt->runs;
+    ++bs->runs;
+    bt->ran = bs->ran = true;
+    bt->last_chunked = bs->last_chunked = false;
+    bt->last_timed = bs->last_timed = false;
+    // both result groups come home behind ONE synchronisation
+    const size_t kp_bytes = (size_t)n * sizeof(float2), grp = kIoHeadBytes + kp_bytes + (size_t)n;
+    const size_t need = 2 * align_up(grp, 256) + 64;
+    if (ctx->pinned_bytes < need) {
+        CU_TRY(cudaStreamSynchronize(st));
+        rc = ensure_pinned(ctx, need);
+        if (rc) return rc;
+    }
+    uint8_t *h_t = ctx->pinned, *h_s = ctx->pinned + align_up(grp, 256);
+    CU_TRY(cudaMemcpyAsync(h_t, bt->d_io + bt->io_out_off, grp, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_s, bs->d_io + bs->io_out_off, grp, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (n) {
+        memcpy(kp_cur_xy, h_t + kIoHeadBytes, kp_bytes);
+        memcpy(success_temporal, h_t + kIoHeadBytes + kp_bytes, (size_t)n);
+        memcpy(kp_right_xy, h_s + kIoHeadBytes, kp_bytes);
+        memcpy(success_stereo, h_s + kIoHeadBytes + kp_bytes, (size_t)n);
+    }
+    if (stats_temporal) {
+        memcpy(bt->h_stats, h_t, kStatCount * sizeof(unsigned long long));
+        fill_stats(bt, stats_temporal);
+    }
+    if (stats_stereo) {
+        memcpy(bs->h_stats, h_s, kStatCount * sizeof(unsigned long long));
+        fill_stats(bs, stats_stereo);
+    }
+    return LEGO_KLT_OK;
 }
 
 int lego_klt_build_pyramid(lego_klt_ctx *ctx, const uint8_t *img, int cols, int rows, size_t step, int levels,

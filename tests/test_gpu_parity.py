@@ -545,3 +545,52 @@ def test_kernel_launch_counter_counts_this_librarys_launches(tracker):
     tracker.track(L, R, kp1, kp2, klt.make_params(levels=3, kernel=klt.KERNEL_EXACT))
     # 2 ingest + level 0->1 + band kernel + exact solver
     assert klt.kernel_launches() - before == 5
+
+
+def test_pipeline_chunk_count_does_not_change_the_bytes(tracker):
+    """lego_klt_track_batched with 1 / 3 / 16 chunks of H2D - compute - D2H overlap, integer and sub-pixel keypoints (the
+    family instance runs on the side stream and is joined per chunk): identical results."""
+    B, rows, cols, n = 33, 188, 620, 1000
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 7000)
+    rng = np.random.default_rng(5)
+    for jitter in (False, True):
+        k1 = kp1.copy()
+        if jitter:
+            k1 += rng.uniform(-0.5, 0.5, k1.shape).astype(np.float32)
+        k1p = klt.pinned_empty(k1.shape, np.float32)
+        np.copyto(k1p, k1)
+        ref = None
+        for chunks in (1, 3, 16, 0):
+            batch = tracker.batch(B, rows, cols, n, levels=4)
+            batch.set_pipeline_chunks(chunks)
+            io = klt.pinned_empty((B, n, 2), np.float32)
+            np.copyto(io, k1)
+            succ = klt.pinned_empty((B, n), np.uint8)
+            st = batch.track(imgs1, imgs2, k1p, io, succ, klt.make_params())
+            cur = (io.copy(), succ.copy(), list(st.gn_iters), int(st.n_success))
+            if ref is None:
+                ref = cur
+            else:
+                assert np.array_equal(cur[0].view(np.uint32), ref[0].view(np.uint32)) and np.array_equal(cur[1], ref[1])
+                assert cur[2] == ref[2] and cur[3] == ref[3]
+            batch.close()
+
+
+@pytest.mark.parametrize("n", [150, 2000, 6000])
+def test_fused_frame_call_equals_two_calls(tracker, oracle, n):
+    """lego_klt_track_frame (temporal track + device-chained stereo match of the kept features, one synchronisation)
+    against lego_klt_track_images twice, and against the oracle run the same way; n = 6000 takes the LANE kernel."""
+    P, Cur, kt, _, _ = synth.temporal_case(376, 1241, n, seed=2, frame=1)
+    _, Rt, _ = synth.stereo_pair(376, 1241, 2)
+    kt[:3] = [[1.0, 1.0], [1239.5, 374.5], [-3.0, 10.0]]       # some that fail / leave the image
+    hp, hc, hr = (tracker.image(376, 1241, 4).upload(x) for x in (P, Cur, Rt))
+    cur, st_, right, ss_, a, b = tracker.track_frame(hp, hc, hr, kt, kt, want_stats=True)
+    cur2, st2, _ = tracker.track_images(hp, hc, kt, kt)
+    assert np.array_equal(cur.view(np.uint32), cur2.view(np.uint32)) and np.array_equal(st_, st2)
+    keep = st2.astype(bool)
+    r2, s2, stat2 = tracker.track_images(hc, hr, cur2[keep], cur2[keep])
+    assert np.array_equal(right[keep].view(np.uint32), r2.view(np.uint32)) and np.array_equal(ss_[keep], s2)
+    assert not ss_[~keep].any() and np.array_equal(right[~keep].view(np.uint32), cur[~keep].view(np.uint32))
+    assert int(b.n_success) == int(s2.sum()) and list(b.gn_iters) == list(stat2.gn_iters)
+    ref_c, ref_s, _ = oracle.track(P, Cur, kt, kt, threads=8)
+    assert np.array_equal(ref_s, st_) and np.abs(ref_c - cur).max() <= 1e-3
