@@ -750,7 +750,7 @@ def run_ours(args):
                               "roofline_solver_frac": solver_roofline(sweep_iters[(cnt, pname)], sweep_B * cnt * LEVELS, pw, False, msol)["frac"],
                               "roofline_pyramid_frac": pyramid_roofline(2 * sweep_B, PYR_BYTES_PER_IMAGE, mpyr)["frac"]})
         line["sweep_c5"] = {"what": "BASELINE config C5: 64 pairs 1241x376 per GPU, device-resident, one batch in flight; "
-                                    "AUTO kernel selection (LANE above 4096 features per launch)", "points": sweep}
+                                    "AUTO kernel selection (LANE above 3000 features per launch)", "points": sweep}
         c4 = {"what": f"BASELINE config C4: {c4_B} pairs {c4_cols}x{c4_rows} per GPU x {c4_n} features, {c4_L} levels, "
                       "device-resident; inverse = the reference's inverse mode with its stale Jacobian (SURVEY.md F4)"}
         c4_pyr_bytes = 2_762_040   # SURVEY.md 8d, 1920x1080, 5 levels

@@ -1,8 +1,9 @@
 // klt_solver_lane.cu -- LEGO_KLT_KERNEL_LANE: one THREAD per feature, persistent per-thread state
-// machine, all pyramid levels fused (sm_100a).  Forward mode (the reference's call sites pass inverse = false:
-// src/frontend_g2o.cpp:473,515); the patch bounds are compile-time and this source is compiled once per patch:
-// here 7x7 = -3..3 (src/algorithm.cpp:40 half_patch_size = 3), in klt_solver_lane_p8.cu 8x8 = -4..3, in
-// klt_solver_lane_p11.cu 11x11 = -5..5.  The numbers quoted below are those of the 7x7 instance.
+// machine, all pyramid levels fused (sm_100a).  The patch bounds and the mode are compile-time and this source is
+// compiled once per configuration: here forward mode (the reference's call sites pass inverse = false:
+// src/frontend_g2o.cpp:473,515), 7x7 = -3..3 (src/algorithm.cpp:40 half_patch_size = 3); in klt_solver_lane_p8.cu 8x8
+// = -4..3, in klt_solver_lane_p11.cu 11x11 = -5..5, in klt_solver_lane_inv.cu the reference's inverse mode (7x7; see
+// LANE_INVERSE below).  The numbers quoted below are those of the forward 7x7 instance.
 //
 // Replaces LKOpticalFlow1Layer + LKOpticalFlowTracker::calcLKOpticalFlow (src/algorithm.cpp:11-125)
 // and the coarse-to-fine loop of LKOpticalFlow4Layer (:158-205).  Two kernels:
@@ -20,11 +21,16 @@
 // is removed by a state machine: each trip of the main loop is exactly one pass for every runnable
 // thread; a thread that converges moves to its next level / next feature while its neighbours keep
 // iterating.  Level set-up (template fetch + img2 window staging) is a per-thread, divergent section run
-// whenever at least LANE_BATCH threads of the warp need it (measured best: 1 with three CTAs per SM; 10 with two).
+// whenever at least LANE_BATCH threads of the warp need it (measured best: 1).
 //
 // Shared memory, per thread, in 16-byte granules  [granule][T]:  img2 window 12 rows x 32 bytes (16-byte aligned
-// origin; the border semantics come from the row aprons), template 7 rows x 8 floats, 18 row weights -- 688 bytes
-// per thread, three CTAs of 96 threads per SM.  A level set-up is 38 16-byte cp.async copies from global memory.
+// origin; the border semantics come from the row aprons) and the template, 7 rows x 8 floats -- 608 bytes per thread
+// (the row factors of a pass are formed inside its row loop, not parked in shared memory), five CTAs of 64 threads per
+// SM.  A level set-up is 38 16-byte cp.async copies from global memory.
+//
+// What bounds it (profiles/README.md, round 2): throughput, not latency -- issue slots are 57 % active whatever the
+// occupancy, most of its instruction kinds cost ~2 issue cycles per sub-partition on this part, so time follows the
+// instruction count: ~2,200 per warp-pass, of which ~1,240 the row loop.
 //
 // Bit-fidelity contract (same as the warp kernel): every fp32 value entering the sums is bit-identical
 // to the reference's; only the ORDER of the fp64 additions differs (row-major here, x-outer there; all
@@ -34,7 +40,8 @@
 //       normally e_c = 0 for all c and a pass is one trip; near a power of two the patch splits into two
 //       families per axis, each with its own grid, and the pass takes one trip per family combination with
 //       the other pixels masked out (sub-pixel source keypoints, i.e. tracked points fed back by the
-//       reference's TrackLastFrame, hit this on ~1-6 % of their levels);
+//       reference's TrackLastFrame, hit this on ~10 % of their passes; such features are listed by the template
+//       kernel and tracked by the FAM = true instance of the kernel);
 //   (b) the double coordinate is not within 16 ulp64 of an fp32 rounding midpoint (checked per pass,
 //       per grid column/row), so the <=2 ulp64 differences between the reference's three ways of
 //       forming a coordinate cannot change the rounded float -- or it is EXACTLY on a midpoint and all

@@ -57,7 +57,8 @@ constexpr int kRing = 64;  // per-run kernel timing ring (lego_klt_batch_timings
 constexpr size_t kIoStatsBytes = 256;                       // device counters (kStatCount x 8 bytes, padded)
 constexpr size_t kIoHeadBytes = kIoStatsBytes + 256;        // + work counters (4 x kMaxChunks ints)
 static_assert(kStatCount * sizeof(unsigned long long) <= kIoStatsBytes && 4 * 16 * sizeof(int) <= 256, "io head layout");
-constexpr int kAutoLaneMinFeatures = 4096;  // LEGO_KLT_KERNEL_AUTO: LANE above, WARP up to this many features per call
+constexpr int kAutoLaneMinFeatures = 3000;  // LEGO_KLT_KERNEL_AUTO: LANE above, WARP up to this many features per call
+                                            // (measured per call, solver only: 2000 features 0.19 / 0.20 ms WARP / LANE, 5000: 0.24 / 0.21)
 constexpr int kMaxChunks = 16;  // chunks of the overlapped end-to-end path (lego_klt_track_batched)
 
 }  // namespace
@@ -404,9 +405,10 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     a.feat_flag = nullptr;
     a.epoch = 0;
     int kernel = params->kernel;
-    // AUTO: the thread-per-feature LANE kernel needs tens of thousands of features to fill the machine (57k resident
-    // threads); below ~4k features of one call the warp-per-feature kernel has the lower latency (measured, 1241x376:
-    // n = 2000: 0.24 vs 0.31 ms per call, n = 5000: equal, n = 20000: 0.70 vs 0.42 ms).  Same fidelity contract.
+    // AUTO: the thread-per-feature LANE kernel needs tens of thousands of features to fill the machine (47k resident
+    // threads); below ~3k features of one call the warp-per-feature kernel has the lower latency (measured, 1241x376,
+    // tools/seq_latency.py: n = 150: 0.13 vs 0.21 ms per call, 2000: 0.19 vs 0.20, 5000: 0.24 vs 0.21, 20000: 0.56 vs
+    // 0.26).  Same fidelity contract.
     // the LANE solver is compiled for three patches (klt_solver_lane*.cu): 0 = none, else the patch width
     // (-7: the reference's inverse mode, 7x7)
     const int lane_patch = lane_kernel_supports(a)       ? 7

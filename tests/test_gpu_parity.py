@@ -468,7 +468,7 @@ def test_two_rank_sharded_gpu_result_equals_single_gpu_bytes(tracker, tmp_path):
     byte-for-byte what ONE context computes for the whole batch."""
     import socket
     import torch.multiprocessing as mp
-    B, rows, cols, n = 5, 188, 620, 1500     # uneven shards (3 + 2); > 4096 features per rank: the LANE kernel
+    B, rows, cols, n = 5, 188, 620, 1500     # uneven shards (3 + 2); the LANE kernel, explicitly
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
