@@ -330,7 +330,7 @@ struct L01Params {
 // together (the first version, one row per warp, was load-latency bound: DRAM 47 % of peak, issue slots 55 % active,
 // 3 trips per warp) and the CTA count drops by the same factor.
 #ifndef PYR_L01_ROWS
-#define PYR_L01_ROWS 2
+#define PYR_L01_ROWS 4
 #endif
 constexpr int kL01Rows = PYR_L01_ROWS;
 constexpr int kL01RowsPerCta = 8 * kL01Rows;
@@ -350,85 +350,77 @@ pyramid_l01_kernel(const __grid_constant__ PyramidView pyr, const __grid_constan
     const int R0 = kL01RowsPerCta * blockIdx.x + kL01Rows * warp;
     if (R0 < l1.rows) {
     const int dcols = l1.cols, nchunks = (dcols + 7) >> 3, src_last = scols - 1;
-    // per-row constants; rows past the end of the level repeat the last row (computed, not stored)
-    const uint8_t *s0[kL01Rows], *s1[kL01Rows];
-    int b0[kL01Rows], b1[kL01Rows];
+    const int nrows = min(kL01Rows, l1.rows - R0);
+    // The warp's work items are (row, chunk) pairs, row-major, a lane takes every 32nd: 78 chunks x 4 rows fill 10 trips
+    // to 97 % (a lane per chunk column and a trip per row filled 81 %).  The chunk's coefficient loads hit L1.
+    const int n_items = nrows * nchunks;
+    for (int item = lane; item < n_items; item += 32) {
+        int k = 0;
 #pragma unroll
-    for (int k = 0; k < kL01Rows; ++k) {
-        const int R = min(R0 + k, l1.rows - 1);
+        for (int q = 1; q < kL01Rows; ++q) k += (item >= q * nchunks) ? 1 : 0;
+        const int i = item - k * nchunks, R = R0 + k;
         const int yo = __ldg(p.yofs + R);
         const short2 b = __ldg(p.ycoef + R);
-        s0[k] = src + (size_t)d_clip(yo, srows) * spitch;
-        s1[k] = src + (size_t)d_clip(yo + 1, srows) * spitch;
-        b0[k] = b.x;
-        b1[k] = b.y;
-    }
-    uint8_t *drow0 = dst + (size_t)R0 * l1.pitch;
-    const int nrows = min(kL01Rows, l1.rows - R0);
-
-    for (int i = lane; i < nchunks; i += 32) {
+        const uint8_t *s0 = src + (size_t)d_clip(yo, srows) * spitch;
+        const uint8_t *s1 = src + (size_t)d_clip(yo + 1, srows) * spitch;
         // chunk i = 16 source bytes per source row + the word after them (for delta = 1)
-        uint4 a[kL01Rows], c[kL01Rows];
-        uint32_t na[kL01Rows], nc[kL01Rows];
-#pragma unroll
-        for (int k = 0; k < kL01Rows; ++k) {
-            a[k] = __ldg(reinterpret_cast<const uint4 *>(s0[k]) + i);
-            c[k] = __ldg(reinterpret_cast<const uint4 *>(s1[k]) + i);
-            na[k] = __ldg(reinterpret_cast<const uint32_t *>(s0[k]) + 4 * i + 4);  // (the row's allocation extends 48 bytes
-            nc[k] = __ldg(reinterpret_cast<const uint32_t *>(s1[k]) + 4 * i + 4);  //  past the last pixel)
-        }
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(s0) + i);
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(s1) + i);
+        const uint32_t na = __ldg(reinterpret_cast<const uint32_t *>(s0) + 4 * i + 4);  // (the row's allocation extends 48 bytes
+        const uint32_t nc = __ldg(reinterpret_cast<const uint32_t *>(s1) + 4 * i + 4);  //  past the last pixel)
         const int info = __ldg(p.cofs + i);
         if (info >= 0) {
             const int sh = (info - 16 * i) * 8;  // 0 or 8 (host-checked)
-            uint4 cf0 = make_uint4(0, 0, 0, 0), cf1 = cf0;
-            if (!X2Y2) {
-                cf0 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i);
-                cf1 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i + 1);
-            }
-            const uint32_t cf[8] = {cf0.x, cf0.y, cf0.z, cf0.w, cf1.x, cf1.y, cf1.z, cf1.w};
+            uint2 out;
+            const uint32_t w0[4] = {__funnelshift_r(a.x, a.y, sh), __funnelshift_r(a.y, a.z, sh), __funnelshift_r(a.z, a.w, sh),
+                                    __funnelshift_r(a.w, na, sh)};
+            const uint32_t w1[4] = {__funnelshift_r(c.x, c.y, sh), __funnelshift_r(c.y, c.z, sh), __funnelshift_r(c.z, c.w, sh),
+                                    __funnelshift_r(c.w, nc, sh)};
+            if (X2Y2) {
+                uint32_t t[4];
 #pragma unroll
-            for (int k = 0; k < kL01Rows; ++k) {
-                uint2 out;
-                const uint32_t w0[4] = {__funnelshift_r(a[k].x, a[k].y, sh), __funnelshift_r(a[k].y, a[k].z, sh),
-                                        __funnelshift_r(a[k].z, a[k].w, sh), __funnelshift_r(a[k].w, na[k], sh)};
-                const uint32_t w1[4] = {__funnelshift_r(c[k].x, c[k].y, sh), __funnelshift_r(c[k].y, c[k].z, sh),
-                                        __funnelshift_r(c[k].z, c[k].w, sh), __funnelshift_r(c[k].w, nc[k], sh)};
-                if (X2Y2) {
-                    uint32_t t[4];
+                for (int q = 0; q < 4; ++q)
+                    t[q] = (__byte_perm(w0[q], 0u, 0x4240) + __byte_perm(w0[q], 0u, 0x4341) + __byte_perm(w1[q], 0u, 0x4240) +
+                            __byte_perm(w1[q], 0u, 0x4341) + 0x00020002u) >> 2;
+                out.x = __byte_perm(t[0], t[1], 0x6420);
+                out.y = __byte_perm(t[2], t[3], 0x6420);
+            } else {
+                const uint4 cf0 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i);
+                const uint4 cf1 = __ldg(reinterpret_cast<const uint4 *>(p.xcoef) + 2 * i + 1);
+                const uint32_t cf[8] = {cf0.x, cf0.y, cf0.z, cf0.w, cf1.x, cf1.y, cf1.z, cf1.w};
+                uint32_t v[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        t[q] = (__byte_perm(w0[q], 0u, 0x4240) + __byte_perm(w0[q], 0u, 0x4341) + __byte_perm(w1[q], 0u, 0x4240) +
-                                __byte_perm(w1[q], 0u, 0x4341) + 0x00020002u) >> 2;
-                    out.x = __byte_perm(t[0], t[1], 0x6420);
-                    out.y = __byte_perm(t[2], t[3], 0x6420);
-                } else {
-                    uint32_t v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int h0 = (j & 1) ? dot2_hi(cf[j], w0[j >> 1]) : dot2_lo(cf[j], w0[j >> 1]);
-                        const int h1 = (j & 1) ? dot2_hi(cf[j], w1[j >> 1]) : dot2_lo(cf[j], w1[j >> 1]);
-                        v[j] = vertical<Y2>(h0, h1, b0[k], b1[k]);
-                    }
-                    out.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
-                    out.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+                for (int j = 0; j < 8; ++j) {
+                    const int h0 = (j & 1) ? dot2_hi(cf[j], w0[j >> 1]) : dot2_lo(cf[j], w0[j >> 1]);
+                    const int h1 = (j & 1) ? dot2_hi(cf[j], w1[j >> 1]) : dot2_lo(cf[j], w1[j >> 1]);
+                    v[j] = vertical<Y2>(h0, h1, b.x, b.y);
                 }
-                if (k < nrows) reinterpret_cast<uint2 *>(drow0 + (size_t)k * l1.pitch)[i] = out;
+                out.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+                out.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
             }
+            reinterpret_cast<uint2 *>(dst + (size_t)R * l1.pitch)[i] = out;
         }
     }
-    // The irregular chunks (where the tap offset steps, and the partial chunk at the row end): one pixel per lane.
-    for (int q = lane; q < 8 * p.n_irr; q += 32) {
+    // The irregular chunks (where the tap offset steps, and the partial chunk at the row end): one pixel per lane, the
+    // rows of the warp flattened the same way.
+    const int n_irr_px = 8 * p.n_irr;
+    for (int item = lane; item < nrows * n_irr_px; item += 32) {
+        int k = 0;
+#pragma unroll
+        for (int q = 1; q < kL01Rows; ++q) k += (item >= q * n_irr_px) ? 1 : 0;
+        const int q = item - k * n_irr_px, R = R0 + k;
         const int col = 8 * __ldg(p.irr + (q >> 3)) + (q & 7);
         if (col < dcols) {
+            const int yo = __ldg(p.yofs + R);
+            const short2 b = __ldg(p.ycoef + R);
+            const uint8_t *s0 = src + (size_t)d_clip(yo, srows) * spitch;
+            const uint8_t *s1 = src + (size_t)d_clip(yo + 1, srows) * spitch;
             const int sx = __ldg(p.xofs + col);
             const int sx1 = min(sx + 1, src_last);
             const short2 cf = __ldg(p.xcoef + col);
-#pragma unroll
-            for (int k = 0; k < kL01Rows; ++k) {
-                const int h0 = (int)s0[k][sx] * cf.x + (int)s0[k][sx1] * cf.y;
-                const int h1 = (int)s1[k][sx] * cf.x + (int)s1[k][sx1] * cf.y;
-                if (k < nrows) drow0[(size_t)k * l1.pitch + col] = (uint8_t)vertical<false>(h0, h1, b0[k], b1[k]);
-            }
+            const int h0 = (int)s0[sx] * cf.x + (int)s0[sx1] * cf.y;
+            const int h1 = (int)s1[sx] * cf.x + (int)s1[sx1] * cf.y;
+            dst[(size_t)R * l1.pitch + col] = (uint8_t)vertical<false>(h0, h1, b.x, b.y);
         }
     }
     }
