@@ -220,6 +220,13 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params,
                            const uint8_t *imgs1, const uint8_t *imgs2,
                            const float *kp1_xy, float *kp2_xy, uint8_t *success,
                            lego_klt_stats *stats_or_null);
+/* The same in two halves (SURVEY.md 8b "batched API may be async with explicit wait"): _begin enqueues the copies and
+ * kernels of the call and returns; _end waits for them (results are in the caller's buffers afterwards).  With two batch
+ * objects (on two contexts) a caller keeps the copy engine busy across calls: begin(A), begin(B), end(A), begin(A) ...
+ * The buffers passed to _begin must stay valid and untouched until _end. */
+int lego_klt_track_batched_begin(lego_klt_batch *b, const lego_klt_params *params, const uint8_t *imgs1,
+                                 const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success);
+int lego_klt_track_batched_end(lego_klt_batch *b, lego_klt_stats *stats_or_null);
 /* lego_klt_track_batched cuts large batches into `chunks` groups of pairs whose H2D copy, kernels and D2H copy overlap
  * (1..16; 0 = the default: 6 for 32 pairs or more, 4 for 8..31, else one). */
 int lego_klt_batch_set_pipeline_chunks(lego_klt_batch *b, int chunks);

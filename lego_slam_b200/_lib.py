@@ -24,7 +24,7 @@ EXPORTS = [
     "lego_klt_kernel_launches", "lego_klt_batch_set_feature_counts", "lego_klt_batch_set_pipeline_chunks",
     "lego_klt_multi_create", "lego_klt_multi_destroy", "lego_klt_multi_shard", "lego_klt_multi_set_feature_counts",
     "lego_klt_multi_track", "lego_klt_detect_features", "lego_klt_image_detect_features", "lego_klt_debug_read_eig",
-    "lego_klt_track_frame",
+    "lego_klt_track_frame", "lego_klt_track_batched_begin", "lego_klt_track_batched_end",
 ]
 
 
@@ -119,6 +119,8 @@ def load():
                                              C.c_int, C.c_double, C.c_double, vp, vp, ip]
     lib.lego_klt_image_detect_features.argtypes = [vp, vp, C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, vp, vp, ip]
     lib.lego_klt_debug_read_eig.argtypes = [vp, vp, C.c_size_t, ip, ip]
+    lib.lego_klt_track_batched_begin.argtypes = [vp, pp, vp, vp, vp, vp, vp]
+    lib.lego_klt_track_batched_end.argtypes = [vp, sp]
     lib.lego_klt_track_frame.argtypes = [vp, pp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, sp, sp]
     _lib = lib
     return lib

@@ -352,6 +352,22 @@ class Batch:
         _lib.check(self._lib.lego_klt_batch_timings(self._h, last_n, C.byref(a), C.byref(b)), "lego_klt_batch_timings")
         return a.value, b.value
 
+    def track_begin(self, imgs1, imgs2, kp1, kp2_inout, success, params: Params | None = None):
+        """lego_klt_track_batched_begin: enqueue the whole call and return; the buffers belong to the call until track_end."""
+        self._check_inputs(imgs1, imgs2, kp1, kp2_inout)
+        params = params or make_params(self.levels)
+        self._pending = (imgs1, imgs2, kp1, kp2_inout, success, params)   # keep the buffers alive
+        _lib.check(self._lib.lego_klt_track_batched_begin(self._h, C.byref(params), imgs1.ctypes.data, imgs2.ctypes.data,
+                                                          kp1.ctypes.data, kp2_inout.ctypes.data, success.ctypes.data),
+                   "lego_klt_track_batched_begin")
+
+    def track_end(self):
+        """lego_klt_track_batched_end: wait for the call begun by track_begin; returns its Stats."""
+        st = Stats()
+        _lib.check(self._lib.lego_klt_track_batched_end(self._h, C.byref(st)), "lego_klt_track_batched_end")
+        self._pending = None
+        return st
+
     def track(self, imgs1, imgs2, kp1, kp2_inout, success, params: Params | None = None):
         """lego_klt_track_batched: H2D + pyramids + solver + D2H; kp2_inout is overwritten."""
         self._check_inputs(imgs1, imgs2, kp1, kp2_inout)

@@ -139,6 +139,7 @@ struct lego_klt_batch {
     cudaEvent_t ev_done[kMaxChunks] = {};
     cudaEvent_t ev_join_c[kMaxChunks] = {};  // side-stream work of chunk c (deferred features, FAMILIES instance) done
     bool uploaded = false, ran = false, pyramids_valid = false, last_chunked = false;
+    bool in_flight = false;        // lego_klt_track_batched_begin without its _end yet
     bool counted = false;          // created through lego_klt_batch_create (counts in ctx->live_handles)
     bool last_timed = false;       // the last run recorded a ring slot
     lego_klt_params last_params;
@@ -877,7 +878,25 @@ int lego_klt_batch_timings(lego_klt_batch *b, int last_n, float *ms_pyramid_avg,
 int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, const uint8_t *imgs1,
                            const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success,
                            lego_klt_stats *stats) {
+    int rc = lego_klt_track_batched_begin(b, params, imgs1, imgs2, kp1_xy, kp2_xy, success);
+    if (rc) return rc;
+    return lego_klt_track_batched_end(b, stats);
+}
+
+int lego_klt_track_batched_end(lego_klt_batch *b, lego_klt_stats *stats) {
     if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (!b->in_flight) return fail(LEGO_KLT_ERR_STATE, "lego_klt_track_batched_end without lego_klt_track_batched_begin");
+    b->in_flight = false;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    CU_TRY(cudaStreamSynchronize(b->ctx->stream));   // (the result copies are joined into the context stream)
+    if (stats) fill_stats(b, stats);
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_track_batched_begin(lego_klt_batch *b, const lego_klt_params *params, const uint8_t *imgs1,
+                                 const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (b->in_flight) return fail(LEGO_KLT_ERR_STATE, "lego_klt_track_batched_begin: the previous call has not been ended");
     // Small batches: plain upload -> run -> download.
     // Equal chunks: more / smaller chunks shorten the pipeline tail but cost launches and solver efficiency
     // (measured: 10 chunks with a fine tail 6 % slower than 8 equal ones; a smaller LAST chunk of 8 or 16 pairs 5 % slower).
@@ -895,7 +914,17 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
         if (rc) return rc;
         rc = lego_klt_batch_run(b, params);
         if (rc) return rc;
-        return lego_klt_batch_download(b, kp2_xy, success, stats);
+        const size_t nt1 = (size_t)b->B * (size_t)b->n_active;
+        if (nt1 && (!kp2_xy || !success)) return fail(LEGO_KLT_ERR_BAD_ARG, "output pointer is null");
+        cudaStream_t st1 = b->ctx->stream;
+        if (nt1) {
+            CU_TRY(cudaMemcpyAsync(kp2_xy, b->d_kp2_out, nt1 * sizeof(float2), cudaMemcpyDeviceToHost, st1));
+            CU_TRY(cudaMemcpyAsync(success, b->d_success, nt1, cudaMemcpyDeviceToHost, st1));
+        }
+        CU_TRY(cudaMemcpyAsync(b->h_stats, b->d_stats, kStatCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st1));
+        CU_TRY(cudaEventRecord(b->ev[EV_D2H], st1));
+        b->in_flight = true;
+        return LEGO_KLT_OK;
     }
     // Large batches: the batch is cut into chunks of pairs; the H2D copy of chunk c+1 (copy stream) overlaps
     // the kernels of chunk c (context stream).  PCIe is the end-to-end bound (933 KB per 1241x376 pair).
@@ -982,10 +1011,12 @@ int lego_klt_track_batched(lego_klt_batch *b, const lego_klt_params *params, con
     b->last_params = *params;
     ++b->runs;
     CU_TRY(cudaMemcpyAsync(b->h_stats, b->d_stats, kStatCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    // the result copies (d2h stream) are joined into the context stream: lego_klt_track_batched_end waits on one stream,
+    // and an event a caller records on it covers the whole call
+    CU_TRY(cudaEventRecord(b->ev_compute_done, b->d2h));
+    CU_TRY(cudaStreamWaitEvent(st, b->ev_compute_done, 0));
     CU_TRY(cudaEventRecord(b->ev[EV_D2H], st));
-    CU_TRY(cudaStreamSynchronize(st));
-    CU_TRY(cudaStreamSynchronize(b->d2h));
-    if (stats) fill_stats(b, stats);
+    b->in_flight = true;
     return LEGO_KLT_OK;
 }
 

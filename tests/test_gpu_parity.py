@@ -594,3 +594,29 @@ def test_fused_frame_call_equals_two_calls(tracker, oracle, n):
     assert int(b.n_success) == int(s2.sum()) and list(b.gn_iters) == list(stat2.gn_iters)
     ref_c, ref_s, _ = oracle.track(P, Cur, kt, kt, threads=8)
     assert np.array_equal(ref_s, st_) and np.abs(ref_c - cur).max() <= 1e-3
+
+
+def test_begin_end_halves_with_two_calls_in_flight_equal_the_synchronous_call(tracker):
+    """lego_klt_track_batched_begin / _end on two batch objects of two contexts, overlapping, against the one-call form."""
+    B, rows, cols, n = 40, 188, 620, 1200
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 8000)
+    ref = klt.pinned_empty((B, n, 2), np.float32)
+    np.copyto(ref, kp2)
+    ref_s = klt.pinned_empty((B, n), np.uint8)
+    one = tracker.batch(B, rows, cols, n, levels=4)
+    st0 = one.track(imgs1, imgs2, kp1, ref, ref_s, klt.make_params())
+    trk2 = klt.Tracker(0)
+    objs = [one, trk2.batch(B, rows, cols, n, levels=4)]
+    bufs = [(klt.pinned_empty((B, n, 2), np.float32), klt.pinned_empty((B, n), np.uint8)) for _ in range(2)]
+    for rounds in range(3):
+        for j in range(2):
+            np.copyto(bufs[j][0], kp2)
+            objs[j].track_begin(imgs1, imgs2, kp1, bufs[j][0], bufs[j][1], klt.make_params())
+        for j in range(2):
+            st = objs[j].track_end()
+            assert np.array_equal(bufs[j][0].view(np.uint32), ref.view(np.uint32)) and np.array_equal(bufs[j][1], ref_s)
+            assert list(st.gn_iters) == list(st0.gn_iters) and int(st.n_success) == int(st0.n_success)
+    with pytest.raises(Exception):
+        objs[0].track_end()          # nothing in flight
+    objs[1].close()
+    one.close()
