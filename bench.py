@@ -440,7 +440,7 @@ def run_ours(args):
     # ---------------- end to end: host buffers -> lego_klt_track_batched -> host buffers ----------------
     # kp2 is in/out (initial guess in, tracked position out): every timed step gets its own pre-filled pinned
     # buffer, so that no host-side refill of the guess sits inside the timed region.
-    n_ring = args.steps if args.steps <= 32 else 2
+    n_ring = max(2, args.steps) if args.steps <= 32 else 2
     kp2_ring = [kp2_io] + [klt.pinned_empty((B, n, 2), np.float32) for _ in range(n_ring - 1)]
     for _ in range(min(args.warmup, 3)):
         np.copyto(kp2_io, kp2)
@@ -473,30 +473,37 @@ def run_ours(args):
         np.copyto(buf, kp2)
     eb[1].track(imgs1, imgs2, kp1, kp2_ring[0], succ2[1], params)    # (warm-up of the second object)
     np.copyto(kp2_ring[0], kp2)
+    def e2e_pipelined(src_kp1, guess, steps):
+        """`steps` end-to-end calls, two in flight; device time between the first enqueue and the last result copy."""
+        ring = kp2_ring if steps <= len(kp2_ring) else kp2_ring[:2]
+        for buf in ring:
+            np.copyto(buf, guess)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(est[0])
+        est[1].wait_event(e0)
+        pending = [False, False]
+        for i in range(steps):
+            j = i % 2
+            if pending[j]:
+                eb[j].track_end()
+                if len(ring) < steps:
+                    np.copyto(ring[i % len(ring)], guess)
+            eb[j].track_begin(imgs1, imgs2, src_kp1, ring[i % len(ring)], succ2[j], params)
+            pending[j] = True
+        for j in range(2):
+            if pending[j]:
+                eb[j].track_end()
+        est[0].wait_stream(est[1])
+        e1.record(est[0])
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ring[(steps - 1) % len(ring)], succ2[(steps - 1) % 2]
+
     barrier()
-    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(est[0])
-    est[1].wait_event(e0)
-    pending = [False, False]
-    for i in range(args.steps):
-        j = i % 2
-        if pending[j]:
-            eb[j].track_end()
-            if n_ring < args.steps:
-                np.copyto(kp2_ring[i % n_ring], kp2)
-        eb[j].track_begin(imgs1, imgs2, kp1, kp2_ring[i % n_ring], succ2[j], params)
-        pending[j] = True
-    for j in range(2):
-        if pending[j]:
-            eb[j].track_end()
-    est[0].wait_stream(est[1])
-    e1.record(est[0])
-    torch.cuda.synchronize()
+    e2e_ms_local, last_kp, last_succ = e2e_pipelined(kp1, kp2, args.steps)
     e2e_wall_s = time.perf_counter() - t0
-    e2e_ms_local = e0.elapsed_time(e1)
-    pipe_kp, pipe_succ = kp2_ring[(args.steps - 1) % n_ring].copy(), succ2[(args.steps - 1) % 2].copy()
+    pipe_kp, pipe_succ = last_kp.copy(), last_succ.copy()
     barrier()
 
     # the same pinned buffers, copy only (H2D of both image sets and the keypoints + the re-pitch kernels), all ranks at
@@ -525,8 +532,6 @@ def run_ours(args):
     cam_r = klt.make_camera(718.856, 718.856, 607.1928, 185.2157, right34)
     tri_pt = klt.pinned_empty((B, n, 3), np.float64)
     tri_ok = klt.pinned_empty((B, n), np.uint8)
-    for b_ in batches[1:]:
-        b_.close()
     batch.upload(imgs1, imgs2, kp1, kp2)
     batch.run(params)
     batch.triangulate(cam_l, cam_r, 1e-3, tri_pt, tri_ok)
@@ -562,13 +567,10 @@ def run_ours(args):
         timed_runs(batch, params, key="subpixel_resident")
         _, _, st_s = batch.download(kp2_io, succ)
         sub_kp, sub_succ = kp2_io.copy(), succ.copy()
-        np.copyto(kp2_io, kp1s)
-        batch.track(imgs1, imgs2, kp1s, kp2_io, succ, params)
-        with Timer(torch, stream) as tmr:
-            for _ in range(3):
-                np.copyto(kp2_io, kp1s)
-                batch.track(imgs1, imgs2, kp1s, kp2_io, succ, params)
-        side_ms["subpixel_e2e"] = tmr.ms / 3
+        e2e_pipelined(kp1s, kp1s, 2)
+        side_ms["subpixel_e2e"] = e2e_pipelined(kp1s, kp1s, 6)[0] / 6
+        for b_ in eb[1:] + batches[1:]:     # (memory back before the sweep batches)
+            b_.close()
         # (c) C5: feature-count sweep x patch on 64 pairs, per-kernel times
         sweep_B = min(64, B)
         sweep_counts = [100, 500, 2000, 5000, 20000]
