@@ -102,11 +102,16 @@ constexpr unsigned kPMask2 = kPMask | (kPMask << kFamY);
 #ifndef LANE_QUEUE
 #define LANE_QUEUE 64          // (measured 32 / 64: 1.465 / 1.44 ms per 512,000 features)
 #endif
-// img2 window per thread: LANE_WROWS rows x 32 bytes, origin aligned to 16 bytes (two 16-byte copies per row).
-constexpr int kWin2Rows = LANE_WROWS, kWin2Words = LANE_WWORDS;
-constexpr int kWinAlign = (LANE_WWORDS == 8) ? 16 : 8;
-constexpr int kWinSlackL = (LANE_WWORDS == 8) ? 2 : 3;         // footprint starts kWinSlackL..kWinSlackL+kWinAlign-1 bytes in
-constexpr int kWinSlackT = (LANE_WROWS - (G + 1)) / 2;         // rows above the footprint
+#ifndef LANE_WUNIT
+#define LANE_WUNIT 4           // words per window copy unit: 16 / 8 / 4-byte cp.async copies, origin aligned to the unit
+#endif
+// img2 window per thread: LANE_WROWS rows x LANE_WWORDS words, origin aligned to one copy unit.
+constexpr int kWin2Rows = LANE_WROWS, kWin2Words = LANE_WWORDS, kWinUnit = LANE_WUNIT;
+static_assert((kWinUnit == 1 || kWinUnit == 2 || kWinUnit == 4) && kWin2Words % kWinUnit == 0, "window copy unit");
+constexpr int kWinAlign = 4 * kWinUnit;
+constexpr int kWinSlackL = (kWinUnit == 4) ? 2 : 3;             // footprint starts kWinSlackL..kWinSlackL+kWinAlign-1 bytes in
+constexpr int kWinSpare = LANE_WROWS - (G + 1);                // window rows beyond the footprint
+constexpr int kWinSlackT = kWinSpare / 2;                      // rows above the footprint (an odd spare row: see the stager)
 static_assert(kWin2Rows >= G + 1 && kWin2Words * 4 >= G + 1 + kWinSlackL + kWinAlign - 1,
               "the window must hold the footprint at every alignment (a footprint that never fits would re-stage forever)");
 constexpr int kTplRows = kInverse ? G + 1 : P + 1;            // img1 window rows in the template kernel
@@ -117,7 +122,6 @@ constexpr int kTplRows = kInverse ? G + 1 : P + 1;            // img1 window row
 // words are read one by one (4-way bank conflicts, affordable: the shared-memory pipe is far from saturated).
 constexpr int kTplPitch = (P + 3) / 4 * 4;                    // floats per template row, in the record and in shared memory
 constexpr int kI1Count = P * kTplPitch;                       // template floats, index y*kTplPitch + x
-static_assert(LANE_WWORDS == 8, "granule layout: 32-byte window rows");
 constexpr int kQueue = LANE_QUEUE;                            // feature ring entries per warp (power of two, >= 32)
 static_assert(kQueue >= 32 && (kQueue & (kQueue - 1)) == 0, "ring size");
 constexpr int kRecPlanes = kInverse ? 3 : 1;                  // record planes: I1 [, img1 x difference, img1 y difference]
@@ -149,10 +153,11 @@ enum : int { ST_FETCH = 0, ST_LEVEL = 1, ST_RUN = 2, ST_DONE = 3 };
 
 template <int T>
 struct LaneSmem {
-    // granules of one thread: window rows (2 each), template rows (kTplPitch / 4 each)
-    static constexpr int kGranTpl = 2 * kWin2Rows,   // (window granules first)
-                         kGranTotal = kGranTpl + kRecCount / 4;
-    uint4 g[kGranTotal][T];
+    // One thread's window: copy units of kWinUnit words, [unit][T] (kWin2Words / kWinUnit per row); its record: 16-byte
+    // granules, [granule][T] (kTplPitch / 4 per template row).
+    static constexpr int kUnitsPerRow = kWin2Words / kWinUnit, kWinUnits = kWin2Rows * kUnitsPerRow;
+    uint32_t win[kWinUnits][T][kWinUnit];
+    uint4 rec[kRecCount / 4][T];
     // per-warp ring of fetched features: one global atomic + coalesced keypoint loads per 32 features
     float2 q_k1[T / 32][kQueue], q_k2[T / 32][kQueue];
     int q_id[T / 32][kQueue];
@@ -161,6 +166,20 @@ struct LaneSmem {
     double parked[6][T];  // partial sums between the sub-passes of a two-family pass
 #endif
 };
+
+#ifndef LANE_ODD_MOV
+#define LANE_ODD_MOV 0
+#endif
+#ifndef LANE_WIDEN_ALU
+#define LANE_WIDEN_ALU 0       // experiment: how many of a pixel's three fp32 -> fp64 conversions avoid the XU pipe (F2F)
+#endif
+// fp32 -> fp64 by integer widening (exact; normal numbers on the ALU pipe, zero / denormal / inf / nan by the convert)
+__device__ __forceinline__ double widen_alu(float f) {
+    const uint32_t u = __float_as_uint(f);
+    if (((u << 1) - 0x01000000u) >= 0xfe000000u) return (double)f;
+    const int hi = (int)((((int)u >> 3) & 0x8fffffff) + 0x38000000);
+    return __hiloint2double(hi, (int)(u << 29));
+}
 
 __device__ __forceinline__ float byte_to_float(uint32_t packed, int k) {
     // place byte k in the low mantissa of 2^23 and subtract 2^23: exact, ALU + FADD, no XU convert
@@ -361,10 +380,17 @@ __device__ __forceinline__ void load_row10_packed(const WinRef &wr, int i, int s
 #pragma unroll
     for (int k = 0; k < kRowWords - 1; ++k) b[k] = __funnelshift_r(w[k], w[k + 1], sh);
 #pragma unroll
-    for (int j = 0; j < kNP; ++j) {
-        row.e[j] = bytes_to_float2(b[(2 * j) >> 2], (2 * j) & 3, b[(2 * j + 1) >> 2], (2 * j + 1) & 3);
-        row.o[j] = bytes_to_float2(b[(2 * j + 1) >> 2], (2 * j + 1) & 3, b[(2 * j + 2) >> 2], (2 * j + 2) & 3);
-    }
+    for (int j = 0; j < kNP; ++j) row.e[j] = bytes_to_float2(b[(2 * j) >> 2], (2 * j) & 3, b[(2 * j + 1) >> 2], (2 * j + 1) & 3);
+#if LANE_ODD_MOV
+    // experiment: the odd pairs (2j+1, 2j+2) re-use the even pairs' converted pixels (two moves instead of two PRMT + one
+    // packed add); the last one needs pixel 2 kNP, converted alone
+#pragma unroll
+    for (int j = 0; j + 1 < kNP; ++j) row.o[j] = make_float2(row.e[j].y, row.e[j + 1].x);
+    row.o[kNP - 1] = make_float2(row.e[kNP - 1].y, byte_to_float(b[(2 * kNP) >> 2], (2 * kNP) & 3));
+#else
+#pragma unroll
+    for (int j = 0; j < kNP; ++j) row.o[j] = bytes_to_float2(b[(2 * j + 1) >> 2], (2 * j + 1) & 3, b[(2 * j + 2) >> 2], (2 * j + 2) & 3);
+#endif
 }
 
 // Samples g = 2j, 2j+1 of one grid row (algorithm.h:51-56 per sample, products and sums individually rounded).
@@ -839,13 +865,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                     const int ixn = __double2int_rd(Sx + (double)(LO - 1)), iyn = __double2int_rd(Sy + (double)(LO - 1));
                     wx0 = (ixn - kWinSlackL) & ~(kWinAlign - 1);
                     wy0 = iyn - kWinSlackT;
+                    if ((kWinSpare & 1) && Sy + (double)(LO - 1) - (double)iyn < 0.5) --wy0;  // odd spare row: on the nearer side
                     no_window = !window_in_apron(lv, wx0);
                 }
                 // Everything the level needs goes global -> shared memory by 16-byte cp.async copies (template record,
                 // two per window row), in flight together; they land while the grid coordinates of the pass are
                 // computed and are waited for just before the pass.
                 const uint8_t *img2 = lv.base[1] + (size_t)img * lv.slot;
-                uint4 *gp = &sm.g[0][tid];
                 if (new_level) {
                     const char *tp = reinterpret_cast<const char *>(args.templates + ((size_t)level * args.tpl_features + (size_t)feat) * kTplStride);
                     if (level > 0) {  // the next level's template will be needed a few trips from now
@@ -853,19 +879,28 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128));
                     }
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(gp + LaneSmem<T>::kGranTpl * T);
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.rec[0][tid]);
 #pragma unroll
                     for (int j = 0; j < kRecCount / 4; ++j)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j * T * 16), "l"(tp + 16 * j) : "memory");
                 }
                 if (!no_window) {
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(gp);
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.win[0][tid][0]);
+                    constexpr int kUnitBytes = 4 * kWinUnit, kUPR = LaneSmem<T>::kUnitsPerRow;
 #pragma unroll
                     for (int i = 0; i < kWin2Rows; ++i) {
                         const int ry = min(max(wy0 + i, 0), lv.rows - 1);
                         const uint8_t *rp = img2 + (ptrdiff_t)ry * lv.pitch + wx0;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * i) * T * 16), "l"(rp) : "memory");
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * i + 1) * T * 16), "l"(rp + 16) : "memory");
+#pragma unroll
+                        for (int j = 0; j < kUPR; ++j) {
+                            const uint32_t d = dst + (i * kUPR + j) * T * kUnitBytes;
+                            if (kWinUnit == 4)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(rp + 16 * j) : "memory");
+                            else if (kWinUnit == 2)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(rp + 8 * j) : "memory");
+                            else
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(rp + 4 * j) : "memory");
+                        }
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -930,7 +965,7 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
         const bool any_masked = FAM && __any_sync(FULL, run && fast && masked);
         if (run) {
             const LevelView &lv = pyr.lv[level];
-            const float *i1p = reinterpret_cast<const float *>(&sm.g[LaneSmem<T>::kGranTpl][tid]);
+            const float *i1p = reinterpret_cast<const float *>(&sm.rec[0][tid]);
             constexpr int kI1Stride = T * 4;   // floats between consecutive granules of one thread
             double sb0 = 0, sb1 = 0, sc = 0, s00 = 0, s01 = 0, s11 = 0;
             bool solve_now = true;
@@ -938,12 +973,13 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
             const int ox = ixn + kG0 - wx0;   // (inverse mode samples grid indices 1..P only)
             const int sh = (ox & 3) * 8;
             WinRef wr;
-            {   // word kw + k of a row: granule (kw + k) >> 2 of the row, position (kw + k) & 3 inside it
+            {   // word kw + k of a row: copy unit (kw + k) / kWinUnit of the row, position (kw + k) % kWinUnit inside it
                 const int kw = ox >> 2;
-                wr.base = reinterpret_cast<const uint32_t *>(&sm.g[2 * (iyn + kG0 - wy0)][tid]);
-                wr.row_stride = 2 * T * 4;
+                constexpr int kUPR = LaneSmem<T>::kUnitsPerRow;
+                wr.base = &sm.win[kUPR * (iyn + kG0 - wy0)][tid][0];
+                wr.row_stride = kUPR * T * kWinUnit;
 #pragma unroll
-                for (int k = 0; k < kRowWords; ++k) wr.off[k] = ((kw + k) >> 2) * (T * 4) + ((kw + k) & 3);
+                for (int k = 0; k < kRowWords; ++k) wr.off[k] = ((kw + k) / kWinUnit) * (T * kWinUnit) + ((kw + k) % kWinUnit);
             }
             // Row factors of grid row r, formed when the row is sampled: n_r = (double)(LO - 1 + r) and
             // fg_r = (float)(origin + r) are carried through the loop (both exact).
@@ -1043,7 +1079,9 @@ klt_lane_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant__
                         gxf = __uint_as_float(__float_as_uint(gxf) & col_word[x] & row_word);
                         gyf = __uint_as_float(__float_as_uint(gyf) & col_word[x] & row_word);
                     }
-                    const double e = (double)ef, gx = (double)gxf, gy = (double)gyf;
+                    const double e = (LANE_WIDEN_ALU >= 1) ? widen_alu(ef) : (double)ef,
+                                 gx = (LANE_WIDEN_ALU >= 2) ? widen_alu(gxf) : (double)gxf,
+                                 gy = (LANE_WIDEN_ALU >= 3) ? widen_alu(gyf) : (double)gyf;
                     sb0 = fma(e, gx, sb0);
                     sb1 = fma(e, gy, sb1);
                     sc = fma(e, e, sc);

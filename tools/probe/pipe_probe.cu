@@ -17,7 +17,7 @@ __global__ void probe(float *out, float seed, unsigned long long *cycles) {
     asm volatile("mov.b64 %0, {%1, %2};" : "=l"(p3) : "f"(a6), "f"(a7));
     p4 = p0; p5 = p1; p6 = p2; p7 = p3;
     asm volatile("mov.b64 %0, {%1, %1};" : "=l"(w) : "f"(0.999f));
-    double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, e0, e1, e2;
+    double d0 = a0, d1 = a1, d2 = a2, d3 = a3, d4 = a4, d5 = a5, e0 = a6, e1 = a7, e2 = a3;
     unsigned u0 = threadIdx.x, u1 = u0 * 3, u2 = u0 * 5, u3 = u0 * 7;
     __syncthreads();
     unsigned long long t0 = clock64();
@@ -84,6 +84,29 @@ __global__ void probe(float *out, float seed, unsigned long long *cycles) {
             asm volatile("mul.rn.f32x2 %0, %0, %8; add.rn.f32x2 %1, %1, %8; mul.rn.f32x2 %2, %2, %8; add.rn.f32x2 %3, %3, %8;"
                          "mul.rn.f32x2 %4, %4, %8; add.rn.f32x2 %5, %5, %8; mul.rn.f32x2 %6, %6, %8; add.rn.f32x2 %7, %7, %8;"
                          : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(w));
+        } else if (MIX == 14) {  // the per-pixel block WITHOUT its conversions: 3 add.f32 + 6 fma.f64 (what does an F2F cost?)
+            asm volatile("add.rn.f32 %6, %6, %9; add.rn.f32 %7, %7, %9; add.rn.f32 %8, %8, %9;"
+                         "fma.rn.f64 %0, %10, %11, %0; fma.rn.f64 %1, %10, %12, %1; fma.rn.f64 %2, %10, %10, %2;"
+                         "fma.rn.f64 %3, %11, %11, %3; fma.rn.f64 %4, %11, %12, %4; fma.rn.f64 %5, %12, %12, %5;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+f"(a0), "+f"(a1), "+f"(a2) : "f"(seed), "d"(e0), "d"(e1), "d"(e2));
+        } else if (MIX == 15) {  // 3 add.f32 + 3 cvt.f64.f32 of their results (inputs change every trip), results xor-folded
+            asm volatile("add.rn.f32 %3, %3, %6; add.rn.f32 %4, %4, %6; add.rn.f32 %5, %5, %6;"
+                         "cvt.f64.f32 %0, %3; cvt.f64.f32 %1, %4; cvt.f64.f32 %2, %5;"
+                         : "=d"(e0), "=d"(e1), "=d"(e2), "+f"(a0), "+f"(a1), "+f"(a2) : "f"(seed));
+            asm volatile("xor.b64 %0, %0, %1; xor.b64 %0, %0, %2; xor.b64 %0, %0, %3;" : "+l"(p7) : "l"(__double_as_longlong(e0)), "l"(__double_as_longlong(e1)), "l"(__double_as_longlong(e2)));
+        } else if (MIX == 16) {  // two pipes: 4 mul.f32x2 (FMA pipe) + 4 prmt (ALU pipe), independent: do they overlap?
+            asm volatile("mul.rn.f32x2 %0, %0, %8; prmt.b32 %4, %4, %9, 0x7440; mul.rn.f32x2 %1, %1, %8; prmt.b32 %5, %5, %9, 0x7441;"
+                         "mul.rn.f32x2 %2, %2, %8; prmt.b32 %6, %6, %9, 0x7442; mul.rn.f32x2 %3, %3, %8; prmt.b32 %7, %7, %9, 0x7443;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+r"(u0), "+r"(u1), "+r"(u2), "+r"(u3) : "l"(w), "r"(0x4B000000u));
+        } else if (MIX == 17) {  // two pipes: 4 fma.f64 (fp64 pipe) + 4 mul.f32x2 (FMA pipe), independent
+            asm volatile("fma.rn.f64 %0, %0, %8, %0; mul.rn.f32x2 %4, %4, %9; fma.rn.f64 %1, %1, %8, %1; mul.rn.f32x2 %5, %5, %9;"
+                         "fma.rn.f64 %2, %2, %8, %2; mul.rn.f32x2 %6, %6, %9; fma.rn.f64 %3, %3, %8, %3; mul.rn.f32x2 %7, %7, %9;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3) : "d"(0.999), "l"(w));
+        } else if (MIX == 18) {  // three pipes: 3 fma.f64 + 3 mul.f32x2 + 3 prmt, independent
+            asm volatile("fma.rn.f64 %0, %0, %9, %0; mul.rn.f32x2 %3, %3, %10; prmt.b32 %6, %6, %11, 0x7440;"
+                         "fma.rn.f64 %1, %1, %9, %1; mul.rn.f32x2 %4, %4, %10; prmt.b32 %7, %7, %11, 0x7441;"
+                         "fma.rn.f64 %2, %2, %9, %2; mul.rn.f32x2 %5, %5, %10; prmt.b32 %8, %8, %11, 0x7442;"
+                         : "+d"(d0), "+d"(d1), "+d"(d2), "+l"(p0), "+l"(p1), "+l"(p2), "+r"(u0), "+r"(u1), "+r"(u2) : "d"(0.999), "l"(w), "r"(0x4B000000u));
         } else if (MIX == 11) {  // 8 x scalar mul.f32 with three distinct registers
             asm volatile("mul.rn.f32 %0, %1, %8; mul.rn.f32 %1, %2, %8; mul.rn.f32 %2, %3, %8; mul.rn.f32 %3, %4, %8;"
                          "mul.rn.f32 %4, %5, %8; mul.rn.f32 %5, %6, %8; mul.rn.f32 %6, %7, %8; mul.rn.f32 %7, %0, %8;"
@@ -98,7 +121,7 @@ __global__ void probe(float *out, float seed, unsigned long long *cycles) {
 }
 
 static int g_sms = 148;
-static double g_best[16];  // best (lowest) cycles per warp-instruction per SMSP of each mix
+static double g_best[24];  // best (lowest) cycles per warp-instruction per SMSP of each mix
 
 template <int MIX>
 void run(const char *name, int insts_per_iter) {
@@ -141,6 +164,11 @@ int main() {
     run<6>("pixel block: 3 FADD + 3 F2F + 6 DFMA", 12);
     run<7>("sample block: 8 FMUL2 + 3 FFMA2", 11);
     run<8>("pixel block + sample block", 23);
+    run<14>("pixel block without conversions: 3 FADD + 6 DFMA", 9);
+    run<15>("3 FADD + 3 F2F (changing inputs) [+3 xor.b64]", 6);
+    run<16>("two pipes: 4 FMUL2 + 4 PRMT", 8);
+    run<17>("two pipes: 4 DFMA + 4 FMUL2", 8);
+    run<18>("three pipes: 3 DFMA + 3 FMUL2 + 3 PRMT", 9);
     run<12>("4 x mul.f32 + 4 x add.f32 (scalar, un-fused)", 8);
     run<13>("4 x mul.f32x2 + 4 x add.f32x2 (packed, un-fused)", 8);
     cudaError_t e = cudaDeviceSynchronize();
