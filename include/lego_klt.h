@@ -277,6 +277,15 @@ void lego_klt_multi_destroy(lego_klt_multi *m);
 /* Block i: its device, first pair and pair count.  Returns the number of blocks (or a negative error). */
 int lego_klt_multi_shard(const lego_klt_multi *m, int i, int *device, int *first_pair, int *n_pairs);
 int lego_klt_multi_set_feature_counts(lego_klt_multi *m, const int *counts);   /* B entries, or NULL */
+/*
+ * Schedule of lego_klt_multi_track.  block_pairs = 0 (default): the static contiguous blocks above.  block_pairs > 0:
+ * the devices PULL blocks of that many pairs from one shared counter, two blocks in flight per device (upload of one
+ * behind the kernels and the result copy of the other), so that a device behind a slower host link -- or one that is
+ * shared with other work -- takes fewer pairs instead of holding the call back.  Same result bytes either way.
+ * lego_klt_multi_last_distribution: pairs each device tracked in the last call (returns the number of devices).
+ */
+int lego_klt_multi_set_schedule(lego_klt_multi *m, int block_pairs);
+int lego_klt_multi_last_distribution(const lego_klt_multi *m, int *pairs_per_device, int capacity);
 int lego_klt_multi_track(lego_klt_multi *m, const lego_klt_params *params, const uint8_t *imgs1,
                          const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success,
                          lego_klt_stats *stats_or_null);

@@ -413,6 +413,18 @@ class MultiTracker:
         _lib.check(self._lib.lego_klt_multi_set_feature_counts(self._h, None if c is None else c.ctypes.data),
                    "lego_klt_multi_set_feature_counts")
 
+    def set_schedule(self, block_pairs: int):
+        """lego_klt_multi_set_schedule: 0 = static contiguous blocks, > 0 = devices pull blocks of that many pairs."""
+        _lib.check(self._lib.lego_klt_multi_set_schedule(self._h, int(block_pairs)), "lego_klt_multi_set_schedule")
+
+    def last_distribution(self):
+        """Pairs each device tracked in the last call (lego_klt_multi_last_distribution)."""
+        out = (C.c_int * 64)()
+        n = self._lib.lego_klt_multi_last_distribution(self._h, out, 64)
+        if n < 0:
+            raise _lib.KltError(n, "lego_klt_multi_last_distribution")
+        return [int(out[i]) for i in range(n)]
+
     def track(self, imgs1, imgs2, kp1, kp2_inout, success, params: Params | None = None):
         """lego_klt_multi_track: every block through lego_klt_track_batched on its device, concurrently."""
         params = params or make_params(self.levels)

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -1624,16 +1625,138 @@ int lego_klt_debug_read_eig(lego_klt_ctx *ctx, float *out, size_t capacity, int 
 }
 
 // ---- one process, several devices (SURVEY.md 8b "device list", 8e) --------------------------------------------
+constexpr int kMultiMaxDepth = 4;
 struct lego_klt_multi {
     struct Shard {
         int device = 0, first = 0, count = 0;
         lego_klt_ctx *ctx = nullptr;
         lego_klt_batch *batch = nullptr;
+        // dynamic schedule: two small batch objects (two contexts = two stream sets), so that the upload of one block
+        // overlaps the kernels and the result copy of the other
+        lego_klt_ctx *dctx[kMultiMaxDepth] = {};
+        lego_klt_batch *dbatch[kMultiMaxDepth] = {};
+        int last_pairs = 0;   // pairs this device tracked in the last call
+        int last_blocks = 0;
     };
     std::vector<Shard> shards;
+    std::vector<int> counts;   // ragged batch: per-pair feature counts (empty: all n)
     int B = 0, cols = 0, rows = 0, n = 0, levels = 0;
+    int block = 0;             // 0: static contiguous blocks; > 0: devices pull blocks of this many pairs
+    int depth = 2;             // blocks in flight per device (dynamic schedule)
     size_t step = 0;
 };
+
+}  // extern "C"
+
+namespace {
+
+void multi_free_dynamic(lego_klt_multi *m) {
+    for (auto &sh : m->shards)
+        for (int j = 0; j < kMultiMaxDepth; ++j) {
+            if (sh.dbatch[j]) lego_klt_batch_destroy(sh.dbatch[j]);
+            if (sh.dctx[j]) lego_klt_destroy(sh.dctx[j]);
+            sh.dbatch[j] = nullptr;
+            sh.dctx[j] = nullptr;
+        }
+}
+
+int multi_ensure_dynamic(lego_klt_multi *m) {
+    for (auto &sh : m->shards)
+        for (int j = 0; j < m->depth; ++j) {
+            if (sh.dbatch[j]) continue;
+            int rc = lego_klt_create(sh.device, &sh.dctx[j]);
+            if (rc == LEGO_KLT_OK)
+                rc = lego_klt_batch_create(sh.dctx[j], m->block, m->cols, m->rows, m->step, m->n, m->levels, &sh.dbatch[j]);
+            if (rc != LEGO_KLT_OK) {
+                const std::string why = g_last_error;
+                multi_free_dynamic(m);
+                g_last_error = why;
+                return rc;
+            }
+        }
+    return LEGO_KLT_OK;
+}
+
+// One block of `npairs` <= b->B pairs through a batch object, everything on its context stream: upload, pyramids,
+// solver, result copy.  Returns once the work is enqueued; block_end waits.  `counts`: per-pair feature counts of
+// these pairs, or null.
+int block_begin(lego_klt_batch *b, const lego_klt_params *params, const uint8_t *imgs1, const uint8_t *imgs2,
+                const float *kp1_xy, float *kp2_xy, uint8_t *success, int npairs, const int *counts) {
+    int rc = validate_params(params, b->levels);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const size_t nt = (size_t)npairs * (size_t)b->n_active;
+    CU_TRY(cudaEventRecord(b->ev[EV_START], st));
+    CU_TRY(cudaMemsetAsync(b->d_stats, 0, kStatCount * sizeof(unsigned long long), st));
+    // every host -> device copy first, the re-pitch kernels after them: a copy queued behind a kernel of its own stream
+    // would hold up the copy engine's queue for the other blocks in flight
+    if (nt) {
+        CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
+    }
+    b->ragged = counts != nullptr;
+    if (counts) {   // (the previous block of this object has been ended: its copy of h_pair_count is done)
+        if (!b->d_pair_count) CU_TRY(cudaMalloc(&b->d_pair_count, (size_t)b->B * sizeof(int)));
+        b->h_pair_count.assign(counts, counts + npairs);
+        b->h_pair_count.resize(b->B, 0);
+        CU_TRY(cudaMemcpyAsync(b->d_pair_count, b->h_pair_count.data(), (size_t)b->B * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(upload_set(b, 0, imgs1, 0, npairs, st));
+    CU_TRY(upload_set(b, 1, imgs2, 0, npairs, st));
+    CU_TRY(ingest_set(b, 0, 0, npairs, st));
+    CU_TRY(ingest_set(b, 1, 0, npairs, st));
+    CU_TRY(cudaEventRecord(b->ev[EV_H2D], st));
+    rc = run_range(b, params, 0, npairs, 0, nullptr);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(b->ev[EV_SOLVE], st));
+    if (nt) {
+        CU_TRY(cudaMemcpyAsync(kp2_xy, b->d_kp2_out, nt * sizeof(float2), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(success, b->d_success, nt, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaMemcpyAsync(b->h_stats, b->d_stats, kStatCount * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(b->ev[EV_D2H], st));
+    b->uploaded = true;
+    b->pyramids_valid = false;   // (only the first npairs pyramids are this block's)
+    b->ran = true;
+    b->last_chunked = true;
+    b->last_timed = false;
+    b->last_params = *params;
+    ++b->runs;
+    return LEGO_KLT_OK;
+}
+
+int block_end(lego_klt_batch *b, lego_klt_stats *stats) {
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    CU_TRY(cudaStreamSynchronize(b->ctx->stream));
+    if (stats) fill_stats(b, stats);
+    return LEGO_KLT_OK;
+}
+
+void add_stats(lego_klt_stats *acc, const lego_klt_stats &s, bool concurrent) {
+    acc->n_success += s.n_success;
+    acc->n_nan += s.n_nan;
+    acc->n_out_of_image += s.n_out_of_image;
+    acc->n_slow_path += s.n_slow_path;
+    acc->n_deferred += s.n_deferred;
+    for (int l = 0; l < LEGO_KLT_MAX_LEVELS; ++l) acc->gn_iters[l] += s.gn_iters[l];
+    for (int k = 0; k < 4; ++k) acc->defer_reason[k] += s.defer_reason[k];
+    if (concurrent) {   // devices work concurrently: the slowest one
+        acc->ms_h2d = std::max(acc->ms_h2d, s.ms_h2d);
+        acc->ms_pyramid = std::max(acc->ms_pyramid, s.ms_pyramid);
+        acc->ms_solver = std::max(acc->ms_solver, s.ms_solver);
+        acc->ms_d2h = std::max(acc->ms_d2h, s.ms_d2h);
+    } else {            // blocks of one device, one after the other
+        acc->ms_h2d += s.ms_h2d;
+        acc->ms_pyramid += s.ms_pyramid;
+        acc->ms_solver += s.ms_solver;
+        acc->ms_d2h += s.ms_d2h;
+    }
+}
+
+}  // namespace
+
+extern "C" {
 
 int lego_klt_multi_create(const int *devices, int n_devices, int batch, int cols, int rows, size_t step, int n_per_pair,
                           int levels, lego_klt_multi **out) {
@@ -1648,6 +1771,7 @@ int lego_klt_multi_create(const int *devices, int n_devices, int batch, int cols
     m->step = step;
     m->n = n_per_pair;
     m->levels = levels;
+    if (const char *d = getenv("LEGO_KLT_MULTI_DEPTH")) m->depth = std::min(std::max(atoi(d), 1), kMultiMaxDepth);  // tuning aid
     m->shards.resize(n_devices);
     // contiguous blocks of pairs whose sizes differ by at most one (the partition of lego_slam_b200/sharding.py)
     const int base = batch / n_devices, rem = batch % n_devices;
@@ -1656,6 +1780,7 @@ int lego_klt_multi_create(const int *devices, int n_devices, int batch, int cols
         sh.device = devices[i];
         sh.first = i * base + (i < rem ? i : rem);
         sh.count = base + (i < rem ? 1 : 0);
+        sh.last_pairs = 0;
         int rc = lego_klt_create(sh.device, &sh.ctx);
         if (rc == LEGO_KLT_OK) rc = lego_klt_batch_create(sh.ctx, sh.count, cols, rows, step, n_per_pair, levels, &sh.batch);
         if (rc != LEGO_KLT_OK) {
@@ -1671,6 +1796,7 @@ int lego_klt_multi_create(const int *devices, int n_devices, int batch, int cols
 
 void lego_klt_multi_destroy(lego_klt_multi *m) {
     if (!m) return;
+    multi_free_dynamic(m);
     for (auto &sh : m->shards) {
         if (sh.batch) lego_klt_batch_destroy(sh.batch);
         if (sh.ctx) lego_klt_destroy(sh.ctx);
@@ -1692,28 +1818,103 @@ int lego_klt_multi_set_feature_counts(lego_klt_multi *m, const int *counts) {
         int rc = lego_klt_batch_set_feature_counts(sh.batch, counts ? counts + sh.first : nullptr);
         if (rc) return rc;
     }
+    if (counts) m->counts.assign(counts, counts + m->B);   // (validated block by block above)
+    else m->counts.clear();
     return LEGO_KLT_OK;
+}
+
+int lego_klt_multi_set_schedule(lego_klt_multi *m, int block_pairs) {
+    if (!m) return fail(LEGO_KLT_ERR_BAD_ARG, "multi is null");
+    if (block_pairs < 0 || block_pairs > m->B) return fail(LEGO_KLT_ERR_BAD_ARG, "block_pairs must be in [0, %d]", m->B);
+    if (block_pairs != m->block) multi_free_dynamic(m);   // (the block objects are sized for one block)
+    m->block = block_pairs;
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_multi_last_distribution(const lego_klt_multi *m, int *pairs_per_device, int capacity) {
+    if (!m || !pairs_per_device) return fail(LEGO_KLT_ERR_BAD_ARG, "null argument");
+    if (capacity < (int)m->shards.size()) return fail(LEGO_KLT_ERR_BAD_ARG, "capacity < number of devices");
+    for (size_t i = 0; i < m->shards.size(); ++i) pairs_per_device[i] = m->shards[i].last_pairs;
+    return (int)m->shards.size();
 }
 
 int lego_klt_multi_track(lego_klt_multi *m, const lego_klt_params *params, const uint8_t *imgs1, const uint8_t *imgs2,
                          const float *kp1_xy, float *kp2_xy, uint8_t *success, lego_klt_stats *stats) {
     if (!m) return fail(LEGO_KLT_ERR_BAD_ARG, "multi is null");
     if (!params || !imgs1 || !imgs2) return fail(LEGO_KLT_ERR_BAD_ARG, "null argument");
+    if ((size_t)m->B * (size_t)m->n && (!kp1_xy || !kp2_xy || !success)) return fail(LEGO_KLT_ERR_BAD_ARG, "keypoint pointer is null");
     const size_t img_bytes = (size_t)m->rows * m->step;
     const int S = (int)m->shards.size();
     std::vector<int> rcs(S, LEGO_KLT_OK);
     std::vector<std::string> errs(S);
     std::vector<lego_klt_stats> st(S);
-    auto work = [&](int i) {
-        const lego_klt_multi::Shard &sh = m->shards[i];
+    for (auto &s1 : st) memset(&s1, 0, sizeof(s1));
+    std::atomic<int> next_block(0);
+    if (m->block > 0) {
+        int rc = multi_ensure_dynamic(m);
+        if (rc) return rc;
+    }
+    const int n_blocks = m->block > 0 ? (m->B + m->block - 1) / m->block : 0;
+    const int *counts = m->counts.empty() ? nullptr : m->counts.data();
+    auto work_static = [&](int i) {
+        lego_klt_multi::Shard &sh = m->shards[i];
         const size_t ko = (size_t)sh.first * (size_t)m->n;
         rcs[i] = lego_klt_track_batched(sh.batch, params, imgs1 + (size_t)sh.first * img_bytes,
                                         imgs2 + (size_t)sh.first * img_bytes, kp1_xy ? kp1_xy + 2 * ko : nullptr,
                                         kp2_xy ? kp2_xy + 2 * ko : nullptr, success ? success + ko : nullptr, &st[i]);
         if (rcs[i]) errs[i] = g_last_error;  // (thread-local in the worker)
+        sh.last_pairs = rcs[i] ? 0 : sh.count;
     };
-    // one host thread per device: each drives its own context, streams and pinned-copy pipeline; no exchange between
+    // Dynamic schedule: the devices pull blocks of pairs from one counter, so that a device behind a slower host link
+    // (or a busier one) simply takes fewer of them; two blocks in flight per device.  Pairs are independent: which
+    // device tracks a block does not change its bytes.
+    auto work_dynamic = [&](int i) {
+        lego_klt_multi::Shard &sh = m->shards[i];
+        bool pending[kMultiMaxDepth] = {};
+        sh.last_pairs = 0;
+        sh.last_blocks = 0;
+        auto finish = [&](int j) {
+            lego_klt_stats s1;
+            const int rc = block_end(sh.dbatch[j], &s1);
+            pending[j] = false;
+            if (rc) {
+                if (!rcs[i]) { rcs[i] = rc; errs[i] = g_last_error; }
+            } else {
+                add_stats(&st[i], s1, false);
+            }
+        };
+        for (int turn = 0; !rcs[i]; ++turn) {
+            const int j = turn % m->depth;
+            if (pending[j]) finish(j);
+            if (rcs[i]) break;
+            const int k = next_block.fetch_add(1);
+            if (k >= n_blocks) break;
+            const int first = k * m->block, np = std::min(m->block, m->B - first);
+            const size_t ko = (size_t)first * (size_t)m->n;
+            const int rc = block_begin(sh.dbatch[j], params, imgs1 + (size_t)first * img_bytes, imgs2 + (size_t)first * img_bytes,
+                                       kp1_xy ? kp1_xy + 2 * ko : nullptr, kp2_xy ? kp2_xy + 2 * ko : nullptr,
+                                       success ? success + ko : nullptr, np, counts ? counts + first : nullptr);
+            if (rc) {
+                rcs[i] = rc;
+                errs[i] = g_last_error;
+                cudaStreamSynchronize(sh.dbatch[j]->ctx->stream);   // nothing of this block stays in flight
+                break;
+            }
+            pending[j] = true;
+            sh.last_pairs += np;
+            ++sh.last_blocks;
+        }
+        for (int q = 0; q < m->depth; ++q) {   // (oldest first)
+            const int j = (int)((q + (long long)sh.last_blocks) % m->depth);
+            if (pending[j]) finish(j);
+        }
+    };
+    // one host thread per device: each drives its own context(s), streams and pinned-copy pipeline; no exchange between
     // them (pairs are independent), results land in disjoint slices of the caller's buffers
+    auto work = [&](int i) {
+        if (m->block > 0) work_dynamic(i);
+        else work_static(i);
+    };
     std::vector<std::thread> pool;
     for (int i = 1; i < S; ++i) pool.emplace_back(work, i);
     work(0);
@@ -1722,19 +1923,11 @@ int lego_klt_multi_track(lego_klt_multi *m, const lego_klt_params *params, const
         if (rcs[i]) return fail(rcs[i], "device %d: %s", m->shards[i].device, errs[i].c_str());
     if (stats) {
         memset(stats, 0, sizeof(*stats));
-        for (int i = 0; i < S; ++i) {
-            stats->n_features += st[i].n_features;
-            stats->n_success += st[i].n_success;
-            stats->n_nan += st[i].n_nan;
-            stats->n_out_of_image += st[i].n_out_of_image;
-            stats->n_slow_path += st[i].n_slow_path;
-            stats->n_deferred += st[i].n_deferred;
-            for (int l = 0; l < LEGO_KLT_MAX_LEVELS; ++l) stats->gn_iters[l] += st[i].gn_iters[l];
-            for (int k = 0; k < 4; ++k) stats->defer_reason[k] += st[i].defer_reason[k];
-            stats->ms_h2d = std::max(stats->ms_h2d, st[i].ms_h2d);          // devices work concurrently
-            stats->ms_pyramid = std::max(stats->ms_pyramid, st[i].ms_pyramid);
-            stats->ms_solver = std::max(stats->ms_solver, st[i].ms_solver);
-            stats->ms_d2h = std::max(stats->ms_d2h, st[i].ms_d2h);
+        for (int i = 0; i < S; ++i) add_stats(stats, st[i], true);
+        if (counts) {
+            for (int v : m->counts) stats->n_features += (uint64_t)v;
+        } else {
+            stats->n_features = (uint64_t)m->B * (uint64_t)m->n;
         }
     }
     return LEGO_KLT_OK;

@@ -539,6 +539,48 @@ def test_multi_device_entry_equals_single_context_bytes(tracker):
     one.close()
 
 
+def test_multi_device_dynamic_schedule_equals_single_context_bytes(tracker):
+    """lego_klt_multi_set_schedule: devices pull blocks of pairs from one counter (two in flight per device); the batch
+    size is not a multiple of the block, one pass is ragged: bytes equal a single context's, every pair tracked once."""
+    import torch
+    B, rows, cols, n = 23, 188, 620, 1500
+    imgs1, imgs2, kp1, kp2 = _make_batch(B, rows, cols, n, 6100)
+    guess = kp2.copy()
+    ndev = torch.cuda.device_count()
+    counts = np.random.default_rng(3).integers(0, n + 1, B).astype(np.int32)
+    counts[5] = 0
+    for ragged in (False, True):
+        one = tracker.batch(B, rows, cols, n, levels=4)
+        one.set_feature_counts(counts if ragged else None)
+        succ1 = klt.pinned_empty((B, n), np.uint8)
+        succ1[:] = 7
+        np.copyto(kp2, guess)
+        st1 = one.track(imgs1, imgs2, kp1, kp2, succ1, klt.make_params(kernel=klt.KERNEL_LANE))
+        ref = kp2.copy()
+        one.close()
+        multi = klt.MultiTracker([0, 1 % ndev, 0], B, rows, cols, n, levels=4)
+        multi.set_feature_counts(counts if ragged else None)
+        multi.set_schedule(4)
+        for _ in range(2):   # (the second call re-uses the block objects)
+            np.copyto(kp2, guess)
+            succ2 = klt.pinned_empty((B, n), np.uint8)
+            succ2[:] = 7
+            st2 = multi.track(imgs1, imgs2, kp1, kp2, succ2, klt.make_params(kernel=klt.KERNEL_LANE))
+            used = np.broadcast_to(np.arange(n)[None, :] < (counts[:, None] if ragged else n), (B, n))
+            assert np.array_equal(kp2.view(np.uint32)[used], ref.view(np.uint32)[used])
+            assert np.array_equal(succ1[used], succ2[used])
+            assert list(st1.gn_iters) == list(st2.gn_iters) and int(st1.n_success) == int(st2.n_success)
+            assert int(st2.n_features) == (int(counts.sum()) if ragged else B * n)
+            dist = multi.last_distribution()
+            assert len(dist) == 3 and sum(dist) == B
+        multi.set_schedule(0)    # back to the static blocks
+        np.copyto(kp2, guess)
+        multi.track(imgs1, imgs2, kp1, kp2, succ2, klt.make_params(kernel=klt.KERNEL_LANE))
+        assert np.array_equal(kp2.view(np.uint32)[used], ref.view(np.uint32)[used])
+        assert multi.last_distribution() == [8, 8, 7]
+        multi.close()
+
+
 def test_kernel_launch_counter_counts_this_librarys_launches(tracker):
     L, R, kp1, kp2, _ = synth.stereo_case(94, 310, 50, seed=8, min_dist=8)
     before = klt.kernel_launches()
