@@ -788,14 +788,16 @@ int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t
     NvtxRange range("lego_klt H2D");
     cudaStream_t st = b->ctx->stream;
     CU_TRY(cudaEventRecord(b->ev[EV_START], st));
-    CU_TRY(upload_set(b, 0, imgs1, 0, b->B, st));
-    CU_TRY(upload_set(b, 1, imgs2, 0, b->B, st));
-    CU_TRY(ingest_set(b, 0, 0, b->B, st));
-    CU_TRY(ingest_set(b, 1, 0, b->B, st));
+    // copies first, the re-pitch kernels after them (a copy queued behind a kernel of its own stream holds up the copy
+    // engine's queue for other streams' uploads)
     if (nt) {
         CU_TRY(cudaMemcpyAsync(b->d_kp1, kp1_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(b->d_kp2_init, kp2_xy, nt * sizeof(float2), cudaMemcpyHostToDevice, st));
     }
+    CU_TRY(upload_set(b, 0, imgs1, 0, b->B, st));
+    CU_TRY(upload_set(b, 1, imgs2, 0, b->B, st));
+    CU_TRY(ingest_set(b, 0, 0, b->B, st));
+    CU_TRY(ingest_set(b, 1, 0, b->B, st));
     b->uploaded = true;
     b->pyramids_valid = false;
     b->last_chunked = false;
