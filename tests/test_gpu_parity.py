@@ -238,6 +238,67 @@ def test_batch_is_idempotent_and_equals_single_calls(tracker):
     batch.close()
 
 
+def test_full_size_config3_size_independent_properties(tracker):
+    """BASELINE config C3 at its FULL size (256 pairs 1241x376 x 2000 features, 4 levels), where the CPU oracle is too
+    slow to be the checker (bench.py does compare this size with the reference's own code on every run): properties
+    that hold at any size.  (a) permuting the pairs permutes the results, byte for byte; (b) permuting the features
+    inside every pair likewise; (c) a second run gives the same bytes; (d) a pair tracked against itself from its own
+    keypoints stays where it is, exactly, and succeeds; (e) a sample of the pairs equals the bit-exact EXACT kernel."""
+    B, rows, cols, n = 256, 376, 1241, 2000
+    base = [synth.stereo_case(rows, cols, n, seed=9000 + i) for i in range(8)]
+    rng = np.random.default_rng(12)
+    imgs1 = klt.pinned_empty((B, rows, cols), np.uint8)
+    imgs2 = klt.pinned_empty((B, rows, cols), np.uint8)
+    kp1 = klt.pinned_empty((B, n, 2), np.float32)
+    kp2 = klt.pinned_empty((B, n, 2), np.float32)
+    for b in range(B):
+        L, R, a, g, _ = base[b % 8]
+        sh = b // 8                       # (every pair distinct: the base pair rolled by whole pixels)
+        imgs1[b], imgs2[b] = np.roll(L, sh, axis=1), np.roll(R, sh, axis=1)
+        ok = (a[:, 0] + sh < cols - 8)[:, None]                # (the keypoints move with the content where they can)
+        kp1[b] = np.where(ok, a + np.float32([sh, 0]), a)
+        kp2[b] = np.where(ok, g + np.float32([sh, 0]), g)
+        if b % 3 == 0:                    # a third of the pairs with sub-pixel source keypoints
+            kp1[b] += rng.uniform(-0.5, 0.5, (n, 2)).astype(np.float32)
+            kp2[b] = kp1[b]
+    p = klt.make_params(kernel=klt.KERNEL_LANE)
+    batch = tracker.batch(B, rows, cols, n, levels=4)
+
+    def run(i1, i2, k1, k2):
+        batch.upload(np.ascontiguousarray(i1), np.ascontiguousarray(i2), np.ascontiguousarray(k1), np.ascontiguousarray(k2))
+        batch.run(p)
+        o, s, st = batch.download()
+        return o.copy(), s.copy(), _iters(st, 4), int(st.n_success)
+
+    o0, s0, it0, ns0 = run(imgs1, imgs2, kp1, kp2)
+    assert ns0 == int(s0.sum()) and ns0 > 0.3 * B * n
+    # (c) same bytes again
+    o1, s1, it1, _ = run(imgs1, imgs2, kp1, kp2)
+    assert np.array_equal(o0.view(np.uint32), o1.view(np.uint32)) and np.array_equal(s0, s1) and it0 == it1
+    # (a) pairs permuted
+    perm = rng.permutation(B)
+    o2, s2, it2, _ = run(imgs1[perm], imgs2[perm], kp1[perm], kp2[perm])
+    assert np.array_equal(o2.view(np.uint32), o0[perm].view(np.uint32)) and np.array_equal(s2, s0[perm]) and it2 == it0
+    # (b) features permuted inside every pair
+    fperm = rng.permutation(n)
+    o3, s3, it3, _ = run(imgs1, imgs2, kp1[:, fperm], kp2[:, fperm])
+    assert np.array_equal(o3.view(np.uint32), o0[:, fperm].view(np.uint32)) and np.array_equal(s3, s0[:, fperm]) and it3 == it0
+    # (d) identity: img2 = img1, guess = source keypoints
+    o4, s4, it4, ns4 = run(imgs1, imgs1, kp1, kp1)
+    assert np.array_equal(o4.view(np.uint32), np.asarray(kp1).view(np.uint32)) and ns4 == B * n and bool(s4.all())
+    assert it4 == [B * n] * 4             # one pass per level: the update is exactly zero
+    batch.close()
+    # (e) sixteen of the pairs through the EXACT kernel
+    pick = np.sort(rng.choice(B, 16, replace=False))
+    chk = tracker.batch(16, rows, cols, n, levels=4)
+    chk.upload(np.ascontiguousarray(imgs1[pick]), np.ascontiguousarray(imgs2[pick]), np.ascontiguousarray(kp1[pick]),
+               np.ascontiguousarray(kp2[pick]))
+    chk.run(klt.make_params(kernel=klt.KERNEL_EXACT))
+    eo, es, _ = chk.download()
+    assert_parity(o0[pick], s0[pick], eo, es, cols, rows, "C3 full size vs EXACT")
+    chk.close()
+
+
 # ------------------------------------------------------------------ edge cases
 @pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT] + FAST_KERNELS)
 def test_edge_cases(tracker, oracle, kernel):
