@@ -535,6 +535,35 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
     const float2 k0 = args.kp1[f];
     const float kx = level_coord(k0.x, L, level), ky = level_coord(k0.y, L, level);
 
+#ifndef LANE_TPL_EARLY
+#define LANE_TPL_EARLY 0
+#endif
+    // Experiment (measured, not adopted): request the img1 window rows BEFORE the grid factors are computed -- 43 % of
+    // the kernel's stall samples wait for these loads right after issuing them.  1: L2 prefetches first (solver 1.55 ms
+    // against 1.48); 2: the loads themselves first, held in registers across the factor computations (167 registers,
+    // three CTAs per SM instead of four: 1.48, no gain -- the scattered 16-byte requests, not their latency, bound it).
+    uint4 q[kTplRows][2];
+    bool early = false;
+    if (!kInverse && LANE_TPL_EARLY && valid && fabs((double)kx) < 1.0e6 && fabs((double)ky) < 1.0e6) {
+        const int ixe = __double2int_rd((double)kx + (double)(LO - 1)), iye = __double2int_rd((double)ky + (double)(LO - 1));
+        const int wx0 = (ixe - 2) & ~15, wy0 = iye + 1;
+        early = window_in_apron(lv, wx0, 32);
+        if (early) {
+            const uint8_t *img1 = lv.base[0] + (size_t)img * lv.slot;
+#pragma unroll
+            for (int i = 0; i < kTplRows; ++i) {
+                const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+                const uint4 *rp = reinterpret_cast<const uint4 *>(img1 + (ptrdiff_t)ry * lv.pitch + wx0);
+                if (LANE_TPL_EARLY == 1) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 1));
+                } else {
+                    q[i][0] = __ldg(rp);
+                    q[i][1] = __ldg(rp + 1);
+                }
+            }
+        }
+    }
     float xx[G], omx[G], yy[G], omy[G];
     int ixn = 0, iyn = 0;
     unsigned mBx, mBy;
@@ -646,14 +675,15 @@ klt_template_kernel(const __grid_constant__ PyramidView pyr, const __grid_consta
         const int ox = ixn - wx0;
         const int k = ox >> 2, sh = (ox & 3) * 8;
         const uint8_t *img1 = lv.base[0] + (size_t)img * lv.slot;
-        uint4 q[kTplRows][2];
+        if (LANE_TPL_EARLY != 2) {
 #pragma unroll
-        for (int i = 0; i < kTplRows; ++i) {  // all loads in flight; rows clamped, columns from the aprons
-            const int ry = min(max(wy0 + i, 0), lv.rows - 1);
-            const uint4 *rp = reinterpret_cast<const uint4 *>(img1 + (ptrdiff_t)ry * lv.pitch + wx0);
-            q[i][0] = __ldg(rp);
-            q[i][1] = __ldg(rp + 1);
-        }
+            for (int i = 0; i < kTplRows; ++i) {  // all loads in flight; rows clamped, columns from the aprons
+                const int ry = min(max(wy0 + i, 0), lv.rows - 1);
+                const uint4 *rp = reinterpret_cast<const uint4 *>(img1 + (ptrdiff_t)ry * lv.pitch + wx0);
+                q[i][0] = __ldg(rp);
+                q[i][1] = __ldg(rp + 1);
+            }
+        }   // (else: requested at the top -- `regular` implies `early`, and ixn / iyn are the origin used there)
         float rowA[G + 1], rowB[G + 1];
         row_from_regs(q[0][0], q[0][1], k, sh, rowA);
 #pragma unroll
