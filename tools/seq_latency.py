@@ -6,7 +6,8 @@ import lego_slam_b200 as klt
 from lego_slam_b200 import synth
 
 trk = klt.Tracker(0)
-for n in (150, 500, 2000, 5000, 20000):
+counts = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [150, 500, 2000, 5000, 20000]
+for n in counts:
     L, R, kp1, kp2, _ = synth.stereo_case(376, 1241, n, seed=2, min_dist=3 if n > 5000 else None)
     a = trk.image(376, 1241).upload(L)
     b = trk.image(376, 1241).upload(R)
