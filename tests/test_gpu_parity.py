@@ -299,6 +299,77 @@ def test_full_size_config3_size_independent_properties(tracker):
     chk.close()
 
 
+def _random_problem(seed, allow_non_finite=False):
+    """The seeded random problems of tests/test_oracle_vs_ref.py (where the oracle is compared with the reference's own
+    code on them): size, texture, keypoints inside / on the border / outside / absurdly far, random guesses."""
+    rng = np.random.default_rng(20_000 + seed)
+    rows, cols = int(rng.integers(40, 160)), int(rng.integers(40, 220))
+
+    def image(kind):
+        if kind == 0:
+            return rng.integers(0, 256, size=(rows, cols), dtype=np.uint8)
+        if kind == 1:
+            yy, xx = np.mgrid[0:rows, 0:cols]
+            f = rng.uniform(0.05, 0.6, 4)
+            img = 127 + 60 * np.sin(f[0] * xx + f[1] * yy) + 60 * np.cos(f[2] * xx - f[3] * yy)
+            return np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+        if kind == 2:
+            return np.full((rows, cols), int(rng.integers(0, 256)), np.uint8)
+        img = np.zeros((rows, cols), np.uint8)
+        img[:, cols // 2:] = 200
+        return img
+
+    img1 = image(int(rng.integers(0, 4)))
+    img2 = np.roll(img1, (int(rng.integers(-2, 3)), int(rng.integers(-3, 4))), axis=(0, 1)) if rng.random() < 0.7 \
+        else image(int(rng.integers(0, 4)))
+    n = int(rng.integers(1, 50))
+    kp1 = np.stack([rng.uniform(-4, cols + 4, n), rng.uniform(-4, rows + 4, n)], axis=1).astype(np.float32)
+    if rng.random() < 0.5:
+        kp1 = np.round(kp1)
+    kp2 = (kp1 + rng.normal(0, 2.5, kp1.shape)).astype(np.float32)
+    special = np.float32([1e7, -1e7, 3e38, -3e38, 65536.5, 0.0, -0.0, 1e-40] + ([np.nan, np.inf, -np.inf] if allow_non_finite else []))
+    for _ in range(int(rng.integers(0, 5)) + (3 if allow_non_finite else 0)):
+        (kp1 if rng.random() < 0.5 else kp2)[int(rng.integers(0, n)), int(rng.integers(0, 2))] = special[int(rng.integers(0, len(special)))]
+    return img1, img2, kp1, kp2, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), (1 if rng.random() < 0.25 else 4)
+
+
+@pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT] + FAST_KERNELS)
+def test_random_problems_match_the_oracle(tracker, oracle, kernel):
+    for seed in range(24):
+        img1, img2, kp1, kp2, inverse, has_initial, layers = _random_problem(seed)
+        kw = dict(levels=layers, inverse=inverse, has_initial=has_initial)
+        if not _supported(kernel, kw):
+            continue
+        ref, rs, rst = oracle.track(img1, img2, kp1, kp2, oracle.make_params(**kw))
+        o, s, st = tracker.track(img1, img2, kp1, kp2, klt.make_params(kernel=kernel, **kw))
+        if kernel == klt.KERNEL_EXACT:
+            assert np.array_equal(o.view(np.uint32), ref.view(np.uint32)) and np.array_equal(s, rs), f"seed {seed}"
+        else:
+            assert_parity(o, s, ref, rs, img1.shape[1], img1.shape[0], f"random problem {seed} kernel={kernel}")
+        assert _iters(st, layers) == _iters(rst, layers), f"seed {seed}"
+
+
+@pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT] + FAST_KERNELS)
+def test_non_finite_keypoints_fail_cleanly(tracker, oracle, kernel):
+    """NaN / infinite coordinates: the reference indexes the image with int(NaN) (undefined behaviour, it typically
+    crashes; an infinite one becomes NaN through k2 - k1 or is clamped to the border).  Here a NaN feature must simply
+    fail -- success = 0 -- and neither kind may disturb the other features of the call, which must equal the oracle's
+    results on the call without the non-finite features."""
+    for seed in range(8):
+        img1, img2, kp1, kp2, inverse, has_initial, layers = _random_problem(100 + seed, allow_non_finite=True)
+        kw = dict(levels=layers, inverse=inverse, has_initial=has_initial)
+        if not _supported(kernel, kw):
+            continue
+        # (the guess is read only where has_initial says so: src/algorithm.cpp:47-50)
+        nan = np.isnan(kp1).any(axis=1) | (np.isnan(kp2).any(axis=1) & has_initial)
+        good = np.isfinite(kp1).all(axis=1) & (np.isfinite(kp2).all(axis=1) | (not has_initial))
+        o, s, st = tracker.track(img1, img2, kp1, kp2, klt.make_params(kernel=kernel, **kw))
+        assert not s[nan].any(), f"seed {seed}: a feature with NaN coordinates reports success"
+        if good.any():
+            ref, rs, _ = oracle.track(img1, img2, kp1[good], kp2[good], oracle.make_params(**kw))
+            assert_parity(o[good], s[good], ref, rs, img1.shape[1], img1.shape[0], f"non-finite neighbours, seed {seed} kernel={kernel}")
+
+
 # ------------------------------------------------------------------ edge cases
 @pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT] + FAST_KERNELS)
 def test_edge_cases(tracker, oracle, kernel):

@@ -120,3 +120,48 @@ def test_track_pairs_equals_single_calls():
     for s in range(3):
         a, b = rb.track(imgs1[s], imgs2[s], k1[s], k2[s])
         assert _same(out[s], a) and np.array_equal(ok[s], b)
+
+
+def _fuzz_image(rng, rows, cols, kind):
+    if kind == 0:      # white noise
+        return rng.integers(0, 256, size=(rows, cols), dtype=np.uint8)
+    if kind == 1:      # smooth texture
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        f = rng.uniform(0.05, 0.6, 4)
+        img = 127 + 60 * np.sin(f[0] * xx + f[1] * yy) + 60 * np.cos(f[2] * xx - f[3] * yy)
+        return np.clip(img + rng.normal(0, 3, img.shape), 0, 255).astype(np.uint8)
+    if kind == 2:      # constant (singular normal equations everywhere)
+        return np.full((rows, cols), int(rng.integers(0, 256)), np.uint8)
+    img = np.zeros((rows, cols), np.uint8)     # step edges: rank-1 normal equations
+    img[:, cols // 2:] = 200
+    return img
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_oracle_equals_reference_tu_on_random_problems(seed):
+    """Seeded random problems: image size, texture (noise / smooth / constant / step edge), keypoints inside, on the
+    border, outside, far and absurdly far outside, random guesses, either mode, with and without the initial guess,
+    1 or 4 layers.  Positions compared by bits (NaN payloads included), flags exactly."""
+    rng = np.random.default_rng(20_000 + seed)
+    rows, cols = int(rng.integers(40, 160)), int(rng.integers(40, 220))
+    kind = int(rng.integers(0, 4))
+    img1 = _fuzz_image(rng, rows, cols, kind)
+    img2 = np.roll(img1, (int(rng.integers(-2, 3)), int(rng.integers(-3, 4))), axis=(0, 1)) if rng.random() < 0.7 \
+        else _fuzz_image(rng, rows, cols, int(rng.integers(0, 4)))
+    n = int(rng.integers(1, 50))
+    kp1 = np.stack([rng.uniform(-4, cols + 4, n), rng.uniform(-4, rows + 4, n)], axis=1).astype(np.float32)
+    if rng.random() < 0.5:
+        kp1 = np.round(kp1)                      # freshly detected corners are integer
+    kp2 = (kp1 + rng.normal(0, 2.5, kp1.shape)).astype(np.float32)
+    # (finite only: a NaN coordinate indexes the image with int(NaN) in the reference -- undefined behaviour,
+    # algorithm.h:42-48 clamps only x < 0 and x >= cols -- and +-inf turns into NaN through k2 - k1)
+    special = np.float32([1e7, -1e7, 3e38, -3e38, 65536.5, 0.0, -0.0, 1e-40])
+    for _ in range(int(rng.integers(0, 5))):
+        (kp1 if rng.random() < 0.5 else kp2)[int(rng.integers(0, n)), int(rng.integers(0, 2))] = special[int(rng.integers(0, len(special)))]
+    inverse, has_initial = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+    layers = 1 if rng.random() < 0.25 else 4
+    with np.errstate(all="ignore"):
+        ref_kp, ref_ok = rb.track(img1, img2, kp1, kp2, inverse=inverse, has_initial=has_initial, layers=layers)
+        o_kp, o_ok, _ = ob.track(img1, img2, kp1, kp2, ob.make_params(levels=layers, inverse=inverse, has_initial=has_initial))
+    assert np.array_equal(o_ok, ref_ok)
+    assert _same(o_kp, ref_kp)
