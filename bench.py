@@ -698,10 +698,11 @@ def run_ours(args):
 
     # ---------------- rank 0 only: single-call configurations, CPU arm, parity ----------------
     threads = os.cpu_count() or 1
-    seq = c1 = None
+    seq = c1 = chain = None
     if not args.no_side and world == 1:
         seq = sequence_mode(trk, n, args)
         c1 = single_call_record(trk, args)
+        chain = frontend_chain_record(trk, imgs1, imgs2, B, cam_l, cam_r)
     cpu = None
     parity = {}
     # the headline batch's first pairs once more through the bit-exact EXACT kernel (the on-GPU checker)
@@ -818,6 +819,7 @@ def run_ours(args):
     if not args.no_side:
         line["sequence_mode"] = seq
         line["single_call"] = c1
+        line["frontend_chain"] = chain
         line["other_patches"] = {
             name: {"patch": list(pb), "value": world * n_tracks / (side_ms[f"patch_{name}"] * 1e-3), "unit": "tracks/s",
                    "ms_per_step": side_ms[f"patch_{name}"]} for name, pb in (("8x8", (-4, 3)), ("11x11", (-5, 5)))}
@@ -860,6 +862,47 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def frontend_chain_record(trk, imgs1, imgs2, B, cam_l, cam_r, n_feat: int = 150):
+    """The frontend's per-frame chain on a batch of frames whose images are in HBM, keypoints never crossing PCIe:
+    DetectFeatures on the left images (cv::GFTTDetector::create(150, 0.01, 20), src/frontend_g2o.cpp:16,279-297) ->
+    FindFeaturesInRight (:495-535, guess = the same pixel) -> triangulation of the matches (:310-349)."""
+    import torch
+    import lego_slam_b200 as klt
+    fb = trk.batch(B, ROWS, COLS, n_feat, levels=LEVELS)
+    z = klt.pinned_empty((B, n_feat, 2), np.float32)
+    z[:] = 0
+    fb.upload(imgs1, imgs2, z, z)
+    p = klt.make_params(levels=LEVELS)
+    tri_pt = klt.pinned_empty((B, n_feat, 3), np.float64)
+    tri_ok = klt.pinned_empty((B, n_feat), np.uint8)
+
+    def once():
+        t0 = time.perf_counter()
+        _, cnt, _ = fb.detect_features(0, n_feat, 0.01, 20.0)
+        t1 = time.perf_counter()
+        fb.use_detected_features()
+        fb.run(p)
+        trk.sync()
+        t2 = time.perf_counter()
+        fb.triangulate(cam_l, cam_r, 1e-3, tri_pt, tri_ok)
+        t3 = time.perf_counter()
+        return cnt, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3
+
+    once()
+    reps = [once() for _ in range(5)]
+    cnt = reps[-1][0]
+    det, trackms, tri = (float(np.median([r[i] for r in reps])) for i in (1, 2, 3))
+    _, succ, st = fb.download()
+    fb.close()
+    total = det + trackms + tri
+    return {"what": f"{B} frames 1241x376 in HBM: lego_klt_batch_detect_features ({n_feat} corners, 0.01, 20) -> "
+                    "lego_klt_batch_use_detected_features -> lego_klt_batch_run (stereo matching) -> lego_klt_batch_triangulate; "
+                    "host wall clock incl. the result copies of detection and triangulation",
+            "ms_detect": det, "ms_track": trackms, "ms_triangulate": tri, "ms_total": total,
+            "frames_per_s": B / (total * 1e-3), "corners_per_frame_mean": float(cnt.mean()),
+            "detect_images_per_s": B / (det * 1e-3), "tracked": int(st.n_success), "triangulated_ok": int(tri_ok.sum())}
 
 
 def single_call_record(trk, args):

@@ -260,6 +260,19 @@ int lego_klt_detect_features(lego_klt_ctx *ctx, const uint8_t *img, int cols, in
 int lego_klt_image_detect_features(lego_klt_image *img, const float *exclude_xy, int n_exclude, float exclude_half,
                                    int max_corners, double quality_level, double min_distance, float *corners_xy,
                                    float *scores_or_null, int *n_corners);
+/* The same for every pair of a batch whose images are in HBM (lego_klt_batch_upload / lego_klt_track_batched): one
+ * Frontend::DetectFeatures per image of `set` (0 = img1, 1 = img2), all pairs per launch.  exclude_source_keypoints != 0:
+ * the mask of src/frontend_g2o.cpp:280-284 is built from the pair's source keypoints (the first counts[b] of them in a
+ * ragged batch).  corners_xy: B x max_corners x {x, y} in OpenCV's order (slots beyond n_corners[b] are zero);
+ * scores_or_null: B x max_corners; n_corners: B.  Images of up to 2^21 pixels. */
+int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_source_keypoints, float exclude_half,
+                                   int max_corners, double quality_level, double min_distance, float *corners_xy,
+                                   float *scores_or_null, int *n_corners);
+/* Makes the corners of the batch's last lego_klt_batch_detect_features call its source keypoints, where they lie in HBM:
+ * pair b tracks its n_corners[b] corners (a ragged batch), initial guess = the same pixel (src/frontend_g2o.cpp:508).
+ * Then lego_klt_batch_run / lego_klt_batch_triangulate: detection -> stereo matching -> triangulation of a batch of
+ * frames without the keypoints crossing PCIe.  The detection's max_corners must not exceed the batch's n_per_pair. */
+int lego_klt_batch_use_detected_features(lego_klt_batch *b);
 /* Test hook: the minimum-eigenvalue map (rows x cols floats) of the context's last detection. */
 int lego_klt_debug_read_eig(lego_klt_ctx *ctx, float *out, size_t capacity, int *cols, int *rows);
 

@@ -23,7 +23,7 @@ EXPORTS = [
     "lego_klt_image_create", "lego_klt_image_destroy", "lego_klt_image_upload", "lego_klt_track_images",
     "lego_klt_kernel_launches", "lego_klt_batch_set_feature_counts", "lego_klt_batch_set_pipeline_chunks",
     "lego_klt_multi_create", "lego_klt_multi_destroy", "lego_klt_multi_shard", "lego_klt_multi_set_feature_counts",
-    "lego_klt_multi_track", "lego_klt_multi_set_schedule", "lego_klt_multi_last_distribution", "lego_klt_detect_features", "lego_klt_image_detect_features", "lego_klt_debug_read_eig",
+    "lego_klt_multi_track", "lego_klt_multi_set_schedule", "lego_klt_multi_last_distribution", "lego_klt_detect_features", "lego_klt_image_detect_features", "lego_klt_batch_detect_features", "lego_klt_batch_use_detected_features", "lego_klt_debug_read_eig",
     "lego_klt_track_frame", "lego_klt_track_batched_begin", "lego_klt_track_batched_end",
 ]
 
@@ -116,6 +116,7 @@ def load():
     lib.lego_klt_multi_set_feature_counts.argtypes = [vp, vp]
     lib.lego_klt_multi_track.argtypes = [vp, pp, vp, vp, vp, vp, vp, sp]
     lib.lego_klt_multi_set_schedule.argtypes = [vp, C.c_int]
+    lib.lego_klt_batch_detect_features.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, vp, vp, vp]
     lib.lego_klt_multi_last_distribution.argtypes = [vp, ip, C.c_int]
     lib.lego_klt_detect_features.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, vp, C.c_int, C.c_float,
                                              C.c_int, C.c_double, C.c_double, vp, vp, ip]

@@ -296,6 +296,22 @@ class Batch:
     def close(self):
         self._fin()
 
+    def detect_features(self, image_set: int = 0, max_corners: int = 150, quality_level: float = 0.01,
+                        min_distance: float = 20.0, exclude_keypoints: bool = False, exclude_half: float = 10.0):
+        """lego_klt_batch_detect_features: Frontend::DetectFeatures on every image of one set of the batch (images already
+        in HBM), all pairs per launch.  Returns (corners (B, max_corners, 2), counts (B,), scores (B, max_corners))."""
+        out = np.zeros((self.B, max_corners, 2), np.float32)
+        sc = np.zeros((self.B, max_corners), np.float32)
+        cnt = np.zeros(self.B, np.int32)
+        _lib.check(self._lib.lego_klt_batch_detect_features(self._h, int(image_set), int(bool(exclude_keypoints)), exclude_half,
+                                                            max_corners, quality_level, min_distance, out.ctypes.data,
+                                                            sc.ctypes.data, cnt.ctypes.data), "lego_klt_batch_detect_features")
+        return out, cnt, sc
+
+    def use_detected_features(self):
+        """lego_klt_batch_use_detected_features: the last detection's corners become the batch's source keypoints (in HBM)."""
+        _lib.check(self._lib.lego_klt_batch_use_detected_features(self._h), "lego_klt_batch_use_detected_features")
+
     def set_feature_counts(self, counts):
         """Ragged batch: pair b tracks its first counts[b] features only (None: all n)."""
         if counts is None:

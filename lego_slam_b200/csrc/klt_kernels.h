@@ -121,6 +121,15 @@ cudaError_t launch_gftt(const uint8_t *d_img, int cols, int rows, int pitch, con
                         int n_exclude, float exclude_half, int max_corners, double quality, float min_distance, uint8_t *ws,
                         size_t ws_bytes, float2 *d_corners, float *d_scores_or_null, int *d_n_out, int *h_n_candidates,
                         cudaStream_t stream);
+// Batched form: n_images images of one layout (image i at d_imgs + i * img_stride, rows of `pitch` bytes), `chunk` of them
+// per pass through the workspace of gftt_batched_workspace_bytes(); an exclusion list of exclude_per_image points per image
+// (d_exclude_counts: how many of them are used, or null = all).  Outputs: corners [n_images][max_corners], n_out [n_images].
+size_t gftt_batched_workspace_bytes(int cols, int rows, int chunk);
+bool gftt_batched_supported(int cols, int rows, int batch);
+cudaError_t launch_gftt_batched(const uint8_t *d_imgs, size_t img_stride, int pitch, int cols, int rows, int n_images,
+                                const float2 *d_exclude, int exclude_per_image, const int *d_exclude_counts, float exclude_half,
+                                int max_corners, double quality, float min_distance, uint8_t *ws, size_t ws_bytes, int chunk,
+                                float2 *d_corners, float *d_scores_or_null, int *d_n_out, cudaStream_t stream);
 // Test hook: the eigenvalue map of the last launch_gftt on this workspace (rows x cols floats) to host memory.
 cudaError_t gftt_debug_eig(const uint8_t *ws, int cols, int rows, float *h_eig, cudaStream_t stream);
 

@@ -119,6 +119,11 @@ struct lego_klt_batch {
     bool lane_ready = false;       // every LANE-path allocation below exists
     int *d_work = nullptr;         // per chunk: [0] lane work counter, [1] deferred count, [2] family count,
                                    // [3] lane<FAMILIES> work counter
+    uint8_t *d_detect = nullptr;   // batched feature detection: workspace | corners | scores | counts (grow-only)
+    size_t detect_bytes = 0;
+    int detect_max = 0;            // max_corners of the last batched detection (0: none yet)
+    size_t detect_ws = 0;          // where its outputs start inside d_detect
+    std::vector<int> detect_counts;
     int *d_defer_list = nullptr;   // [B * n_cap]
     int *d_fam_list = nullptr;     // [B * n_cap]
     float *d_templates = nullptr;  // LANE kernel: I1 patches, allocated on first use
@@ -750,6 +755,7 @@ void lego_klt_batch_destroy(lego_klt_batch *b) {
         for (int i = 0; i < 3; ++i)
             if (b->ring[r][i]) cudaEventDestroy(b->ring[r][i]);
     cudaFree(b->d_pair_count);
+    cudaFree(b->d_detect);
     cudaFree(b->d_defer_list);
     cudaFree(b->d_fam_list);
     cudaFree(b->d_templates);
@@ -1614,6 +1620,78 @@ int lego_klt_image_detect_features(lego_klt_image *im, const float *exclude_xy, 
     if (rc) return rc;
     const LevelView &lv = im->view.lv[0];
     return gftt_run(im->ctx, lv.base[0], lv.pitch, nullptr, 0, im->cols, im->rows, g, corners_xy, scores, n_corners);
+}
+
+int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_source_keypoints, float exclude_half, int max_corners,
+                                   double quality_level, double min_distance, float *corners_xy, float *scores, int *n_corners) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (!b->uploaded) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_detect_features before the images are uploaded");
+    if (set != 0 && set != 1) return fail(LEGO_KLT_ERR_BAD_ARG, "set must be 0 (img1) or 1 (img2)");
+    if (b->cols < 3 || b->rows < 3) return fail(LEGO_KLT_ERR_BAD_ARG, "image too small");
+    const GfttArgs g{nullptr, 0, nullptr, 0, exclude_half, max_corners, quality_level, min_distance};
+    int rc = gftt_check(g, corners_xy, n_corners);
+    if (rc) return rc;
+    // images per pass through the workspace (~25 bytes per pixel and image): as many as ~4 GB hold, at most 256
+    const size_t fit = ((size_t)4 << 30) / ((size_t)b->cols * (size_t)b->rows * 25);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)b->B, 256), fit));
+    if (!gftt_batched_supported(b->cols, b->rows, chunk))
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "batched detection: images of up to 2^21 pixels");
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const size_t ws = align_up(gftt_batched_workspace_bytes(b->cols, b->rows, chunk), 256);
+    const size_t nc = (size_t)b->B * (size_t)max_corners;
+    const size_t out_b = align_up(nc * (sizeof(float2) + sizeof(float)) + (size_t)b->B * sizeof(int) + 64, 256);
+    if (ws + out_b > b->detect_bytes) {
+        CU_TRY(cudaStreamSynchronize(st));
+        if (b->d_detect) cudaFree(b->d_detect);
+        b->d_detect = nullptr;
+        b->detect_bytes = 0;
+        CU_TRY(cudaMalloc(&b->d_detect, ws + out_b));
+        b->detect_bytes = ws + out_b;
+    }
+    float2 *d_corners = reinterpret_cast<float2 *>(b->d_detect + ws);
+    float *d_scores = reinterpret_cast<float *>(d_corners + nc);
+    int *d_n = reinterpret_cast<int *>(d_scores + nc);
+    CU_TRY(cudaMemsetAsync(d_corners, 0, out_b, st));   // (slots beyond a pair's corner count read as zeros)
+    const LevelView &lv = b->view.lv[0];
+    const bool ex = exclude_source_keypoints != 0 && b->n_active > 0;
+    NvtxRange range("lego_klt detect features (batch)");
+    CU_TRY(launch_gftt_batched(lv.base[set], lv.slot, lv.pitch, b->cols, b->rows, b->B, ex ? b->d_kp1 : nullptr, ex ? b->n_active : 0,
+                               ex && b->ragged ? b->d_pair_count : nullptr, exclude_half, max_corners, quality_level, (float)min_distance,
+                               b->d_detect, ws, chunk, d_corners, scores ? d_scores : nullptr, d_n, st));
+    CU_TRY(cudaMemcpyAsync(corners_xy, d_corners, nc * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    if (scores) CU_TRY(cudaMemcpyAsync(scores, d_scores, nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(n_corners, d_n, (size_t)b->B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    b->detect_max = max_corners;
+    b->detect_ws = ws;
+    b->detect_counts.assign(n_corners, n_corners + b->B);
+    return LEGO_KLT_OK;
+}
+
+int lego_klt_batch_use_detected_features(lego_klt_batch *b) {
+    if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
+    if (b->detect_max <= 0) return fail(LEGO_KLT_ERR_STATE, "lego_klt_batch_use_detected_features before lego_klt_batch_detect_features");
+    if (b->detect_max > b->n_active)
+        return fail(LEGO_KLT_ERR_BAD_ARG, "the detection asked for up to %d corners per image, the batch holds %d features per pair",
+                    b->detect_max, b->n_active);
+    if (b == b->ctx->single) return fail(LEGO_KLT_ERR_BAD_ARG, "internal batch");
+    CU_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const float2 *d_corners = reinterpret_cast<const float2 *>(b->d_detect + b->detect_ws);
+    // corners [B][detect_max] -> source keypoints and initial guesses [B][n_active] (the same pixel: src/frontend_g2o.cpp:508)
+    const size_t w = (size_t)b->detect_max * sizeof(float2);
+    CU_TRY(cudaMemcpy2DAsync(b->d_kp1, (size_t)b->n_active * sizeof(float2), d_corners, w, w, b->B, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaMemcpy2DAsync(b->d_kp2_init, (size_t)b->n_active * sizeof(float2), d_corners, w, w, b->B, cudaMemcpyDeviceToDevice, st));
+    if (!b->d_pair_count) CU_TRY(cudaMalloc(&b->d_pair_count, (size_t)b->B * sizeof(int)));
+    CU_TRY(cudaStreamSynchronize(st));  // an earlier copy may still read the host vector
+    b->h_pair_count = b->detect_counts;
+    unsigned long long total = 0;
+    for (int v : b->h_pair_count) total += (unsigned long long)v;
+    CU_TRY(cudaMemcpyAsync(b->d_pair_count, b->h_pair_count.data(), (size_t)b->B * sizeof(int), cudaMemcpyHostToDevice, st));
+    b->ragged = true;
+    b->n_valid = total;
+    return LEGO_KLT_OK;
 }
 
 int lego_klt_debug_read_eig(lego_klt_ctx *ctx, float *out, size_t capacity, int *cols, int *rows) {

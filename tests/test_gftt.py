@@ -130,6 +130,81 @@ def test_gpu_detection_matches_cv2_within_the_stated_tolerance(tracker):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,md,exclude", [(150, 20.0, False), (150, 20.0, True), (800, 5.0, True), (60, 0.0, False)])
+def test_gpu_batched_detection_equals_the_single_image_calls(tracker, n, md, exclude):
+    """lego_klt_batch_detect_features (every image of a batch per launch, more images than one workspace pass holds, both
+    image sets, the exclusion mask from the pair's own source keypoints, a ragged batch) against the single-image entry
+    point on each image -- which equals the numpy oracle exactly (above)."""
+    import lego_slam_b200 as klt
+    B, rows, cols, nk = 37, 120, 200, 40
+    rng = np.random.default_rng(21)
+    base = _images()[:2]
+    imgs1 = klt.pinned_empty((B, rows, cols), np.uint8)
+    imgs2 = klt.pinned_empty((B, rows, cols), np.uint8)
+    for b in range(B):
+        src = base[b % len(base)]
+        y0, x0 = int(rng.integers(0, src.shape[0] - rows + 1)), int(rng.integers(0, src.shape[1] - cols + 1))
+        imgs1[b] = src[y0:y0 + rows, x0:x0 + cols]
+        imgs2[b] = np.roll(imgs1[b], 3, axis=1)
+    imgs1[5] = 77                                   # a flat image: no corners at all
+    kp1 = klt.pinned_empty((B, nk, 2), np.float32)
+    kp1[:] = np.stack([rng.uniform(-5, cols + 5, (B, nk)), rng.uniform(-5, rows + 5, (B, nk))], axis=2)
+    counts = rng.integers(0, nk + 1, B).astype(np.int32)
+    batch = tracker.batch(B, rows, cols, nk, levels=3)
+    batch.set_feature_counts(counts)
+    batch.upload(imgs1, imgs2, kp1, kp1)
+    for image_set, imgs in ((0, imgs1), (1, imgs2)):
+        pts, cnt, sc = batch.detect_features(image_set, n, 0.01, md, exclude_keypoints=exclude, exclude_half=10.0)
+        for b in range(B):
+            ex = kp1[b, :counts[b]] if exclude and counts[b] else None
+            ref, rsc = tracker.detect_features(np.ascontiguousarray(imgs[b]), n, 0.01, md, exclude=ex)
+            assert cnt[b] == ref.shape[0], (image_set, b)
+            assert np.array_equal(pts[b, :cnt[b]], ref) and np.array_equal(sc[b, :cnt[b]].view(np.uint32), rsc.view(np.uint32))
+            assert not pts[b, cnt[b]:].any()
+        assert image_set == 1 or cnt[5] == 0
+    batch.close()
+
+
+@pytest.mark.gpu
+def test_gpu_detect_track_triangulate_chain_stays_on_the_device(tracker, oracle):
+    """lego_klt_batch_detect_features -> lego_klt_batch_use_detected_features -> lego_klt_batch_run: the detected
+    corners become the source keypoints where they lie in HBM.  Same bytes as fetching the corners, uploading them as
+    keypoints of a ragged batch and running; one pair also against the CPU oracle."""
+    import lego_slam_b200 as klt
+    B, rows, cols, n = 6, 188, 620, 200
+    imgs1 = klt.pinned_empty((B, rows, cols), np.uint8)
+    imgs2 = klt.pinned_empty((B, rows, cols), np.uint8)
+    for b in range(B):
+        imgs1[b], imgs2[b], _ = synth.stereo_pair(rows, cols, 40 + b)
+    zeros = klt.pinned_empty((B, n, 2), np.float32)
+    zeros[:] = 0
+    batch = tracker.batch(B, rows, cols, n, levels=4)
+    batch.upload(imgs1, imgs2, zeros, zeros)
+    pts, cnt, _ = batch.detect_features(0, n, 0.01, 12.0)
+    assert cnt.min() > 20
+    batch.use_detected_features()
+    batch.run(klt.make_params(kernel=klt.KERNEL_LANE))
+    o1, s1, st1 = batch.download()
+    assert int(st1.n_features) == int(cnt.sum())
+    # the host round trip
+    other = tracker.batch(B, rows, cols, n, levels=4)
+    other.set_feature_counts(cnt)
+    kp = klt.pinned_empty((B, n, 2), np.float32)
+    kp[:] = pts
+    other.upload(imgs1, imgs2, kp, kp)
+    other.run(klt.make_params(kernel=klt.KERNEL_LANE))
+    o2, s2, st2 = other.download()
+    used = np.arange(n)[None, :] < cnt[:, None]
+    assert np.array_equal(o1.view(np.uint32)[used], o2.view(np.uint32)[used]) and np.array_equal(s1[used], s2[used])
+    assert [int(v) for v in st1.gn_iters][:4] == [int(v) for v in st2.gn_iters][:4]
+    ref, rs, _ = oracle.track(imgs1[2], imgs2[2], pts[2, :cnt[2]], pts[2, :cnt[2]])
+    from parity_util import assert_parity
+    assert_parity(o1[2, :cnt[2]], s1[2, :cnt[2]], ref, rs, cols, rows, "chain pair 2")
+    batch.close()
+    other.close()
+
+
+@pytest.mark.gpu
 def test_detected_features_track(tracker, oracle):
     """The frontend's sequence on the device: detect on the left image, track into the right one."""
     import lego_slam_b200 as klt

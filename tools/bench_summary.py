@@ -29,6 +29,8 @@ for path in sys.argv[1:]:
             print(f"parity {name}: flags {q['flag_mismatches']} max {q['max_abs_dpos_px']:.2e} over {q['n_over_1e-3_px']} bit-identical {q['bit_identical_fraction']:.5f}")
     print(f"guess = truth + N(0,2): {g(d,'guess_projected','value',default=0):.4g} iters {g(d,'guess_projected','gn_iters_per_level')} accuracy {g(d,'guess_projected','accuracy_vs_truth')}")
     print(f"accuracy vs truth (kp2 = kp1): {d.get('accuracy_vs_truth')}   GN passes exact/this {g(d,'parity','vs_exact_kernel','gn_passes_per_level_exact_kernel')} / {g(d,'parity','vs_exact_kernel','gn_passes_per_level_this_kernel')}")
+    fc = g(d, 'frontend_chain', default={}) or {}
+    print(f"frontend chain: detect {fc.get('ms_detect', 0):.3f} + track {fc.get('ms_track', 0):.3f} + triangulate {fc.get('ms_triangulate', 0):.3f} ms per {d['config'].get('pairs_per_gpu')} frames = {fc.get('frames_per_s', 0):.4g} frames/s, {fc.get('corners_per_frame_mean', 0):.0f} corners/frame")
     pts = g(d, 'sweep_c5', 'points', default=[])
     print("sweep: " + "  ".join(f"{q['features_per_pair']}/{q['patch']}:{q['value']:.3g}" for q in pts))
     print(f"clocks {g(d,'clocks','sm_mhz')} / {g(d,'clocks','sm_max_mhz')} {g(d,'clocks','reasons')}   per-rank resident {g(d,'per_rank','resident_ms_per_step')}")
