@@ -264,7 +264,7 @@ int lego_klt_image_detect_features(lego_klt_image *img, const float *exclude_xy,
  * Frontend::DetectFeatures per image of `set` (0 = img1, 1 = img2), all pairs per launch.  exclude_source_keypoints != 0:
  * the mask of src/frontend_g2o.cpp:280-284 is built from the pair's source keypoints (the first counts[b] of them in a
  * ragged batch).  corners_xy: B x max_corners x {x, y} in OpenCV's order (slots beyond n_corners[b] are zero);
- * scores_or_null: B x max_corners; n_corners: B.  Images of up to 2^21 pixels. */
+ * scores_or_null: B x max_corners; n_corners: B. */
 int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_source_keypoints, float exclude_half,
                                    int max_corners, double quality_level, double min_distance, float *corners_xy,
                                    float *scores_or_null, int *n_corners);

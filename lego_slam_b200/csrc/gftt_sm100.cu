@@ -16,6 +16,7 @@
 // eigenvalue map -- and with it the corner list -- equals the numpy oracle's bit for bit; against OpenCV itself the pin is
 // tolerance-aware (its box filter's summation order is not fixed by its published behaviour): tests/test_gftt.py.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include "klt_kernels.h"
 
@@ -32,6 +33,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 constexpr int kTW = 32, kTH = 8;   // output tile of gftt_eig_kernel; block = kTW x kTH threads
+constexpr int kEigTilesY = 4;      // tiles per block
 
 // Monotone map float -> unsigned (for atomicMax on floats of either sign).
 __device__ __forceinline__ unsigned float_key(float v) {
@@ -62,9 +64,15 @@ gftt_eig_kernel(const uint8_t *__restrict__ img, int cols, int rows, int pitch, 
         max_key += z;
     }
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTW + tx;
-    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int x0 = blockIdx.x * kTW;
     if (tid == 0) block_max = 0u;
     const float s = 1.0f / 3060.0f;
+    unsigned my_max = 0u;
+    // kEigTilesY tiles per block, one below the other (one tile per block: the kernel was bound by the rate at which
+    // 469,000 two-microsecond blocks per 256 images can be launched)
+    for (int k = 0; k < kEigTilesY; ++k) {
+    const int y0 = (blockIdx.y * kEigTilesY + k) * kTH;
+    if (y0 >= rows) break;
     // products of the scaled Sobel derivatives at the tile and its one-pixel ring; positions outside the image take the
     // value of their BORDER_REFLECT_101 mirror position (the box filter's border rule on the product images).
     // (Measured: staging the raw pixels in shared memory first -- each loaded once instead of nine times -- is SLOWER,
@@ -100,8 +108,12 @@ gftt_eig_kernel(const uint8_t *__restrict__ img, int cols, int rows, int pitch, 
         const float amc = __fadd_rn(a, -c);
         const float e = __fadd_rn(__fadd_rn(a, c), -__fsqrt_rn(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
         eig[(size_t)y * cols + x] = e;
-        if (!mask || mask[(size_t)y * mask_pitch + x]) atomicMax(&block_max, float_key(e));
+        if (!mask || mask[(size_t)y * mask_pitch + x]) my_max = max(my_max, float_key(e));
     }
+    __syncthreads();   // (the product tiles are rewritten by the next trip)
+    }
+    my_max = __reduce_max_sync(0xffffffffu, my_max);   // one shared-memory atomic per warp, one global one per block
+    if ((tid & 31) == 0 && my_max) atomicMax(&block_max, my_max);
     __syncthreads();
     if (tid == 0 && block_max) atomicMax(max_key, block_max);
 }
@@ -119,12 +131,12 @@ __global__ void gftt_exclusion_kernel(uint8_t *__restrict__ mask, int cols, int 
     for (int k = threadIdx.x; k < w * h; k += blockDim.x) mask[(size_t)(y1 + k / w) * cols + x1 + k % w] = 0;
 }
 
-// Threshold + 3x3 non-maximum suppression for the pixel of this thread (block = 32 x 8 pixels at blockIdx.x / .y).
+// Threshold + 3x3 non-maximum suppression for the pixel of this thread (block = 32 x 8 pixels at tile column blockIdx.x, tile row tile_y).
 // Returns the thresholded score; cand = it is a candidate (non-zero, allowed by the mask, equal to the maximum of its 3x3
 // neighbourhood; border pixels of the image are never candidates).
 __device__ __forceinline__ float nms_candidate(const float *__restrict__ eig, int cols, int rows, const uint8_t *__restrict__ mask,
-                                               int mask_pitch, float thr, bool &cand) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+                                               int mask_pitch, float thr, int tile_y, bool &cand) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = tile_y * 8 + (threadIdx.x >> 5);
     cand = false;
     float v = 0.f;
     if (x >= 1 && y >= 1 && x < cols - 1 && y < rows - 1) {
@@ -153,7 +165,7 @@ gftt_candidates_kernel(const float *__restrict__ eig, int cols, int rows, const 
     // cv::threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO) on a CV_32F image compares with (float)thresh
     const float thr = (float)((double)key_float(*max_key) * quality);
     bool cand = false;
-    const float v = nms_candidate(eig, cols, rows, mask, mask_pitch, thr, cand);
+    const float v = nms_candidate(eig, cols, rows, mask, mask_pitch, thr, blockIdx.y, cand);
     const unsigned ballot = __ballot_sync(0xffffffffu, cand);
     if (ballot) {
         const int lane = threadIdx.x & 31;
@@ -240,11 +252,10 @@ gftt_select_kernel(const unsigned long long *__restrict__ keys, unsigned n, int 
     if (tid == 0) *n_out = accepted;
 }
 
-// ---- batched detection: B images of one batch object at once (keys carry the image index) -----------------------
-// key = image (11 bits) | score bits (32) | flat pixel index (21 bits): one radix sort orders every image's candidates
-// by score, ties by higher address first, images in descending index order.
-constexpr int kKeyIdxBits = 21, kKeyImgShift = 32 + kKeyIdxBits;
-
+// ---- batched detection: B images of one batch object at once ------------------------------------------------------
+// Image b appends its candidate keys (score bits << 32 | flat pixel index, as above) to ITS segment of the key array
+// (px slots at b * px) through its own counter; one segmented radix sort orders every segment; one selection CTA per
+// image.  No count comes back to the host: the whole detection is asynchronous on the stream.
 __global__ void gftt_exclusion_batched_kernel(uint8_t *__restrict__ mask, int cols, int rows, const float2 *__restrict__ pts,
                                               int pts_per_image, const int *__restrict__ counts, float half) {
     const int i = blockIdx.x, b = blockIdx.y;
@@ -262,51 +273,50 @@ __global__ void gftt_exclusion_batched_kernel(uint8_t *__restrict__ mask, int co
 __global__ void __launch_bounds__(256)
 gftt_candidates_batched_kernel(const float *__restrict__ eig_all, int cols, int rows, const uint8_t *__restrict__ mask_all,
                                const unsigned *__restrict__ max_keys, double quality, unsigned long long *__restrict__ keys,
-                               unsigned capacity, unsigned *__restrict__ total, unsigned *__restrict__ per_image) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+                               unsigned *__restrict__ per_image) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), b = blockIdx.z;
     const size_t px = (size_t)cols * rows;
     const float *eig = eig_all + (size_t)b * px;
     const uint8_t *mask = mask_all ? mask_all + (size_t)b * px : nullptr;
     const float thr = (float)((double)key_float(max_keys[b]) * quality);
-    bool cand = false;
-    const float v = nms_candidate(eig, cols, rows, mask, cols, thr, cand);
-    // one global atomic per BLOCK (a counter shared by every warp of 32 images serialises: 0.57 ms per 15 M pixels)
     __shared__ unsigned s_count, s_base;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    const unsigned ballot = __ballot_sync(0xffffffffu, cand);
-    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
-    unsigned off = 0;
-    if (ballot) {
-        if (lane == leader) off = atomicAdd(&s_count, (unsigned)__popc(ballot));
-        off = __shfl_sync(0xffffffffu, off, leader) + __popc(ballot & ((1u << lane) - 1u));
+    for (int k = 0; k < kEigTilesY; ++k) {   // several tiles per block, as in gftt_eig_kernel
+        const int tile_y = blockIdx.y * kEigTilesY + k, y = tile_y * 8 + (threadIdx.x >> 5);
+        if (tile_y * 8 >= rows) break;
+        bool cand = false;
+        const float v = nms_candidate(eig, cols, rows, mask, cols, thr, tile_y, cand);
+        // one global atomic per tile, on the image's own counter
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+        const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+        unsigned off = 0;
+        if (ballot) {
+            if (lane == leader) off = atomicAdd(&s_count, (unsigned)__popc(ballot));
+            off = __shfl_sync(0xffffffffu, off, leader) + __popc(ballot & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) s_base = atomicAdd(per_image + b, s_count);
+        __syncthreads();
+        if (cand)   // (a segment holds one key per pixel: it cannot overflow)
+            keys[(size_t)b * px + s_base + off] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * cols + x);
+        __syncthreads();   // (s_base is rewritten by the next trip)
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_count) {
-        s_base = atomicAdd(total, s_count);
-        atomicAdd(per_image + b, s_count);
-    }
-    __syncthreads();
-    const unsigned pos = s_base + off;
-    if (cand && pos < capacity)   // (the host checks total <= capacity before it trusts the keys)
-        keys[pos] = ((unsigned long long)b << kKeyImgShift) | ((unsigned long long)__float_as_uint(v) << kKeyIdxBits) |
-                    (unsigned)(y * cols + x);
 }
 
-// first key of image b in the descending order = number of candidates of the images above it
-__global__ void gftt_segment_starts_kernel(const unsigned *__restrict__ per_image, int B, unsigned *__restrict__ start) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned acc = 0;
-        for (int b = B - 1; b >= 0; --b) {
-            start[b] = acc;
-            acc += per_image[b];
-        }
+// segment b of the key array: [b * px, b * px + per_image[b])
+__global__ void gftt_segment_offsets_kernel(const unsigned *__restrict__ per_image, int B, int px, int *__restrict__ begin,
+                                            int *__restrict__ end) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        begin[b] = b * px;
+        end[b] = b * px + (int)per_image[b];
     }
 }
 
 // The greedy selection of gftt_select_kernel, one CTA per image.
 __global__ void __launch_bounds__(1024)
-gftt_select_batched_kernel(const unsigned long long *__restrict__ keys_all, const unsigned *__restrict__ start,
+gftt_select_batched_kernel(const unsigned long long *__restrict__ keys_all, size_t px_per_image,
                            const unsigned *__restrict__ per_image, int cols, int max_corners, float min_dist, int cell, int reach,
                            int gw, int gh, int *__restrict__ cell_all, float2 *__restrict__ corners_all,
                            float *__restrict__ scores_all, int *__restrict__ n_out) {
@@ -314,12 +324,12 @@ gftt_select_batched_kernel(const unsigned long long *__restrict__ keys_all, cons
     __shared__ short2 chunk_xy[1024];
     __shared__ int accepted;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const unsigned long long *keys = keys_all + start[b];
+    const unsigned long long *keys = keys_all + (size_t)b * px_per_image;
     const unsigned n = per_image[b];
     int *cell_of = cell_all + (size_t)b * gw * gh;
     float2 *corners = corners_all + (size_t)b * max_corners;
     float *scores = scores_all ? scores_all + (size_t)b * max_corners : nullptr;
-    const unsigned idx_mask = (1u << kKeyIdxBits) - 1u;
+    const unsigned idx_mask = 0xffffffffu;
     if (tid == 0) accepted = 0;
     const float md2 = min_dist * min_dist;
     __syncthreads();
@@ -365,7 +375,7 @@ gftt_select_batched_kernel(const unsigned long long *__restrict__ keys_all, cons
                         chunk_xy[n_chunk] = make_short2((short)px, (short)py);
                         if (min_dist >= 1.f) cell_of[(py / cell) * gw + px / cell] = (int)idx;
                         corners[acc] = make_float2((float)px, (float)py);
-                        if (scores) scores[acc] = __uint_as_float((unsigned)(key >> kKeyIdxBits));
+                        if (scores) scores[acc] = __uint_as_float((unsigned)(key >> 32));
                     }
                     __syncwarp();
                     ++n_chunk;
@@ -383,29 +393,27 @@ gftt_select_batched_kernel(const unsigned long long *__restrict__ keys_all, cons
 }  // namespace
 
 // ---- batched entry ------------------------------------------------------------------------------------------------
-// Workspace for `chunk` images at a time: eigenvalue maps, masks, keys and sorted keys (one per pixel: the suppression
-// keeps ties, so plateaus of equal scores are all candidates), cell grids, scalars, cub's temporary storage.
-static size_t batched_key_capacity(int cols, int rows, int chunk) { return (size_t)chunk * (size_t)cols * rows; }
-
+// Workspace for `chunk` images at a time: eigenvalue maps, masks, keys and sorted keys (one slot per pixel: the
+// suppression keeps ties, so plateaus of equal scores are all candidates), cell grids, scalars, cub's temporary storage.
 size_t gftt_batched_workspace_bytes(int cols, int rows, int chunk) {
-    const size_t px = (size_t)cols * rows, cap = batched_key_capacity(cols, rows, chunk);
+    const size_t px = (size_t)cols * rows, cap = (size_t)chunk * px;
     size_t sort_tmp = 0;
-    cub::DeviceRadixSort::SortKeysDescending(nullptr, sort_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
-                                             (int)cap);
+    cub::DeviceSegmentedRadixSort::SortKeysDescending(nullptr, sort_tmp, (const unsigned long long *)nullptr,
+                                                      (unsigned long long *)nullptr, (int)cap, chunk, (const int *)nullptr,
+                                                      (const int *)nullptr);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    return up((size_t)chunk * px * 4) + up((size_t)chunk * px) + 2 * up(cap * 8) + up((size_t)chunk * px * 4 + 4096) +
-           up((size_t)(3 * chunk + 2) * 4) + sort_tmp + 4096;
+    return up(cap * 4) + up(cap) + 2 * up(cap * 8) + up(cap * 4 + 4096) + up((size_t)(4 * chunk + 2) * 4) + sort_tmp + 4096;
 }
 
-bool gftt_batched_supported(int cols, int rows, int batch) {
-    return (size_t)cols * rows <= ((size_t)1 << kKeyIdxBits) && batch <= (1 << (64 - kKeyImgShift));
+bool gftt_batched_supported(int cols, int rows, int chunk) {   // (segment offsets are ints)
+    return (size_t)cols * rows * (size_t)chunk < ((size_t)1 << 31);
 }
 
 cudaError_t launch_gftt_batched(const uint8_t *d_imgs, size_t img_stride, int pitch, int cols, int rows, int n_images,
                                 const float2 *d_exclude, int exclude_per_image, const int *d_exclude_counts, float exclude_half,
                                 int max_corners, double quality, float min_distance, uint8_t *ws, size_t ws_bytes, int chunk,
                                 float2 *d_corners, float *d_scores_or_null, int *d_n_out, cudaStream_t stream) {
-    const size_t px = (size_t)cols * rows, cap = batched_key_capacity(cols, rows, chunk);
+    const size_t px = (size_t)cols * rows, cap = (size_t)chunk * px;
     if (!gftt_batched_supported(cols, rows, chunk) || ws_bytes < gftt_batched_workspace_bytes(cols, rows, chunk)) return cudaErrorInvalidValue;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     int cell = 1, reach = 0, gw = 1, gh = 1;
@@ -418,26 +426,27 @@ cudaError_t launch_gftt_batched(const uint8_t *d_imgs, size_t img_stride, int pi
     }
     size_t off = 0;
     float *eig = reinterpret_cast<float *>(ws + off);
-    off += up((size_t)chunk * px * 4);
+    off += up(cap * 4);
     uint8_t *mask = ws + off;
-    off += up((size_t)chunk * px);
+    off += up(cap);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + off);
     off += up(cap * 8);
     unsigned long long *sorted = reinterpret_cast<unsigned long long *>(ws + off);
     off += up(cap * 8);
     int *cell_of = reinterpret_cast<int *>(ws + off);
-    off += up((size_t)chunk * px * 4 + 4096);   // (worst case: one cell per pixel)
-    unsigned *scalars = reinterpret_cast<unsigned *>(ws + off);   // [0] total, [1] pad, then max key / count / start per image
-    off += up((size_t)(3 * chunk + 2) * 4);
+    off += up(cap * 4 + 4096);   // (worst case: one cell per pixel)
+    unsigned *scalars = reinterpret_cast<unsigned *>(ws + off);   // max key / count / segment begin / segment end per image
+    off += up((size_t)(4 * chunk + 2) * 4);
     uint8_t *sort_tmp = ws + off;
     size_t sort_tmp_bytes = ws_bytes - off;
-    unsigned *max_keys = scalars + 2, *per_image = max_keys + chunk, *start = per_image + chunk;
+    unsigned *max_keys = scalars, *per_image = max_keys + chunk;
+    int *seg_begin = reinterpret_cast<int *>(per_image + chunk), *seg_end = seg_begin + chunk;
     const bool masked = d_exclude && exclude_per_image > 0;
 
     cudaError_t e;
     for (int b0 = 0; b0 < n_images; b0 += chunk) {
         const int nb = n_images - b0 < chunk ? n_images - b0 : chunk;
-        if ((e = cudaMemsetAsync(scalars, 0, (size_t)(3 * chunk + 2) * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(scalars, 0, (size_t)(2 * chunk) * 4, stream)) != cudaSuccess) return e;
         if (masked) {
             if ((e = cudaMemsetAsync(mask, 255, (size_t)nb * px, stream)) != cudaSuccess) return e;
             gftt_exclusion_batched_kernel<<<dim3(exclude_per_image, nb), 128, 0, stream>>>(
@@ -445,27 +454,22 @@ cudaError_t launch_gftt_batched(const uint8_t *d_imgs, size_t img_stride, int pi
                 d_exclude_counts ? d_exclude_counts + b0 : nullptr, exclude_half);
             note_launch();
         }
-        gftt_eig_kernel<<<dim3((cols + kTW - 1) / kTW, (rows + kTH - 1) / kTH, nb), dim3(kTW, kTH), 0, stream>>>(
+        gftt_eig_kernel<<<dim3((cols + kTW - 1) / kTW, (rows + kTH * kEigTilesY - 1) / (kTH * kEigTilesY), nb), dim3(kTW, kTH), 0, stream>>>(
             d_imgs + (size_t)b0 * img_stride, cols, rows, pitch, masked ? mask : nullptr, cols, eig, max_keys, img_stride);
         note_launch();
-        gftt_candidates_batched_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8, nb), 256, 0, stream>>>(
-            eig, cols, rows, masked ? mask : nullptr, max_keys, quality, keys, (unsigned)cap, scalars, per_image);
+        gftt_candidates_batched_kernel<<<dim3((cols + 31) / 32, (rows + 8 * kEigTilesY - 1) / (8 * kEigTilesY), nb), 256, 0, stream>>>(
+            eig, cols, rows, masked ? mask : nullptr, max_keys, quality, keys, per_image);
+        note_launch();
+        gftt_segment_offsets_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(per_image, nb, (int)px, seg_begin, seg_end);
         note_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        unsigned n_total = 0;   // the sort needs the count on the host: one 4-byte read-back per chunk of images
-        if ((e = cudaMemcpyAsync(&n_total, scalars, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-        if (n_total > cap) return cudaErrorInvalidValue;   // (cannot happen: at most one candidate per pixel)
-        if (n_total > 0) {
-            e = cub::DeviceRadixSort::SortKeysDescending(sort_tmp, sort_tmp_bytes, keys, sorted, (int)n_total, 0, 64, stream);
-            if (e != cudaSuccess) return e;
-            note_launch(3);
-        }
-        gftt_segment_starts_kernel<<<1, 32, 0, stream>>>(per_image, nb, start);
-        note_launch();
+        e = cub::DeviceSegmentedRadixSort::SortKeysDescending(sort_tmp, sort_tmp_bytes, keys, sorted, (int)((size_t)nb * px), nb,
+                                                              seg_begin, seg_end, 0, 64, stream);
+        if (e != cudaSuccess) return e;
+        note_launch(2);
         if (min_distance >= 1.f)
             if ((e = cudaMemsetAsync(cell_of, 0xff, (size_t)nb * gw * gh * sizeof(int), stream)) != cudaSuccess) return e;
-        gftt_select_batched_kernel<<<nb, 1024, 0, stream>>>(sorted, start, per_image, cols, max_corners, min_distance, cell, reach, gw,
+        gftt_select_batched_kernel<<<nb, 1024, 0, stream>>>(sorted, px, per_image, cols, max_corners, min_distance, cell, reach, gw,
                                                             gh, cell_of, d_corners + (size_t)b0 * max_corners,
                                                             d_scores_or_null ? d_scores_or_null + (size_t)b0 * max_corners : nullptr,
                                                             d_n_out + b0);
@@ -523,7 +527,7 @@ cudaError_t launch_gftt(const uint8_t *d_img, int cols, int rows, int pitch, con
         }
         mask_used = mask;
     }
-    dim3 grid((cols + kTW - 1) / kTW, (rows + kTH - 1) / kTH);
+    dim3 grid((cols + kTW - 1) / kTW, (rows + kTH * kEigTilesY - 1) / (kTH * kEigTilesY));
     gftt_eig_kernel<<<grid, dim3(kTW, kTH), 0, stream>>>(d_img, cols, rows, pitch, mask_used, cols, eig, scalars, 0);
     note_launch();
     gftt_candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), 256, 0, stream>>>(eig, cols, rows, mask_used, cols, scalars,

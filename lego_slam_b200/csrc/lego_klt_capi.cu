@@ -1635,7 +1635,7 @@ int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_sourc
     const size_t fit = ((size_t)4 << 30) / ((size_t)b->cols * (size_t)b->rows * 25);
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)b->B, 256), fit));
     if (!gftt_batched_supported(b->cols, b->rows, chunk))
-        return fail(LEGO_KLT_ERR_UNSUPPORTED, "batched detection: images of up to 2^21 pixels");
+        return fail(LEGO_KLT_ERR_UNSUPPORTED, "batched detection: image too large");
     CU_TRY(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->stream;
     const size_t ws = align_up(gftt_batched_workspace_bytes(b->cols, b->rows, chunk), 256);
