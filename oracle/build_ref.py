@@ -61,7 +61,11 @@ def _parametrised_tu(half_patch: int, pyramids: int) -> str:
         text, k = re.subn(pat, rep, text)
         if k != 1:
             raise RuntimeError(f"reference text changed: {pat!r} matched {k} times")
-    path = os.path.join(OUT, f"algorithm_p{half_patch}_l{pyramids}.cpp")
+    # the scratch copy lives in a temporary directory OUTSIDE the repository and is deleted after the compile: no text of
+    # the reference stays under this tree, not even in the git-ignored output directory
+    import tempfile
+    d = tempfile.mkdtemp(prefix="klt_ref_")
+    path = os.path.join(d, f"algorithm_p{half_patch}_l{pyramids}.cpp")
     with open(path, "w") as f:
         f.write(text)
     return path
@@ -83,8 +87,12 @@ def build(force: bool = False) -> list[str]:
             if (hp, lv) == (3, 4):
                 _compile(REF_TU, out, [])
             else:
-                _compile(_parametrised_tu(hp, lv), out,
-                         ["-DKLT_REF_PARAMETRISED", f"-DKLT_REF_HALF_PATCH={hp}", f"-DKLT_REF_PYRAMIDS={lv}"])
+                tu = _parametrised_tu(hp, lv)
+                try:
+                    _compile(tu, out, ["-DKLT_REF_PARAMETRISED", f"-DKLT_REF_HALF_PATCH={hp}", f"-DKLT_REF_PYRAMIDS={lv}"])
+                finally:
+                    import shutil
+                    shutil.rmtree(os.path.dirname(tu), ignore_errors=True)
         built.append(out)
     return built
 
