@@ -44,14 +44,16 @@ enum {
 /* ---- solver kernel selection ---- */
 enum {
     LEGO_KLT_KERNEL_AUTO = 0,   /* LANE where it is compiled (forward mode: patch -3..3, -4..3 or -5..5; the reference's
-                                   inverse mode: -3..3) and the call has more than 3000 features, else WARP (lower
+                                   inverse mode: -3..3) and the call has more than 3000 features, else PATCH (lowest
                                    latency on small calls) */
     LEGO_KLT_KERNEL_EXACT = 1,  /* one thread per feature, reference operation order, flat global
                                    addressing: bit-identical to the CPU oracle; the on-GPU checker  */
     LEGO_KLT_KERNEL_WARP = 2,   /* one warp per feature, windows staged in shared memory, fp64
                                    warp-shuffle reductions, all levels fused in-kernel             */
-    LEGO_KLT_KERNEL_LANE = 3    /* one thread per feature, persistent iteration state machine,
+    LEGO_KLT_KERNEL_LANE = 3,   /* one thread per feature, persistent iteration state machine,
                                    shared sample grid; forward 7x7, 8x8, 11x11, inverse 7x7 */
+    LEGO_KLT_KERNEL_PATCH = 4   /* one CTA per feature, one thread per patch pixel, every sample as the reference
+                                   takes it: the shortest Gauss-Newton pass -- lowest latency on small calls      */
 };
 
 /*

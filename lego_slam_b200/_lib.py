@@ -43,7 +43,7 @@ class Stats(C.Structure):
                 ("ms_solver", C.c_float), ("ms_d2h", C.c_float)]
 
 
-KERNEL_AUTO, KERNEL_EXACT, KERNEL_WARP, KERNEL_LANE = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_WARP, KERNEL_LANE, KERNEL_PATCH = 0, 1, 2, 3, 4
 
 _lib = None
 

@@ -14,7 +14,7 @@ import weakref
 import numpy as np
 
 from . import _lib
-from ._lib import KERNEL_AUTO, KERNEL_EXACT, KERNEL_LANE, KERNEL_WARP, Params, Stats  # noqa: F401
+from ._lib import KERNEL_AUTO, KERNEL_EXACT, KERNEL_LANE, KERNEL_PATCH, KERNEL_WARP, Params, Stats  # noqa: F401
 
 
 def make_params(levels=4, patch_lo=-3, patch_hi=3, max_iters=10, inverse=False, has_initial=True,

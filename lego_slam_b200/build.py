@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("LEGO_KLT_LIB") or os.path.join(HERE, "liblego_klt.so")  # override: tuning experiments only
-SOURCES = ["lego_klt_capi.cu", "pyramid_sm100.cu", "klt_solver_exact.cu", "klt_solver_warp.cu",
+SOURCES = ["lego_klt_capi.cu", "pyramid_sm100.cu", "klt_solver_exact.cu", "klt_solver_warp.cu", "klt_solver_patch.cu",
            "klt_solver_lane.cu", "klt_solver_lane_p8.cu", "klt_solver_lane_p11.cu", "klt_solver_lane_inv.cu",
            "triangulate_sm100.cu", "gftt_sm100.cu"]
 NVCC_FLAGS = [

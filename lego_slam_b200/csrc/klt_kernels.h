@@ -62,6 +62,9 @@ cudaError_t launch_aprons(const PyramidView &pyr, int img0, int nimg, cudaStream
 
 // ---- solver kernels ---------------------------------------------------------------------------
 cudaError_t launch_klt_exact(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
+// One CTA per feature, one thread per patch pixel (klt_solver_patch.cu): the low-latency kernel of small calls.
+bool patch_kernel_supports(const SolverArgs &args);
+cudaError_t launch_klt_patch(const PyramidView &pyr, const SolverArgs &args, cudaStream_t stream);
 
 struct WarpKernelMaps;  // TMA descriptors, defined in klt_solver_warp.cu
 cudaError_t warp_maps_create(const PyramidView &pyr, WarpKernelMaps **out);

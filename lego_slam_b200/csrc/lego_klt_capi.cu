@@ -196,7 +196,7 @@ int validate_params(const lego_klt_params *p, int levels_of_batch) {
         return fail(LEGO_KLT_ERR_UNSUPPORTED, "patch %d..%d unsupported (max %d wide)", p->patch_lo, p->patch_hi,
                     kMaxPatch);
     if (p->max_iters < 0) return fail(LEGO_KLT_ERR_BAD_ARG, "max_iters < 0");
-    if (p->kernel < LEGO_KLT_KERNEL_AUTO || p->kernel > LEGO_KLT_KERNEL_LANE)
+    if (p->kernel < LEGO_KLT_KERNEL_AUTO || p->kernel > LEGO_KLT_KERNEL_PATCH)
         return fail(LEGO_KLT_ERR_BAD_ARG, "unknown kernel id %d", p->kernel);
     return LEGO_KLT_OK;
 }
@@ -424,13 +424,18 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
                            : lane_kernel_supports_inv(a) ? -7
                                                          : 0;
     if (kernel == LEGO_KLT_KERNEL_AUTO)
-        kernel = (lane_patch && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE : LEGO_KLT_KERNEL_WARP;
+        kernel = (lane_patch && a.n_total > kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_LANE
+                 : (patch_kernel_supports(a) && a.n_total <= kAutoLaneMinFeatures) ? LEGO_KLT_KERNEL_PATCH
+                                                                                   : LEGO_KLT_KERNEL_WARP;
     if (kernel == LEGO_KLT_KERNEL_LANE && !lane_patch)
         return fail(LEGO_KLT_ERR_UNSUPPORTED,
                     "LANE kernel: forward mode with the 7x7 (-3..3), 8x8 (-4..3) or 11x11 (-5..5) patch, or inverse mode "
                     "with the 7x7 patch");
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(view, a, st));
+    } else if (kernel == LEGO_KLT_KERNEL_PATCH) {
+        if (!patch_kernel_supports(a)) return fail(LEGO_KLT_ERR_UNSUPPORTED, "PATCH kernel: patches of up to 16 x 16");
+        CU_TRY(launch_klt_patch(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_WARP) {
         CU_TRY(launch_klt_warp(view, maps, a, ctx->sm_count, st));
     } else if (a.n_total > 0) {

@@ -11,7 +11,7 @@ from parity_util import assert_parity
 
 pytestmark = pytest.mark.gpu
 
-FAST_KERNELS = [klt.KERNEL_WARP, klt.KERNEL_LANE]
+FAST_KERNELS = [klt.KERNEL_WARP, klt.KERNEL_LANE, klt.KERNEL_PATCH]
 
 
 def _supported(kernel, kw):
