@@ -146,17 +146,21 @@ klt_patch_kernel(const __grid_constant__ PyramidView pyr, const __grid_constant_
             for (int k = 0; k < 6; ++k) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v[k] = __dadd_rn(v[k], __shfl_down_sync(0xffffffffu, v[k], o));
-                if (lane == 0) part[warp][k] = v[k];
+                if (lane == 0 && warp > 0) part[warp][k] = v[k];   // (warp 0's sums stay in thread 0's registers)
             }
             __syncthreads();
             // ---- thread 0: solve, decide (:92-117)
             if (tid == 0) {
                 double s[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    s[k] = part[0][k];
-                    for (int w = 1; w < n_warps; ++w) s[k] = __dadd_rn(s[k], part[w][k]);
+                for (int k = 0; k < 6; ++k) s[k] = v[k];
+                if (n_warps >= 2) {   // (the common case, 7x7 and 8x8: two warps -- six independent loads)
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s[k] = __dadd_rn(s[k], part[1][k]);
                 }
+                for (int w = 2; w < n_warps; ++w)
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s[k] = __dadd_rn(s[k], part[w][k]);
                 ++iters;
                 if (!inverse || iter == 0) {
                     H00 = s[3];

@@ -12,7 +12,10 @@ for n in counts:
     a = trk.image(376, 1241).upload(L)
     b = trk.image(376, 1241).upload(R)
     row = [f"n={kp1.shape[0]:6d}"]
-    for name, k in (("lane", klt.KERNEL_LANE), ("warp", klt.KERNEL_WARP), ("patch", klt.KERNEL_PATCH)):
+    kernels = (("lane", klt.KERNEL_LANE), ("warp", klt.KERNEL_WARP), ("patch", klt.KERNEL_PATCH))
+    if len(sys.argv) > 2:
+        kernels = tuple(kv for kv in kernels if kv[0] in sys.argv[2].split(","))
+    for name, k in kernels:
         p = klt.make_params(kernel=k)
         for _ in range(5):
             trk.track_images(a, b, kp1, kp2, p)
