@@ -273,7 +273,8 @@ int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_sourc
 /* Makes the corners of the batch's last lego_klt_batch_detect_features call its source keypoints, where they lie in HBM:
  * pair b tracks its n_corners[b] corners (a ragged batch), initial guess = the same pixel (src/frontend_g2o.cpp:508).
  * Then lego_klt_batch_run / lego_klt_batch_triangulate: detection -> stereo matching -> triangulation of a batch of
- * frames without the keypoints crossing PCIe.  The detection's max_corners must not exceed the batch's n_per_pair. */
+ * frames without the keypoints crossing PCIe.  The detection's max_corners must not exceed the batch's n_per_pair.
+ * The per-pair counts stay in force like those of lego_klt_batch_set_feature_counts (reset them with counts = NULL). */
 int lego_klt_batch_use_detected_features(lego_klt_batch *b);
 /* Test hook: the minimum-eigenvalue map (rows x cols floats) of the context's last detection. */
 int lego_klt_debug_read_eig(lego_klt_ctx *ctx, float *out, size_t capacity, int *cols, int *rows);
