@@ -32,8 +32,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return min(max(i, 0), n - 1);
 }
 
-constexpr int kTW = 32, kTH = 8;   // output tile of gftt_eig_kernel; block = kTW x kTH threads
-constexpr int kEigTilesY = 4;      // tiles per block
+constexpr int kEigTilesY = 4;       // 32 x 8 tiles per block of the candidates kernel
 
 // Monotone map float -> unsigned (for atomicMax on floats of either sign).
 __device__ __forceinline__ unsigned float_key(float v) {
@@ -51,10 +50,20 @@ __host__ __device__ __forceinline__ float key_float(unsigned k) {
 #endif
 }
 
-__global__ void __launch_bounds__(kTW *kTH)
+// Row-streaming form of the eigenvalue kernel.  A warp owns a strip of kEigStripW = 30 output columns (lanes 1..30; lanes 0
+// and 31 are its one-column halo) and walks down kEigChunkRows output rows.  Per pixel row a lane loads the three pixels
+// around its column (BORDER_REFLECT_101 on the coordinates: what the Sobel of a position INSIDE the image reads beyond
+// the border), forms the row's two 1-D passes, and keeps the last two rows' in registers: the Sobel pair of row y is
+// complete when row y + 1 arrives.  The three products go to the neighbouring lanes by shuffle for the horizontal
+// 3-sums, which are again kept for three rows for the vertical ones.  Products OUTSIDE the image take the value of their
+// mirror position (the box filter's border rule): column -1 := column 1, row -1 := row 1 (and the same at the far
+// ends) -- a substitution of whole products, never a Sobel of mirrored pixels (its cross term would change sign).
+// Same fp32 operations in the same order as the tile version it replaces (183 instructions per pixel; this one ~80).
+constexpr int kEigStripW = 30, kEigChunkRows = 32, kEigWarps = 8;
+
+__global__ void __launch_bounds__(32 * kEigWarps)
 gftt_eig_kernel(const uint8_t *__restrict__ img, int cols, int rows, int pitch, const uint8_t *__restrict__ mask, int mask_pitch,
                 float *__restrict__ eig, unsigned *__restrict__ max_key, size_t img_stride) {
-    __shared__ float cxx[kTH + 2][kTW + 2], cxy[kTH + 2][kTW + 2], cyy[kTH + 2][kTW + 2];
     __shared__ unsigned block_max;
     {   // batched launch: image blockIdx.z (its own eigenvalue map, mask and maximum)
         const size_t z = blockIdx.z, px = (size_t)cols * rows;
@@ -63,59 +72,74 @@ gftt_eig_kernel(const uint8_t *__restrict__ img, int cols, int rows, int pitch, 
         if (mask) mask += z * px;
         max_key += z;
     }
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTW + tx;
-    const int x0 = blockIdx.x * kTW;
-    if (tid == 0) block_max = 0u;
-    const float s = 1.0f / 3060.0f;
-    unsigned my_max = 0u;
-    // kEigTilesY tiles per block, one below the other (one tile per block: the kernel was bound by the rate at which
-    // 469,000 two-microsecond blocks per 256 images can be launched)
-    for (int k = 0; k < kEigTilesY; ++k) {
-    const int y0 = (blockIdx.y * kEigTilesY + k) * kTH;
-    if (y0 >= rows) break;
-    // products of the scaled Sobel derivatives at the tile and its one-pixel ring; positions outside the image take the
-    // value of their BORDER_REFLECT_101 mirror position (the box filter's border rule on the product images).
-    // (Measured: staging the raw pixels in shared memory first -- each loaded once instead of nine times -- is SLOWER,
-    // 1.50 against 1.21 ms per 256 images of 1241x376; so is a shared-memory tile in the candidates kernels.)
-    for (int i = tid; i < (kTH + 2) * (kTW + 2); i += kTW * kTH) {
-        const int ly = i / (kTW + 2), lx = i - ly * (kTW + 2);
-        const int y = reflect101(y0 + ly - 1, rows), x = reflect101(x0 + lx - 1, cols);
-        const int xm = reflect101(x - 1, cols), xp = reflect101(x + 1, cols);
-        const uint8_t *r0 = img + (size_t)reflect101(y - 1, rows) * pitch, *r1 = img + (size_t)y * pitch,
-                      *r2 = img + (size_t)reflect101(y + 1, rows) * pitch;
-        const float a0 = (float)__ldg(r0 + xm), a1 = (float)__ldg(r0 + x), a2 = (float)__ldg(r0 + xp);
-        const float b0 = (float)__ldg(r1 + xm), b1 = (float)__ldg(r1 + x), b2 = (float)__ldg(r1 + xp);
-        const float c0 = (float)__ldg(r2 + xm), c1 = (float)__ldg(r2 + x), c2 = (float)__ldg(r2 + xp);
-        // Dx: row pass (p[x+1] - p[x-1]) * s, column pass [1 2 1];  Dy: row pass [1 2 1], column pass (below - above) * s
-        const float rx0 = __fmul_rn(__fadd_rn(a2, -a0), s), rx1 = __fmul_rn(__fadd_rn(b2, -b0), s), rx2 = __fmul_rn(__fadd_rn(c2, -c0), s);
-        const float dx = __fadd_rn(__fadd_rn(rx0, __fmul_rn(rx1, 2.f)), rx2);
-        const float sx0 = __fadd_rn(__fadd_rn(a0, __fmul_rn(a1, 2.f)), a2), sx2 = __fadd_rn(__fadd_rn(c0, __fmul_rn(c1, 2.f)), c2);
-        const float dy = __fmul_rn(__fadd_rn(sx2, -sx0), s);
-        cxx[ly][lx] = __fmul_rn(dx, dx);
-        cxy[ly][lx] = __fmul_rn(dx, dy);
-        cyy[ly][lx] = __fmul_rn(dy, dy);
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) block_max = 0u;
     __syncthreads();
-    const int x = x0 + tx, y = y0 + ty;
-    if (x < cols && y < rows) {
-        auto box = [&](const float(&c)[kTH + 2][kTW + 2]) {   // rows first, then the three row sums
-            float r[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) r[j] = __fadd_rn(__fadd_rn(c[ty + j][tx], c[ty + j][tx + 1]), c[ty + j][tx + 2]);
-            return __fadd_rn(__fadd_rn(r[0], r[1]), r[2]);
+    const int strip = blockIdx.x * kEigWarps + warp;
+    const int c = strip * kEigStripW - 1 + lane;                       // this lane's column (may lie outside the image)
+    const int y0 = blockIdx.y * kEigChunkRows, y1 = min(y0 + kEigChunkRows, rows);
+    unsigned my_max = 0u;
+    if (strip * kEigStripW < cols && y0 < rows) {                       // (uniform per warp)
+        const float s = 1.0f / 3060.0f;
+        const int cc = min(max(c, 0), cols - 1);                        // halo lanes outside the image: any valid column
+        const int cl = reflect101(cc - 1, cols), cr = reflect101(cc + 1, cols);
+        const bool first_col = (c == 0), last_col = (c == cols - 1);
+        const bool writes = lane >= 1 && lane <= kEigStripW && c >= 0 && c < cols;
+        const int ya = max(y0 - 1, 0), yb = min(y1, rows - 1);          // product rows this chunk needs
+        float rx_a = 0.f, rx_b = 0.f, sx_a = 0.f, sx_b = 0.f;           // 1-D passes of pixel rows q-2, q-1
+        float h2[3] = {0.f, 0.f, 0.f}, h1[3] = {0.f, 0.f, 0.f};         // horizontal 3-sums of product rows y-2, y-1
+        auto emit = [&](int yo, const float (&top)[3], const float (&mid)[3], const float (&bot)[3]) {
+            const float bxx = __fadd_rn(__fadd_rn(top[0], mid[0]), bot[0]);
+            const float bxy = __fadd_rn(__fadd_rn(top[1], mid[1]), bot[1]);
+            const float byy = __fadd_rn(__fadd_rn(top[2], mid[2]), bot[2]);
+            const float a = __fmul_rn(bxx, 0.5f), b = bxy, cq = __fmul_rn(byy, 0.5f);
+            const float amc = __fadd_rn(a, -cq);
+            const float e = __fadd_rn(__fadd_rn(a, cq), -__fsqrt_rn(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
+            if (writes) {
+                eig[(size_t)yo * cols + c] = e;
+                if (!mask || mask[(size_t)yo * mask_pitch + c]) my_max = max(my_max, float_key(e));
+            }
         };
-        const float a = __fmul_rn(box(cxx), 0.5f), b = box(cxy), c = __fmul_rn(box(cyy), 0.5f);
-        const float amc = __fadd_rn(a, -c);
-        const float e = __fadd_rn(__fadd_rn(a, c), -__fsqrt_rn(__fadd_rn(__fmul_rn(amc, amc), __fmul_rn(b, b))));
-        eig[(size_t)y * cols + x] = e;
-        if (!mask || mask[(size_t)y * mask_pitch + x]) my_max = max(my_max, float_key(e));
-    }
-    __syncthreads();   // (the product tiles are rewritten by the next trip)
+        for (int q = ya - 1; q <= yb + 1; ++q) {
+            const uint8_t *r = img + (size_t)reflect101(q, rows) * pitch;
+            const float pl = (float)__ldg(r + cl), pc = (float)__ldg(r + cc), pr = (float)__ldg(r + cr);
+            // row passes of pixel row q: Dx (p[x+1] - p[x-1]) * s;  Dy [1 2 1]
+            const float rx_c = __fmul_rn(__fadd_rn(pr, -pl), s);
+            const float sx_c = __fadd_rn(__fadd_rn(pl, __fmul_rn(pc, 2.f)), pr);
+            if (q >= ya + 1) {
+                const int y = q - 1;                                     // the product row completed by pixel row q
+                // column passes: Dx [1 2 1] over rows y-1, y, y+1;  Dy (below - above) * s
+                const float dx = __fadd_rn(__fadd_rn(rx_a, __fmul_rn(rx_b, 2.f)), rx_c);
+                const float dy = __fmul_rn(__fadd_rn(sx_c, -sx_a), s);
+                const float p[3] = {__fmul_rn(dx, dx), __fmul_rn(dx, dy), __fmul_rn(dy, dy)};
+                float h0[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {                            // (left + centre) + right; mirror at the image's sides
+                    const float up = __shfl_up_sync(0xffffffffu, p[k], 1), dn = __shfl_down_sync(0xffffffffu, p[k], 1);
+                    const float left = first_col ? dn : up, right = last_col ? up : dn;
+                    h0[k] = __fadd_rn(__fadd_rn(left, p[k]), right);
+                }
+                if (y >= 1 && y - 1 >= y0) {                             // output row y - 1: rows y-2 (row 1 for row 0), y-1, y
+                    if (y - 1 == 0) emit(0, h0, h1, h0);
+                    else emit(y - 1, h2, h1, h0);
+                }
+                if (y == rows - 1 && y < y1) emit(y, h1, h0, h1);        // the image's last row: row rows := row rows-2
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    h2[k] = h1[k];
+                    h1[k] = h0[k];
+                }
+            }
+            rx_a = rx_b;
+            rx_b = rx_c;
+            sx_a = sx_b;
+            sx_b = sx_c;
+        }
     }
     my_max = __reduce_max_sync(0xffffffffu, my_max);   // one shared-memory atomic per warp, one global one per block
-    if ((tid & 31) == 0 && my_max) atomicMax(&block_max, my_max);
+    if (lane == 0 && my_max) atomicMax(&block_max, my_max);
     __syncthreads();
-    if (tid == 0 && block_max) atomicMax(max_key, block_max);
+    if (threadIdx.x == 0 && block_max) atomicMax(max_key, block_max);
 }
 
 // Mask of DetectFeatures (src/frontend_g2o.cpp:280-284): 255, then 0 in pt +- (h, h) for every listed point, both corners
@@ -390,6 +414,11 @@ gftt_select_batched_kernel(const unsigned long long *__restrict__ keys_all, size
     if (tid == 0) n_out[b] = accepted;
 }
 
+static dim3 eig_grid(int cols, int rows, int images) {
+    const int strips = (cols + kEigStripW - 1) / kEigStripW;
+    return dim3((strips + kEigWarps - 1) / kEigWarps, (rows + kEigChunkRows - 1) / kEigChunkRows, images);
+}
+
 }  // namespace
 
 // ---- batched entry ------------------------------------------------------------------------------------------------
@@ -454,7 +483,7 @@ cudaError_t launch_gftt_batched(const uint8_t *d_imgs, size_t img_stride, int pi
                 d_exclude_counts ? d_exclude_counts + b0 : nullptr, exclude_half);
             note_launch();
         }
-        gftt_eig_kernel<<<dim3((cols + kTW - 1) / kTW, (rows + kTH * kEigTilesY - 1) / (kTH * kEigTilesY), nb), dim3(kTW, kTH), 0, stream>>>(
+        gftt_eig_kernel<<<eig_grid(cols, rows, nb), 32 * kEigWarps, 0, stream>>>(
             d_imgs + (size_t)b0 * img_stride, cols, rows, pitch, masked ? mask : nullptr, cols, eig, max_keys, img_stride);
         note_launch();
         gftt_candidates_batched_kernel<<<dim3((cols + 31) / 32, (rows + 8 * kEigTilesY - 1) / (8 * kEigTilesY), nb), 256, 0, stream>>>(
@@ -527,8 +556,7 @@ cudaError_t launch_gftt(const uint8_t *d_img, int cols, int rows, int pitch, con
         }
         mask_used = mask;
     }
-    dim3 grid((cols + kTW - 1) / kTW, (rows + kTH * kEigTilesY - 1) / (kTH * kEigTilesY));
-    gftt_eig_kernel<<<grid, dim3(kTW, kTH), 0, stream>>>(d_img, cols, rows, pitch, mask_used, cols, eig, scalars, 0);
+    gftt_eig_kernel<<<eig_grid(cols, rows, 1), 32 * kEigWarps, 0, stream>>>(d_img, cols, rows, pitch, mask_used, cols, eig, scalars, 0);
     note_launch();
     gftt_candidates_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), 256, 0, stream>>>(eig, cols, rows, mask_used, cols, scalars,
                                                                                       quality, keys, scalars + 1);
