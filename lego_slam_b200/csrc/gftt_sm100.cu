@@ -294,38 +294,68 @@ __global__ void gftt_exclusion_batched_kernel(uint8_t *__restrict__ mask, int co
     for (int k = threadIdx.x; k < w * h; k += blockDim.x) m[(size_t)(y1 + k / w) * cols + x1 + k % w] = 0;
 }
 
-__global__ void __launch_bounds__(256)
+// Threshold + 3x3 non-maximum suppression of a batch, streaming down rows like gftt_eig_kernel (a warp per 30-column
+// strip; the thresholded scores of three rows in registers, neighbours by shuffle).  Candidate keys are collected in a
+// per-warp buffer in shared memory and appended to the image's segment with ONE atomic per flush (the tile version's
+// atomic per 32 x 8 tile: 469,000 per 256 images; an atomic per warp and row: 3.7 million -- 2.0 ms).
+constexpr int kCandBuf = 128;   // keys per warp buffer; flushed when a row could overflow it
+
+__global__ void __launch_bounds__(32 * kEigWarps)
 gftt_candidates_batched_kernel(const float *__restrict__ eig_all, int cols, int rows, const uint8_t *__restrict__ mask_all,
-                               const unsigned *__restrict__ max_keys, double quality, unsigned long long *__restrict__ keys,
+                               const unsigned *__restrict__ max_keys, double quality, unsigned long long *__restrict__ keys_all,
                                unsigned *__restrict__ per_image) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), b = blockIdx.z;
+    __shared__ unsigned long long buf[kEigWarps][kCandBuf];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.z;
     const size_t px = (size_t)cols * rows;
     const float *eig = eig_all + (size_t)b * px;
     const uint8_t *mask = mask_all ? mask_all + (size_t)b * px : nullptr;
+    unsigned long long *keys = keys_all + (size_t)b * px;
+    const int strip = blockIdx.x * kEigWarps + warp;
+    const int c = strip * kEigStripW - 1 + lane;
+    const int y0 = blockIdx.y * kEigChunkRows, y1 = min(y0 + kEigChunkRows, rows);
+    if (strip * kEigStripW >= cols || y0 >= rows) return;   // (uniform per warp; no block barrier below)
+    // cv::threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO) on a CV_32F image compares with (float)thresh
     const float thr = (float)((double)key_float(max_keys[b]) * quality);
-    __shared__ unsigned s_count, s_base;
-    for (int k = 0; k < kEigTilesY; ++k) {   // several tiles per block, as in gftt_eig_kernel
-        const int tile_y = blockIdx.y * kEigTilesY + k, y = tile_y * 8 + (threadIdx.x >> 5);
-        if (tile_y * 8 >= rows) break;
-        bool cand = false;
-        const float v = nms_candidate(eig, cols, rows, mask, cols, thr, tile_y, cand);
-        // one global atomic per tile, on the image's own counter
-        if (threadIdx.x == 0) s_count = 0;
-        __syncthreads();
-        const unsigned ballot = __ballot_sync(0xffffffffu, cand);
-        const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
-        unsigned off = 0;
-        if (ballot) {
-            if (lane == leader) off = atomicAdd(&s_count, (unsigned)__popc(ballot));
-            off = __shfl_sync(0xffffffffu, off, leader) + __popc(ballot & ((1u << lane) - 1u));
+    const bool in_cols = c >= 0 && c < cols;
+    // a candidate is an interior pixel of the image (all eight neighbours exist) in an output lane
+    const bool may = lane >= 1 && lane <= kEigStripW && c >= 1 && c < cols - 1;
+    int n_buf = 0;
+    auto flush = [&]() {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(per_image + b, (unsigned)n_buf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < n_buf; i += 32) keys[base + i] = buf[warp][i];
+        __syncwarp();
+        n_buf = 0;
+    };
+    // row maxima over (left, centre, right) of the thresholded scores of rows y-1, y and the centre value of row y
+    float m_a = 0.f, m_b = 0.f, v_b = 0.f;
+    for (int q = max(y0 - 1, 0); q <= min(y1, rows - 1); ++q) {
+        float v = 0.f;
+        if (in_cols) {
+            v = eig[(size_t)q * cols + c];
+            v = v > thr ? v : 0.f;
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && s_count) s_base = atomicAdd(per_image + b, s_count);
-        __syncthreads();
-        if (cand)   // (a segment holds one key per pixel: it cannot overflow)
-            keys[(size_t)b * px + s_base + off] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * cols + x);
-        __syncthreads();   // (s_base is rewritten by the next trip)
+        const float up = __shfl_up_sync(0xffffffffu, v, 1), dn = __shfl_down_sync(0xffffffffu, v, 1);
+        const float m_c = fmaxf(fmaxf(up, v), dn);
+        const int y = q - 1;                                   // the row completed by row q
+        if (y >= y0 && y >= 1 && y < rows - 1) {               // (y < y1 holds: q <= y1)
+            const bool cand = may && v_b != 0.f && (!mask || mask[(size_t)y * cols + c]) && v_b == fmaxf(fmaxf(m_a, m_b), m_c);
+            const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+            if (ballot) {
+                if (n_buf + 32 > kCandBuf) flush();
+                if (cand)
+                    buf[warp][n_buf + __popc(ballot & ((1u << lane) - 1u))] =
+                        ((unsigned long long)__float_as_uint(v_b) << 32) | (unsigned)(y * cols + c);
+                n_buf += __popc(ballot);
+                __syncwarp();
+            }
+        }
+        m_a = m_b;
+        m_b = m_c;
+        v_b = v;
     }
+    if (n_buf) flush();
 }
 
 // segment b of the key array: [b * px, b * px + per_image[b])
@@ -486,7 +516,7 @@ cudaError_t launch_gftt_batched(const uint8_t *d_imgs, size_t img_stride, int pi
         gftt_eig_kernel<<<eig_grid(cols, rows, nb), 32 * kEigWarps, 0, stream>>>(
             d_imgs + (size_t)b0 * img_stride, cols, rows, pitch, masked ? mask : nullptr, cols, eig, max_keys, img_stride);
         note_launch();
-        gftt_candidates_batched_kernel<<<dim3((cols + 31) / 32, (rows + 8 * kEigTilesY - 1) / (8 * kEigTilesY), nb), 256, 0, stream>>>(
+        gftt_candidates_batched_kernel<<<eig_grid(cols, rows, nb), 32 * kEigWarps, 0, stream>>>(
             eig, cols, rows, masked ? mask : nullptr, max_keys, quality, keys, per_image);
         note_launch();
         gftt_segment_offsets_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(per_image, nb, (int)px, seg_begin, seg_end);
