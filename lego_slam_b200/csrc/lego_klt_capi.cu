@@ -1638,7 +1638,8 @@ int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_sourc
     if (rc) return rc;
     // images per pass through the workspace (~25 bytes per pixel and image): as many as ~4 GB hold, at most 256
     const size_t fit = ((size_t)4 << 30) / ((size_t)b->cols * (size_t)b->rows * 25);
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)b->B, 256), fit));
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)b->B, 256), fit));
+    if (const char *c = getenv("LEGO_KLT_DETECT_CHUNK")) chunk = std::max(1, std::min(chunk, atoi(c)));   // (test hook: several passes)
     if (!gftt_batched_supported(b->cols, b->rows, chunk))
         return fail(LEGO_KLT_ERR_UNSUPPORTED, "batched detection: image too large");
     CU_TRY(cudaSetDevice(b->ctx->device));

@@ -166,6 +166,45 @@ def test_gpu_batched_detection_equals_the_single_image_calls(tracker, n, md, exc
 
 
 @pytest.mark.gpu
+def test_gpu_batched_detection_in_several_workspace_passes_and_on_1080p(tracker, monkeypatch):
+    """More images than one pass through the workspace holds (LEGO_KLT_DETECT_CHUNK = 5 of 13), and a 1920x1080 image
+    (strips and row chunks that do not divide the image) against the numpy oracle."""
+    import lego_slam_b200 as klt
+    B, rows, cols = 13, 97, 131
+    rng = np.random.default_rng(4)
+    imgs = klt.pinned_empty((B, rows, cols), np.uint8)
+    src = _images()[2]
+    for b in range(B):
+        imgs[b] = np.roll(src, (int(rng.integers(0, rows)), int(rng.integers(0, cols))), axis=(0, 1))
+    kp = klt.pinned_empty((B, 4, 2), np.float32)
+    kp[:] = 5
+    batch = tracker.batch(B, rows, cols, 4, levels=2)
+    batch.upload(imgs, imgs, kp, kp)
+    monkeypatch.setenv("LEGO_KLT_DETECT_CHUNK", "5")
+    pts, cnt, sc = batch.detect_features(1, 40, 0.01, 7.0)
+    monkeypatch.delenv("LEGO_KLT_DETECT_CHUNK")
+    for b in range(B):
+        ref, rsc = g.good_features_to_track(np.ascontiguousarray(imgs[b]), 40, 0.01, 7.0)
+        assert cnt[b] == ref.shape[0] and np.array_equal(pts[b, :cnt[b]], ref)
+        assert np.array_equal(sc[b, :cnt[b]].view(np.uint32), rsc.view(np.uint32))
+    batch.close()
+    big, _, _ = synth.stereo_pair(1080, 1920, 3)
+    pts, sc = tracker.detect_features(big, 500, 0.01, 15.0)
+    e_gpu = tracker.debug_read_eig(1080, 1920)
+    e, _ = g.corner_min_eigen_val(big)
+    assert np.array_equal(e_gpu.view(np.uint32), e.view(np.uint32))
+    ref, rsc = g.good_features_to_track(big, 500, 0.01, 15.0)
+    assert np.array_equal(pts, ref) and np.array_equal(sc.view(np.uint32), rsc.view(np.uint32))
+    one = tracker.batch(1, 1080, 1920, 4, levels=2)
+    k1 = klt.pinned_empty((1, 4, 2), np.float32)
+    k1[:] = 9
+    one.upload(big[None], big[None], k1, k1)
+    bp, bc, _ = one.detect_features(0, 500, 0.01, 15.0)
+    assert bc[0] == ref.shape[0] and np.array_equal(bp[0, :bc[0]], ref)
+    one.close()
+
+
+@pytest.mark.gpu
 def test_gpu_detect_track_triangulate_chain_stays_on_the_device(tracker, oracle):
     """lego_klt_batch_detect_features -> lego_klt_batch_use_detected_features -> lego_klt_batch_run: the detected
     corners become the source keypoints where they lie in HBM.  Same bytes as fetching the corners, uploading them as
