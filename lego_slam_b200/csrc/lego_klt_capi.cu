@@ -812,6 +812,7 @@ int lego_klt_batch_upload(lego_klt_batch *b, const uint8_t *imgs1, const uint8_t
     b->uploaded = true;
     b->pyramids_valid = false;
     b->last_chunked = false;
+    b->detect_max = 0;   // (corners of the previous images are not handed over to the new ones)
     return LEGO_KLT_OK;
 }
 
@@ -911,6 +912,7 @@ int lego_klt_track_batched_begin(lego_klt_batch *b, const lego_klt_params *param
                                  const uint8_t *imgs2, const float *kp1_xy, float *kp2_xy, uint8_t *success) {
     if (!b) return fail(LEGO_KLT_ERR_BAD_ARG, "batch is null");
     if (b->in_flight) return fail(LEGO_KLT_ERR_STATE, "lego_klt_track_batched_begin: the previous call has not been ended");
+    b->detect_max = 0;
     // Small batches: plain upload -> run -> download.
     // Equal chunks: more / smaller chunks shorten the pipeline tail but cost launches and solver efficiency
     // (measured: 10 chunks with a fine tail 6 % slower than 8 equal ones; a smaller LAST chunk of 8 or 16 pairs 5 % slower).
@@ -1636,6 +1638,7 @@ int lego_klt_batch_detect_features(lego_klt_batch *b, int set, int exclude_sourc
     const GfttArgs g{nullptr, 0, nullptr, 0, exclude_half, max_corners, quality_level, min_distance};
     int rc = gftt_check(g, corners_xy, n_corners);
     if (rc) return rc;
+    b->detect_max = 0;   // (no detection to hand over until this one has completed)
     // images per pass through the workspace (~25 bytes per pixel and image): as many as ~4 GB hold, at most 256
     const size_t fit = ((size_t)4 << 30) / ((size_t)b->cols * (size_t)b->rows * 25);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)b->B, 256), fit));
