@@ -403,6 +403,26 @@ def test_edge_cases(tracker, oracle, kernel):
     assert s.all() and int(st.n_nan) == 0 and np.array_equal(o, kp + np.float32(0.25))
 
 
+@pytest.mark.parametrize("kernel", [klt.KERNEL_EXACT, klt.KERNEL_WARP, klt.KERNEL_PATCH])
+def test_iteration_limits_and_odd_patch_shapes(tracker, oracle, kernel):
+    """max_iters 0 / 1 / 3 (the level keeps its guess, one pass, the cap cuts the solve short), a looser and a zero eps,
+    1x1, 2x2 (asymmetric), 13x13 patches (six warps of the PATCH kernel), both modes -- kernels that take any
+    configuration, against the oracle incl. the pass counts."""
+    rows, cols, n = 120, 200, 90
+    L, R, kp1, kp2, _ = synth.stereo_case(rows, cols, n, seed=77, min_dist=6, guess="noisy")
+    for kw in (dict(max_iters=0), dict(max_iters=1), dict(max_iters=3, inverse=True), dict(eps=0.5), dict(eps=0.0, max_iters=4),
+               dict(patch_lo=0, patch_hi=0), dict(patch_lo=-1, patch_hi=0, inverse=True), dict(patch_lo=-6, patch_hi=6),
+               dict(patch_lo=-6, patch_hi=6, inverse=True, levels=2), dict(levels=1, has_initial=False)):
+        kw = dict(dict(levels=3), **kw)
+        ref, rs, rst = oracle.track(L, R, kp1, kp2, oracle.make_params(**kw))
+        o, s, st = tracker.track(L, R, kp1, kp2, klt.make_params(kernel=kernel, **kw))
+        if kernel == klt.KERNEL_EXACT:
+            assert np.array_equal(o.view(np.uint32), ref.view(np.uint32)) and np.array_equal(s, rs), kw
+        else:
+            assert_parity(o, s, ref, rs, cols, rows, f"{kw} kernel={kernel}")
+        assert _iters(st, kw["levels"]) == _iters(rst, kw["levels"]), kw
+
+
 @pytest.mark.parametrize("lo,hi", [(-3, 3), (-4, 3), (-5, 5)])
 def test_subpixel_keypoints_and_deferred_features(tracker, oracle, lo, hi):
     """Tracked (sub-pixel) source points, as Frontend::TrackLastFrame feeds them: float(kx+c) is sometimes
