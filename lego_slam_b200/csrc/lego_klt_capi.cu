@@ -359,7 +359,6 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
     const PyramidView &view = view_override ? *view_override : b->view;   // cached pyramids of image handles
     const WarpKernelMaps *maps = maps_override ? maps_override : b->maps;
     int *work = b->d_work + 4 * chunk;
-    CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
     if (ring) CU_TRY(cudaEventRecord(ring[0], st));
     if (!view_override) {
         NvtxRange r("lego_klt K1 pyramid");
@@ -431,6 +430,8 @@ int run_range(lego_klt_batch *b, const lego_klt_params *params, int img0, int ni
         return fail(LEGO_KLT_ERR_UNSUPPORTED,
                     "LANE kernel: forward mode with the 7x7 (-3..3), 8x8 (-4..3) or 11x11 (-5..5) patch, or inverse mode "
                     "with the 7x7 patch");
+    // the device work counters (feature queue, deferred / family lists) of the warp and lane kernels
+    if (kernel == LEGO_KLT_KERNEL_WARP || kernel == LEGO_KLT_KERNEL_LANE) CU_TRY(cudaMemsetAsync(work, 0, 4 * sizeof(int), st));
     if (kernel == LEGO_KLT_KERNEL_EXACT) {
         CU_TRY(launch_klt_exact(view, a, st));
     } else if (kernel == LEGO_KLT_KERNEL_PATCH) {
