@@ -107,6 +107,42 @@ __global__ void probe(float *out, float seed, unsigned long long *cycles) {
                          "fma.rn.f64 %1, %1, %9, %1; mul.rn.f32x2 %4, %4, %10; prmt.b32 %7, %7, %11, 0x7441;"
                          "fma.rn.f64 %2, %2, %9, %2; mul.rn.f32x2 %5, %5, %10; prmt.b32 %8, %8, %11, 0x7442;"
                          : "+d"(d0), "+d"(d1), "+d"(d2), "+l"(p0), "+l"(p1), "+l"(p2), "+r"(u0), "+r"(u1), "+r"(u2) : "d"(0.999), "l"(w), "r"(0x4B000000u));
+        } else if (MIX == 19) {  // 8 x cvt.rn.f32.u8 of a byte of a changing word (I2F.U8 Rx, Ry.Bk on the XU pipe), xor-folded
+            float c0, c1, c2, c3, c4, c5, c6, c7;
+            c0 = __uint2float_rn(u0 & 0xffu); c1 = __uint2float_rn((u0 >> 8) & 0xffu); c2 = __uint2float_rn((u0 >> 16) & 0xffu); c3 = __uint2float_rn(u0 >> 24);
+            c4 = __uint2float_rn(u1 & 0xffu); c5 = __uint2float_rn((u1 >> 8) & 0xffu); c6 = __uint2float_rn((u1 >> 16) & 0xffu); c7 = __uint2float_rn(u1 >> 24);
+            u2 ^= __float_as_uint(c0) ^ __float_as_uint(c1) ^ __float_as_uint(c2) ^ __float_as_uint(c3);
+            u3 ^= __float_as_uint(c4) ^ __float_as_uint(c5) ^ __float_as_uint(c6) ^ __float_as_uint(c7);
+            u0 += 0x01010101u; u1 += 0x03050709u;
+        } else if (MIX == 20) {  // the same 8 conversions + 8 mul.f32x2: do the conversions hide behind the FMA pipe?
+            float c0, c1, c2, c3, c4, c5, c6, c7;
+            c0 = __uint2float_rn(u0 & 0xffu); c1 = __uint2float_rn((u0 >> 8) & 0xffu); c2 = __uint2float_rn((u0 >> 16) & 0xffu); c3 = __uint2float_rn(u0 >> 24);
+            c4 = __uint2float_rn(u1 & 0xffu); c5 = __uint2float_rn((u1 >> 8) & 0xffu); c6 = __uint2float_rn((u1 >> 16) & 0xffu); c7 = __uint2float_rn(u1 >> 24);
+            u2 ^= __float_as_uint(c0) ^ __float_as_uint(c1) ^ __float_as_uint(c2) ^ __float_as_uint(c3);
+            u3 ^= __float_as_uint(c4) ^ __float_as_uint(c5) ^ __float_as_uint(c6) ^ __float_as_uint(c7);
+            u0 += 0x01010101u; u1 += 0x03050709u;
+            asm volatile("mul.rn.f32x2 %0, %0, %8; mul.rn.f32x2 %1, %1, %8; mul.rn.f32x2 %2, %2, %8; mul.rn.f32x2 %3, %3, %8;"
+                         "mul.rn.f32x2 %4, %4, %8; mul.rn.f32x2 %5, %5, %8; mul.rn.f32x2 %6, %6, %8; mul.rn.f32x2 %7, %7, %8;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(w));
+        } else if (MIX == 21) {  // what the solver does today for 8 pixels: 8 prmt + 4 add.f32x2 (+ the same 8 mul.f32x2)
+            unsigned q0, q1, q2, q3, q4, q5, q6, q7;
+            asm volatile("prmt.b32 %0, %8, %10, 0x7440; prmt.b32 %1, %8, %10, 0x7441; prmt.b32 %2, %8, %10, 0x7442; prmt.b32 %3, %8, %10, 0x7443;"
+                         "prmt.b32 %4, %9, %10, 0x7440; prmt.b32 %5, %9, %10, 0x7441; prmt.b32 %6, %9, %10, 0x7442; prmt.b32 %7, %9, %10, 0x7443;"
+                         : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3), "=r"(q4), "=r"(q5), "=r"(q6), "=r"(q7) : "r"(u0), "r"(u1), "r"(0x4B000000u));
+            unsigned long long g0, g1, g2, g3, m;
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(g0) : "r"(q0), "r"(q1));
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(g1) : "r"(q2), "r"(q3));
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(g2) : "r"(q4), "r"(q5));
+            asm volatile("mov.b64 %0, {%1, %2};" : "=l"(g3) : "r"(q6), "r"(q7));
+            asm volatile("mov.b64 %0, {%1, %1};" : "=l"(m) : "f"(-8388608.0f));
+            asm volatile("add.rn.f32x2 %0, %0, %4; add.rn.f32x2 %1, %1, %4; add.rn.f32x2 %2, %2, %4; add.rn.f32x2 %3, %3, %4;"
+                         : "+l"(g0), "+l"(g1), "+l"(g2), "+l"(g3) : "l"(m));
+            p4 ^= g0 ^ g1; p5 ^= g2 ^ g3;
+            u0 += 0x01010101u; u1 += 0x03050709u;
+            asm volatile("mul.rn.f32x2 %0, %0, %4; mul.rn.f32x2 %1, %1, %4; mul.rn.f32x2 %2, %2, %4; mul.rn.f32x2 %3, %3, %4;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3) : "l"(w));
+            asm volatile("mul.rn.f32x2 %0, %0, %4; mul.rn.f32x2 %1, %1, %4; mul.rn.f32x2 %2, %2, %4; mul.rn.f32x2 %3, %3, %4;"
+                         : "+l"(p6), "+l"(p7), "+l"(p0), "+l"(p1) : "l"(w));
         } else if (MIX == 11) {  // 8 x scalar mul.f32 with three distinct registers
             asm volatile("mul.rn.f32 %0, %1, %8; mul.rn.f32 %1, %2, %8; mul.rn.f32 %2, %3, %8; mul.rn.f32 %3, %4, %8;"
                          "mul.rn.f32 %4, %5, %8; mul.rn.f32 %5, %6, %8; mul.rn.f32 %6, %7, %8; mul.rn.f32 %7, %0, %8;"
@@ -169,6 +205,9 @@ int main() {
     run<16>("two pipes: 4 FMUL2 + 4 PRMT", 8);
     run<17>("two pipes: 4 DFMA + 4 FMUL2", 8);
     run<18>("three pipes: 3 DFMA + 3 FMUL2 + 3 PRMT", 9);
+    run<19>("8 x cvt.f32.u8 of a byte (I2F.U8) [+8 xor +2 add]", 8);
+    run<20>("8 I2F.U8 [+10 int] + 8 FMUL2", 16);
+    run<21>("today: 8 PRMT + 4 FADD2 [+6 xor/add] + 8 FMUL2", 20);
     run<12>("4 x mul.f32 + 4 x add.f32 (scalar, un-fused)", 8);
     run<13>("4 x mul.f32x2 + 4 x add.f32x2 (packed, un-fused)", 8);
     cudaError_t e = cudaDeviceSynchronize();
