@@ -29,7 +29,10 @@ def _iters(st, levels):
 
 # ------------------------------------------------------------------ pyramid (K1): bit exact
 @pytest.mark.parametrize("rows,cols,levels", [(376, 1241, 4), (188, 620, 4), (1080, 1920, 5), (217, 333, 3),
-                                              (95, 157, 4), (64, 64, 5), (9, 11, 2), (376, 1241, 1)])
+                                              (95, 157, 4), (64, 64, 5), (9, 11, 2), (376, 1241, 1),
+                                              # levels 2 and 3 both exact halvings (the fused streaming kernel): level-3
+                                              # width even / odd, a single level-3 row, a padded step below
+                                              (720, 1280, 4), (1080, 1920, 4), (8, 24, 4), (16, 1241, 4), (377, 1243, 4)])
 def test_pyramid_bit_exact(tracker, oracle, rows, cols, levels):
     img = np.random.default_rng(rows * 31 + cols).integers(0, 256, size=(rows, cols), dtype=np.uint8)
     got = tracker.build_pyramid(img, levels)
@@ -49,7 +52,8 @@ def test_pyramid_with_row_step(tracker, oracle):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("rows,cols,levels,pad", [(376, 1241, 4, 0), (270, 481, 5, 0), (120, 333, 3, 67), (97, 203, 1, 0),
-                                                  (1080, 1920, 5, 0)])
+                                                  (1080, 1920, 5, 0), (720, 1280, 4, 0), (376, 1241, 4, 39), (8, 24, 4, 0),
+                                                  (17, 1243, 4, 5)])
 def test_row_aprons_of_every_level(tracker, oracle, rows, cols, levels, pad):
     """The device layout the solver's border path relies on (LevelView): 32 bytes left of column 0 replicate it,
     column `cols` holds the reference's flat-address neighbour data[r*step + cols] (algorithm.h:48,53: first pixel
