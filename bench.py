@@ -795,8 +795,8 @@ def run_ours(args):
             "traffic_template_kernel": prof_of("klt_template_kernel", "dram_bytes"), "peak_source": peak_source,
             "gn_iters_per_level": iters, "share_of_step": ms_sol / (ms_sol + ms_pyr), "executed": executed}),
         "roofline_pyramid": dict(pyramid_roofline(2 * B, PYR_BYTES_PER_IMAGE, ms_pyr), **{
-            "kernel": "pyramid_l01_kernel + pyramid_band_kernel (all levels + row aprons)", "bound": "hbm",
-            "traffic": ((prof_of("pyramid_l01_kernel", "dram_bytes") or 0) + (prof_of("pyramid_band_kernel", "dram_bytes") or 0)) or None,
+            "kernel": "pyramid_l01_kernel + pyramid_x2x2_kernel (all levels + row aprons; the band kernel on other shapes)", "bound": "hbm",
+            "traffic": ((prof_of("pyramid_l01_kernel", "dram_bytes") or 0) + (prof_of("pyramid_x2x2_kernel", "dram_bytes") or prof_of("pyramid_band_kernel", "dram_bytes") or 0)) or None,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}),
         "per_rank": {"resident_ms_per_step": per_rank_resident, "e2e_ms_per_step": per_rank_e2e, "h2d_ceiling_gbs": per_rank_h2d},
         "triangulation": {"what": "lego_klt_batch_triangulate on the tracked batch (keypoints in HBM, world points to "
